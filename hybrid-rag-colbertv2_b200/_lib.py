@@ -1,0 +1,214 @@
+"""ctypes binding of libhrc.so (C ABI declared in include/hrc.h).
+
+There is deliberately NO fallback: if the shared library is missing, or the device is not a CUDA
+sm_100 GPU, every operation raises.  PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhrc.so")
+
+PATH_AUTO, PATH_SIMT, PATH_TC = 0, 1, 2
+DIM = 128
+MAX_TOPK = 2048
+TC_MAX_LQ = 32
+
+#: every symbol include/hrc.h declares: name -> (restype, argtypes)
+_c = ctypes
+SYMBOLS = {
+    "hrc_version": (_c.c_int, []),
+    "hrc_last_error": (_c.c_char_p, []),
+    "hrc_launch_count": (_c.c_uint64, []),
+    "hrc_maxsim_scores": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int,
+                                     _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p]),
+    "hrc_maxsim_scores_ids": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int,
+                                         _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p]),
+    "hrc_topk_workspace_bytes": (_c.c_size_t, [_c.c_int64, _c.c_int, _c.c_int]),
+    "hrc_topk": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int32, _c.c_void_p,
+                            _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "hrc_topk_merge": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    "hrc_keys_unpack": (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "hrc_rrf_fuse": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "hrc_synth_tokens": (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_int64, _c.c_uint64, _c.c_void_p]),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+class HrcError(RuntimeError):
+    """A libhrc call returned a non-zero status."""
+
+
+def load() -> ctypes.CDLL:
+    """Load libhrc.so (once) and type every exported symbol.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HrcError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU / PyTorch fallback for the MaxSim path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI and the header disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().hrc_last_error().decode("utf-8", "replace")
+        raise HrcError(f"{what} failed (status {rc}): {msg}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise HrcError("libhrc operates on CUDA tensors only (no CPU fallback)")
+        if not t.is_contiguous():
+            raise HrcError("libhrc needs contiguous tensors")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise HrcError(f"tensors on different devices: {dev} vs {t.device}")
+    assert dev is not None
+    return dev
+
+
+def version() -> int:
+    return load().hrc_version()
+
+
+def launch_count() -> int:
+    return int(load().hrc_launch_count())
+
+
+def maxsim_scores(tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.Tensor, *,
+                  path: int = PATH_AUTO, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """scores[q, d] = sum_i max_{t in doc d} <queries[q, i], tokens[t]>  ->  fp32 [n_queries, n_docs]."""
+    dev = _require_cuda(tokens, offsets, queries)
+    assert tokens.dtype == torch.bfloat16 and tokens.dim() == 2 and tokens.shape[1] == DIM
+    assert offsets.dtype == torch.int64 and offsets.dim() == 1 and offsets.numel() >= 1
+    assert queries.dtype == torch.bfloat16 and queries.dim() == 3 and queries.shape[2] == DIM
+    n_docs = offsets.numel() - 1
+    nq, lq = int(queries.shape[0]), int(queries.shape[1])
+    if out is None:
+        out = torch.empty((nq, n_docs), dtype=torch.float32, device=dev)
+    else:
+        assert out.shape == (nq, n_docs) and out.dtype == torch.float32 and out.is_contiguous()
+    with torch.cuda.device(dev):
+        rc = load().hrc_maxsim_scores(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), _ptr(queries),
+                                      nq, lq, _ptr(out), path, _stream(dev))
+    _check(rc, "hrc_maxsim_scores")
+    return out
+
+
+def maxsim_scores_ids(tokens: torch.Tensor, offsets: torch.Tensor, cand_ids: torch.Tensor,
+                      queries: torch.Tensor, *, path: int = PATH_AUTO) -> torch.Tensor:
+    """scores[q, j] = maxsim(queries[q], doc cand_ids[q, j])  ->  fp32 [n_queries, n_cand]."""
+    dev = _require_cuda(tokens, offsets, cand_ids, queries)
+    assert cand_ids.dtype == torch.int32 and cand_ids.dim() == 2 and cand_ids.shape[0] == queries.shape[0]
+    assert tokens.dtype == torch.bfloat16 and queries.dtype == torch.bfloat16 and offsets.dtype == torch.int64
+    n_docs = offsets.numel() - 1
+    nq, lq = int(queries.shape[0]), int(queries.shape[1])
+    n_cand = int(cand_ids.shape[1])
+    out = torch.empty((nq, n_cand), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = load().hrc_maxsim_scores_ids(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), _ptr(cand_ids),
+                                          n_cand, _ptr(queries), nq, lq, _ptr(out), path, _stream(dev))
+    _check(rc, "hrc_maxsim_scores_ids")
+    return out
+
+
+def topk_workspace_bytes(n: int, n_rows: int, k: int) -> int:
+    return int(load().hrc_topk_workspace_bytes(n, n_rows, k))
+
+
+def topk(scores: torch.Tensor, k: int, *, ids: Optional[torch.Tensor] = None, id_base: int = 0,
+         workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-row top-k keys (int64 view of the uint64 keys), sorted best first.  [n_rows, k]."""
+    dev = _require_cuda(scores, ids)
+    assert scores.dtype == torch.float32 and scores.dim() == 2
+    n_rows, n = int(scores.shape[0]), int(scores.shape[1])
+    if ids is not None:
+        assert ids.dtype == torch.int32 and ids.shape == scores.shape
+    need = topk_workspace_bytes(n, n_rows, k)
+    if need and (workspace is None or workspace.numel() * workspace.element_size() < need):
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    keys = torch.empty((n_rows, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = load().hrc_topk(_ptr(scores), _ptr(ids), n, n_rows, k, id_base, _ptr(keys), _ptr(workspace),
+                             0 if workspace is None else workspace.numel() * workspace.element_size(),
+                             _stream(dev))
+    _check(rc, "hrc_topk")
+    return keys
+
+
+def topk_merge(keys_in: torch.Tensor, k: int) -> torch.Tensor:
+    """Per-row top-k of candidate keys [n_rows, n_in] -> sorted keys [n_rows, k]."""
+    dev = _require_cuda(keys_in)
+    assert keys_in.dtype == torch.int64 and keys_in.dim() == 2
+    n_rows, n_in = int(keys_in.shape[0]), int(keys_in.shape[1])
+    out = torch.empty((n_rows, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = load().hrc_topk_merge(_ptr(keys_in), n_in, n_rows, k, _ptr(out), _stream(dev))
+    _check(rc, "hrc_topk_merge")
+    return out
+
+
+def keys_unpack(keys: torch.Tensor):
+    """keys (int64 view) -> (ids int32, scores fp32), same shape; empty slots give (-1, -inf)."""
+    dev = _require_cuda(keys)
+    assert keys.dtype == torch.int64
+    ids = torch.empty(keys.shape, dtype=torch.int32, device=dev)
+    scores = torch.empty(keys.shape, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = load().hrc_keys_unpack(_ptr(keys), keys.numel(), _ptr(ids), _ptr(scores), _stream(dev))
+    _check(rc, "hrc_keys_unpack")
+    return ids, scores
+
+
+def rrf_fuse(ids_a: torch.Tensor, ids_b: torch.Tensor, rrf_k: int, top_n: int):
+    """Row-wise RRF of two ranked id lists (int32 [rows, n]); returns (ids int32, scores fp64, counts int32)."""
+    dev = _require_cuda(ids_a, ids_b)
+    assert ids_a.dtype == torch.int32 and ids_b.dtype == torch.int32 and ids_a.dim() == 2 and ids_b.dim() == 2
+    assert ids_a.shape[0] == ids_b.shape[0]
+    rows = int(ids_a.shape[0])
+    ids = torch.empty((rows, top_n), dtype=torch.int32, device=dev)
+    scores = torch.empty((rows, top_n), dtype=torch.float64, device=dev)
+    counts = torch.empty((rows,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = load().hrc_rrf_fuse(_ptr(ids_a), int(ids_a.shape[1]), _ptr(ids_b), int(ids_b.shape[1]), rows, rrf_k,
+                                 top_n, _ptr(ids), _ptr(scores), _ptr(counts), _stream(dev))
+    _check(rc, "hrc_rrf_fuse")
+    return ids, scores, counts
+
+
+def synth_tokens(out: torch.Tensor, token_begin: int, seed: int) -> torch.Tensor:
+    """Fill `out` (bf16 [n, 128]) with the deterministic synthetic rows token_begin .. token_begin+n."""
+    dev = _require_cuda(out)
+    assert out.dtype == torch.bfloat16 and out.dim() == 2 and out.shape[1] == DIM
+    with torch.cuda.device(dev):
+        rc = load().hrc_synth_tokens(_ptr(out), token_begin, int(out.shape[0]), seed & (2**64 - 1), _stream(dev))
+    _check(rc, "hrc_synth_tokens")
+    return out

@@ -1,0 +1,135 @@
+// capi.cu — the extern "C" surface of libhrc.so (declared in include/hrc.h).
+// Argument validation, path selection and error reporting live here; kernels live in
+// maxsim_tc.cu / maxsim_simt.cu / topk.cu / rrf.cu / synth.cu.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "hrc_common.cuh"
+
+namespace hrc {
+
+static thread_local char g_error[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(uint64_t(n), std::memory_order_relaxed); }
+
+int launch_maxsim_simt(const void*, const int64_t*, int64_t, const int32_t*, int64_t, const void*, int, int, float*,
+                       cudaStream_t);
+int launch_maxsim_tc(const void*, const int64_t*, int64_t, int64_t, const int32_t*, int64_t, const void*, int, int,
+                     float*, cudaStream_t);
+size_t topk_workspace_bytes(int64_t, int, int);
+int launch_topk(const float*, const int32_t*, int64_t, int, int, int32_t, uint64_t*, void*, size_t, cudaStream_t);
+int launch_topk_merge(const uint64_t*, int, int, int, uint64_t*, cudaStream_t);
+int launch_keys_unpack(const uint64_t*, int64_t, int32_t*, float*, cudaStream_t);
+int launch_rrf(const int32_t*, int, const int32_t*, int, int, int, int, int32_t*, double*, int32_t*, cudaStream_t);
+int launch_synth(void*, int64_t, int64_t, uint64_t, cudaStream_t);
+
+static int check_device() {
+  static int ok = -1;
+  if (ok >= 0) return ok ? 0 : 3;
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    set_error("no CUDA device available (libhrc has no CPU fallback)");
+    return 3;
+  }
+  if (prop.major != 10) {
+    set_error("libhrc is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
+    ok = 0;
+    return 3;
+  }
+  ok = 1;
+  return 0;
+}
+
+static int maxsim_dispatch(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                           const int32_t* d_cand_ids, int64_t n_items, const void* d_queries, int n_queries, int lq,
+                           float* d_scores, int path, cudaStream_t stream) {
+  if (int rc = check_device()) return rc;
+  HRC_REQUIRE(n_docs >= 0 && total_tokens >= 0 && n_queries >= 0 && lq >= 1, "maxsim: negative size or lq < 1");
+  HRC_REQUIRE(n_items == 0 || n_queries == 0 ||
+                  (d_tokens != nullptr && d_offsets != nullptr && d_queries != nullptr && d_scores != nullptr),
+              "maxsim: null pointer argument");
+  if (path == HRC_PATH_AUTO) path = (lq <= HRC_TC_MAX_LQ && total_tokens > 0) ? HRC_PATH_TC : HRC_PATH_SIMT;
+  if (path == HRC_PATH_TC)
+    return launch_maxsim_tc(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_items, d_queries, n_queries, lq,
+                            d_scores, stream);
+  HRC_REQUIRE(path == HRC_PATH_SIMT, "maxsim: unknown path %d", path);
+  return launch_maxsim_simt(d_tokens, d_offsets, n_docs, d_cand_ids, n_items, d_queries, n_queries, lq, d_scores,
+                            stream);
+}
+
+}  // namespace hrc
+
+using namespace hrc;
+
+extern "C" {
+
+int hrc_version(void) { return 100; }
+
+const char* hrc_last_error(void) { return g_error; }
+
+uint64_t hrc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int hrc_maxsim_scores(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                      const void* d_queries, int n_queries, int lq, float* d_scores, int path, void* stream) {
+  return maxsim_dispatch(d_tokens, d_offsets, n_docs, total_tokens, nullptr, n_docs, d_queries, n_queries, lq,
+                         d_scores, path, static_cast<cudaStream_t>(stream));
+}
+
+int hrc_maxsim_scores_ids(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                          const int32_t* d_cand_ids, int n_cand, const void* d_queries, int n_queries, int lq,
+                          float* d_scores, int path, void* stream) {
+  HRC_REQUIRE(n_cand >= 0, "maxsim_ids: n_cand < 0");
+  HRC_REQUIRE(n_cand == 0 || d_cand_ids != nullptr, "maxsim_ids: null candidate list");
+  return maxsim_dispatch(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_cand, d_queries, n_queries, lq,
+                         d_scores, path, static_cast<cudaStream_t>(stream));
+}
+
+size_t hrc_topk_workspace_bytes(int64_t n, int n_rows, int k) { return topk_workspace_bytes(n, n_rows, k); }
+
+int hrc_topk(const float* d_scores, const int32_t* d_ids, int64_t n, int n_rows, int k, int32_t id_base,
+             uint64_t* d_keys_out, void* d_workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_device()) return rc;
+  HRC_REQUIRE(n >= 0 && n_rows >= 0 && k >= 0, "topk: negative size");
+  HRC_REQUIRE(n_rows == 0 || k == 0 || d_keys_out != nullptr, "topk: null output");
+  HRC_REQUIRE(n == 0 || n_rows == 0 || k == 0 || d_scores != nullptr, "topk: null scores");
+  return launch_topk(d_scores, d_ids, n, n_rows, k, id_base, d_keys_out, d_workspace, workspace_bytes,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int hrc_topk_merge(const uint64_t* d_keys_in, int n_in, int n_rows, int k, uint64_t* d_keys_out, void* stream) {
+  if (int rc = check_device()) return rc;
+  HRC_REQUIRE(n_in >= 0 && n_rows >= 0 && k >= 0, "topk_merge: negative size");
+  HRC_REQUIRE(n_rows == 0 || k == 0 || d_keys_out != nullptr, "topk_merge: null output");
+  return launch_topk_merge(d_keys_in, n_in, n_rows, k, d_keys_out, static_cast<cudaStream_t>(stream));
+}
+
+int hrc_keys_unpack(const uint64_t* d_keys, int64_t n, int32_t* d_ids_out, float* d_scores_out, void* stream) {
+  if (int rc = check_device()) return rc;
+  HRC_REQUIRE(n >= 0, "keys_unpack: negative size");
+  return launch_keys_unpack(d_keys, n, d_ids_out, d_scores_out, static_cast<cudaStream_t>(stream));
+}
+
+int hrc_rrf_fuse(const int32_t* d_ids_a, int n_a, const int32_t* d_ids_b, int n_b, int n_rows, int rrf_k, int top_n,
+                 int32_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out, void* stream) {
+  if (int rc = check_device()) return rc;
+  HRC_REQUIRE(n_rows >= 0 && top_n >= 0, "rrf: negative size");
+  HRC_REQUIRE(n_rows == 0 || top_n == 0 || (d_ids_out != nullptr && d_scores_out != nullptr), "rrf: null output");
+  return launch_rrf(d_ids_a, n_a, d_ids_b, n_b, n_rows, rrf_k, top_n, d_ids_out, d_scores_out, d_counts_out,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int hrc_synth_tokens(void* d_tokens_out, int64_t token_begin, int64_t n_tokens, uint64_t seed, void* stream) {
+  if (int rc = check_device()) return rc;
+  return launch_synth(d_tokens_out, token_begin, n_tokens, seed, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

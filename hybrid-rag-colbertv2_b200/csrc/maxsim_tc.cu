@@ -1,0 +1,425 @@
+// maxsim_tc.cu — tensor-core MaxSim: TMA -> tcgen05.mma (TMEM accumulators) -> fused segmented
+// row-max / query-token-sum epilogue.  The [Lq x Ld] similarity matrix never leaves the SM.
+//
+// Data layout in HBM
+//   tokens  : bf16 [total_tokens][128], packed, padding-free           (TMA map: 2-D, 128B swizzle)
+//   offsets : int64 [n_docs + 1] CSR document boundaries
+//   queries : bf16 [n_queries][lq][128], lq <= 32                      (TMA map: 3-D, zero-filled
+//             out of bounds, so each query lands in a 32-row "slot" of the 128-row A tile)
+//
+// One CTA = one contiguous run of whole documents ("segment") x one group of 4*MT queries.
+//   warp 0      : TMA producer  — streams 128-token x 128-dim tiles (32 KB) through a ring
+//   warp 1      : MMA issuer    — per tile and M-tile: 8 x tcgen05.mma (M=128, N=128, K=16),
+//                                 accumulator = 128 TMEM columns; owns TMEM alloc/dealloc
+//   warps 2..5  : epilogue      — warp w owns TMEM lanes 32*(w%4).. = query slot (w%4): thread i
+//                                 holds query token i of that query, so the max over document
+//                                 tokens is a per-thread reduction over TMEM columns and document
+//                                 boundaries are warp-uniform; a doc's score is one warp_sum.
+// MMA orientation: A = queries (M = 4 slots x 32 tokens), B = document tokens (N), so that
+// D[row = query token][col = doc token].
+//
+// Reference semantics: local_rag_complete.py:807-812 (docstring), :813-817 (shapes), summed over
+// query tokens per BASELINE.json north_star.  Algorithmic traffic: 256 B per document token.
+#include <cuda.h>
+#include <climits>
+#include <cstdio>
+
+#include "hrc_common.cuh"
+
+namespace hrc {
+
+namespace {
+
+constexpr int kTileN = 128;                       // document tokens per tile (MMA N)
+constexpr int kTileBytes = kTileN * HRC_DIM * 2;  // 32 KB
+constexpr int kHalfTileBytes = kTileBytes / 2;    // one 64-dim (128-byte-row) slab
+constexpr int kQTileBytes = 128 * HRC_DIM * 2;    // 128 query rows x 128 dims, 32 KB
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 192;
+constexpr int kEpiWarp0 = 2;
+constexpr int kMaxSmem = 232448;                  // 227 KB opt-in limit per CTA
+constexpr uint32_t kIdesc = make_idesc_bf16_f32(128, kTileN);
+
+struct TcParams {
+  const int64_t* offsets;
+  const int32_t* cand_ids;  // nullptr: corpus mode
+  float* scores;
+  int64_t n_docs;
+  int64_t total_tokens;
+  int64_t n_items;          // row stride of scores (n_docs, or n_cand)
+  int n_queries;
+  int n_segments;           // corpus mode: CTAs along the corpus
+  int n_qgroups;            // corpus mode: query groups (4*MT queries each)
+  int n_stages;             // smem ring depth
+  uint64_t doc_policy;      // L2 policy for document tiles (evict-first when read once)
+};
+
+// Spin on an mbarrier with a wall-clock watchdog: a protocol bug must fault, not hang the GPU.
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ffu) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ull) {
+        printf("hrc: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+
+// first d in [0, n] with offsets[d] >= target
+__device__ __forceinline__ int64_t lower_bound_doc(const int64_t* __restrict__ offsets, int64_t n,
+                                                   int64_t target) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (offsets[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <int MT>
+__global__ void __launch_bounds__(kThreads, 1)
+maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_q,
+                 const TcParams p) {
+  constexpr int kTileStages = 4 / MT;  // accumulator ring: tiles in flight between MMA and epilogue
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                              // MT x 32 KB
+  uint8_t* sD = smem + MT * kQTileBytes;           // n_stages x 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + p.n_stages * kTileBytes);
+  uint64_t* full = bars;                           // [n_stages]   TMA -> MMA
+  uint64_t* empty = bars + 8;                      // [n_stages]   MMA -> TMA
+  uint64_t* tfull = bars + 16;                     // [kTileStages] MMA -> epilogue
+  uint64_t* tempty = bars + 20;                    // [kTileStages] epilogue -> MMA
+  uint64_t* qfull = bars + 24;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+  int64_t* seg = reinterpret_cast<int64_t*>(bars + 26);  // [0]=doc_begin [1]=doc_end [2]=tok_begin [3]=tok_end
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- which segment / queries does this CTA own? -------------------------------------------
+  int q_base;   // first query of slot 0, M-tile 0
+  int64_t item = 0;
+  if (p.cand_ids == nullptr) {
+    q_base = int(blockIdx.x % p.n_qgroups) * 4 * MT;   // query groups vary fastest: CTAs sharing a
+    item = blockIdx.x / p.n_qgroups;                   // corpus segment run together (L2 reuse)
+  } else {
+    q_base = blockIdx.y;
+    item = blockIdx.x;
+  }
+  if (threadIdx.x == 0) {
+    int64_t d0, d1;
+    if (p.cand_ids == nullptr) {
+      const int64_t b0 = (p.total_tokens * item) / p.n_segments;
+      const int64_t b1 = (p.total_tokens * (item + 1)) / p.n_segments;
+      d0 = lower_bound_doc(p.offsets, p.n_docs, b0);
+      d1 = (item + 1 == p.n_segments) ? p.n_docs : lower_bound_doc(p.offsets, p.n_docs, b1);
+      if (item == 0) d0 = 0;
+    } else {
+      const int64_t id = p.cand_ids[int64_t(q_base) * p.n_items + item];
+      if (id < 0 || id >= p.n_docs) {
+        p.scores[int64_t(q_base) * p.n_items + item] = -INFINITY;
+        d0 = d1 = 0;
+      } else {
+        d0 = id; d1 = id + 1;
+      }
+    }
+    seg[0] = d0; seg[1] = d1;
+    seg[2] = p.offsets[d0];
+    seg[3] = p.offsets[d1];
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_d);
+    tma_prefetch_desc(&tmap_q);
+    for (int i = 0; i < p.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kTileStages; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    mbar_init(qfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t doc_begin = seg[0], doc_end = seg[1], tok_begin = seg[2], tok_end = seg[3];
+  const int n_tiles = int((tok_end - tok_begin + kTileN - 1) / kTileN);
+
+  if (warp == 0) {
+    // =============================== TMA producer =============================================
+    if (lane == 0 && n_tiles > 0) {
+      mbar_arrive_expect_tx(qfull, MT * kQTileBytes);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        tma_load_3d(sQ + mt * kQTileBytes, &tmap_q, qfull, 0, 0, q_base + 4 * mt, kEvictLast);
+        tma_load_3d(sQ + mt * kQTileBytes + kQTileBytes / 2, &tmap_q, qfull, 64, 0, q_base + 4 * mt, kEvictLast);
+      }
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait_wd(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], kTileBytes);
+        const int row = int(tok_begin + int64_t(t) * kTileN);
+        uint8_t* dst = sD + stage * kTileBytes;
+        tma_load_2d(dst, &tmap_d, &full[stage], 0, row, p.doc_policy);
+        tma_load_2d(dst + kHalfTileBytes, &tmap_d, &full[stage], 64, row, p.doc_policy);
+        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================================
+    if (lane == 0 && n_tiles > 0) {
+      mbar_wait_wd(qfull, 0);
+      tc_fence_after_sync();
+      const uint32_t sQ_addr = smem_u32(sQ);
+      const uint32_t sD_addr = smem_u32(sD);
+      int stage = 0; uint32_t phase = 0;
+      int ts = 0; uint32_t tphase = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait_wd(&tempty[ts], tphase ^ 1);
+        mbar_wait_wd(&full[stage], phase);
+        tc_fence_after_sync();
+        const uint32_t b_addr = sD_addr + stage * kTileBytes;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint32_t a_addr = sQ_addr + mt * kQTileBytes;
+          const uint32_t d_tmem = tmem_base + uint32_t((ts * MT + mt) * kTileN);
+#pragma unroll
+          for (int k = 0; k < HRC_DIM / 16; ++k) {
+            // k-th 16-element K slice: slab (k / 4), 32 bytes per slice inside the 128-byte row
+            const uint32_t koff = (k >> 2) * kHalfTileBytes + (k & 3) * 32;
+            umma_bf16_ss(d_tmem, make_kmajor_sw128_desc(a_addr + koff),
+                         make_kmajor_sw128_desc(b_addr + koff), kIdesc, k > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[stage]);   // smem slot reusable once these MMAs have read it
+        umma_commit(&tfull[ts]);      // accumulators ready for the epilogue
+        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+        if (++ts == kTileStages) { ts = 0; tphase ^= 1; }
+      }
+    }
+  } else {
+    // =============================== epilogue ==================================================
+    const int slot = warp & 3;                 // TMEM lanes 32*slot .. 32*slot+31
+    const uint32_t lane_base = uint32_t(slot * 32) << 16;
+    bool active[MT];
+    int64_t out_row[MT];
+    bool any_active = false;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int q = q_base + 4 * mt + slot;
+      active[mt] = (p.cand_ids == nullptr) ? (q < p.n_queries) : (mt == 0 && slot == 0);
+      out_row[mt] = int64_t(q) * p.n_items;
+      any_active |= active[mt];
+    }
+    const int n_docs_seg = int(doc_end - doc_begin);
+    // document-boundary walk state; token positions are relative to tok_begin
+    int cur = 0;       // local index of the document being accumulated
+    int bj = 0;        // position of `cur` inside the 32-entry register batch of doc ends
+    int ends = INT_MAX, ends_next = INT_MAX;
+    auto load_ends = [&](int batch) -> int {
+      const int d = batch * 32 + lane;
+      return (d < n_docs_seg) ? int(p.offsets[doc_begin + d + 1] - tok_begin) : INT_MAX;
+    };
+    if (any_active) {
+      ends = load_ends(0);
+      ends_next = load_ends(1);
+    }
+    int cur_end = __shfl_sync(0xffffffffu, ends, 0);
+    float m[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) m[mt] = -INFINITY;
+
+    auto flush = [&]() {   // document `cur` is complete: emit its score(s), move to the next one
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const float s = warp_sum(m[mt]);
+        if (lane == 0 && active[mt]) {
+          const int64_t col = (p.cand_ids == nullptr) ? (doc_begin + cur) : item;
+          p.scores[out_row[mt] + col] = s;
+        }
+        m[mt] = -INFINITY;
+      }
+      ++cur;
+      if (++bj == 32) {
+        bj = 0;
+        ends = ends_next;
+        ends_next = load_ends(cur / 32 + 1);
+      }
+      cur_end = __shfl_sync(0xffffffffu, ends, bj);
+    };
+
+    int ts = 0; uint32_t tphase = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      mbar_wait_wd(&tfull[ts], tphase);
+      tc_fence_after_sync();
+      if (any_active) {
+#pragma unroll 1
+        for (int c32 = 0; c32 < kTileN / 32; ++c32) {
+          uint32_t v[MT][32];
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            tmem_ld_32x32(tmem_base + lane_base + uint32_t((ts * MT + mt) * kTileN + c32 * 32), v[mt]);
+          tmem_ld_wait();
+          const int col0 = t * kTileN + c32 * 32;
+          while (cur_end <= col0 && cur < n_docs_seg) flush();
+          if (cur_end >= col0 + 32) {
+            // no document boundary inside this 32-column chunk
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              float x = m[mt];
+#pragma unroll
+              for (int c = 0; c < 32; ++c) x = fmaxf(x, __uint_as_float(v[mt][c]));
+              m[mt] = x;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              if (c > 0) {
+                while (cur_end == col0 + c && cur < n_docs_seg) flush();
+              }
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) m[mt] = fmaxf(m[mt], __uint_as_float(v[mt][c]));
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[ts]);
+      if (++ts == kTileStages) { ts = 0; tphase ^= 1; }
+    }
+    if (any_active) {
+      while (cur < n_docs_seg) flush();
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// --- host side -------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || sym == nullptr) {
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+template <int MT>
+int launch_mt(const CUtensorMap& tmap_d, const CUtensorMap& tmap_q, const TcParams& p, dim3 grid,
+              cudaStream_t stream) {
+  const int smem_bytes = 1024 + MT * kQTileBytes + p.n_stages * kTileBytes + 512;
+  static bool configured = false;
+  if (!configured) {
+    HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kMaxSmem));
+    configured = true;
+  }
+  maxsim_tc_kernel<MT><<<grid, kThreads, smem_bytes, stream>>>(tmap_d, tmap_q, p);
+  count_launch();
+  HRC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                     const int32_t* d_cand_ids, int64_t n_items, const void* d_queries, int n_queries,
+                     int lq, float* d_scores, cudaStream_t stream) {
+  if (n_items == 0 || n_queries == 0) return 0;
+  HRC_REQUIRE(lq >= 1 && lq <= HRC_TC_MAX_LQ, "tc path: lq=%d not in [1,%d]", lq, HRC_TC_MAX_LQ);
+  HRC_REQUIRE(total_tokens > 0 && total_tokens < (1ll << 31), "tc path: total_tokens=%lld out of range",
+              (long long)total_tokens);
+  HRC_REQUIRE((reinterpret_cast<uintptr_t>(d_tokens) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_queries) & 15) == 0,
+              "tc path: token / query buffers must be 16-byte aligned");
+  EncodeTiledFn encode = get_encode_fn();
+  HRC_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+
+  CUtensorMap tmap_d, tmap_q;
+  {
+    cuuint64_t dims[2] = {HRC_DIM, (cuuint64_t)total_tokens};
+    cuuint64_t strides[1] = {HRC_DIM * 2};
+    cuuint32_t box[2] = {64, kTileN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmap_d, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d_tokens), dims, strides,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    HRC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(tokens) failed: %d", int(r));
+  }
+  {
+    cuuint64_t dims[3] = {HRC_DIM, (cuuint64_t)lq, (cuuint64_t)n_queries};
+    cuuint64_t strides[2] = {HRC_DIM * 2, (cuuint64_t)lq * HRC_DIM * 2};
+    cuuint32_t box[3] = {64, 32, 4};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&tmap_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d_queries), dims, strides,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    HRC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(queries) failed: %d", int(r));
+  }
+
+  TcParams p;
+  p.offsets = d_offsets;
+  p.cand_ids = d_cand_ids;
+  p.scores = d_scores;
+  p.n_docs = n_docs;
+  p.total_tokens = total_tokens;
+  p.n_items = n_items;
+  p.n_queries = n_queries;
+  p.n_segments = 1;
+  p.n_qgroups = 1;
+  p.doc_policy = kEvictFirst;
+
+  if (d_cand_ids != nullptr) {
+    HRC_REQUIRE(n_queries <= 65535, "tc path: too many queries for a candidate launch (%d)", n_queries);
+    p.n_stages = 6;
+    return launch_mt<1>(tmap_d, tmap_q, p, dim3((unsigned)n_items, (unsigned)n_queries), stream);
+  }
+  const int64_t tiles = (total_tokens + kTileN - 1) / kTileN;
+  p.n_segments = int(tiles < sm_count() ? tiles : sm_count());
+  if (n_queries <= 4) {
+    p.n_qgroups = 1;
+    p.n_stages = 6;
+    return launch_mt<1>(tmap_d, tmap_q, p, dim3((unsigned)p.n_segments), stream);
+  }
+  p.n_qgroups = (n_queries + 7) / 8;
+  p.doc_policy = kEvictNormal;  // the other query groups re-read this tile from L2
+  p.n_stages = 5;
+  return launch_mt<2>(tmap_d, tmap_q, p, dim3((unsigned)(p.n_segments * p.n_qgroups)), stream);
+}
+
+}  // namespace hrc

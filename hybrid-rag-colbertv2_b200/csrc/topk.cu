@@ -1,0 +1,309 @@
+// topk.cu — per-row top-k over MaxSim scores as exact radix select on 64-bit (score, id) keys.
+//
+// Replaces torch.topk (local_rag_complete.py:767) and torch.argsort + [:k] (:789-792).
+// A key is orderable(score) << 32 | ~id, so keys of one row are unique and totally ordered
+// (higher score first, then lower id): the k-th largest key is exact and the result is
+// deterministic, which torch.topk's tie order is not.
+//
+//   stage 1  select_scores_kernel : grid (chunks, rows); each CTA turns <= 8192 scores into keys in
+//            shared memory, radix-selects the chunk's top-k (8 passes of 8 bits, MSB first, with
+//            warp-aggregated histogram atomics) and writes k unsorted candidates.  When the row is
+//            a single chunk it sorts and writes the final answer itself.
+//   stage 2  select_keys_kernel : per row (and per group while the candidate list is too long for
+//            shared memory) the same select over candidate keys; the last level bitonic-sorts.
+// The same stage-2 kernel is hrc_topk_merge, the on-device merge of all-gathered per-GPU lists.
+// HBM traffic: 4 B per score, once.
+#include "hrc_common.cuh"
+
+namespace hrc {
+
+namespace {
+
+constexpr int kSelThreads = 1024;
+constexpr int kChunk = 8192;          // scores per stage-1 CTA (64 KB of keys)
+constexpr int kMergeMax = 24576;      // keys per stage-2 CTA (192 KB)
+constexpr int kSortMax = HRC_MAX_TOPK;
+
+struct SelectScratch {
+  uint32_t hist[256];
+  uint64_t prefix;
+  int k_rem;
+  int count;
+};
+
+__device__ __forceinline__ int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Exact k-th largest key among keys[0..n) (n > k >= 1, all threads of the CTA call this).
+__device__ uint64_t radix_kth_largest(const uint64_t* keys, int n, int k, SelectScratch& sc) {
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  uint64_t prefix = 0, mask = 0;
+  int k_rem = k;
+  const int n_pad = (n + 31) & ~31;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    if (tid < 256) sc.hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_pad; i += kSelThreads) {
+      uint32_t digit = 0xffffffffu;
+      if (i < n) {
+        const uint64_t key = keys[i];
+        if ((key & mask) == prefix) digit = uint32_t(key >> shift) & 255u;
+      }
+      const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+      if (digit != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&sc.hist[digit], __popc(peers));
+    }
+    __syncthreads();
+    if (tid < 32) {
+      // lane l owns bins [255 - 8l - 7, 255 - 8l], i.e. lanes walk the digits from high to low
+      uint32_t local[8];
+      uint32_t sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        local[j] = sc.hist[255 - 8 * lane - j];
+        sum += local[j];
+      }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      const uint32_t excl = incl - sum;  // keys with a digit above this lane's bins
+      if (excl < uint32_t(k_rem) && incl >= uint32_t(k_rem)) {
+        uint32_t above = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (above < uint32_t(k_rem) && above + local[j] >= uint32_t(k_rem)) {
+            sc.prefix = prefix | (uint64_t(255 - 8 * lane - j) << shift);
+            sc.k_rem = k_rem - int(above);
+            above = 0xffffffffu;  // done
+          } else if (above != 0xffffffffu) {
+            above += local[j];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    prefix = sc.prefix;
+    k_rem = sc.k_rem;
+    mask |= uint64_t(255) << shift;
+  }
+  return prefix;
+}
+
+// In-place bitonic sort, descending, n_pad a power of two, all threads of the CTA participate.
+__device__ void bitonic_sort_desc(uint64_t* a, int n_pad) {
+  for (int size = 2; size <= n_pad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n_pad / 2; i += kSelThreads) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const uint64_t x = a[lo], y = a[hi];
+        if ((x < y) == desc) { a[lo] = y; a[hi] = x; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Top-k of keys[0..n) in shared memory -> out[0..k).  sorted: descending order, else any order.
+// Slots beyond min(k, n) are zero.  sort_buf: shared, >= next_pow2(k) entries (only if sorted).
+__device__ void select_topk(const uint64_t* keys, int n, int k, uint64_t* out, bool sorted,
+                            uint64_t* sort_buf, SelectScratch& sc) {
+  const int tid = threadIdx.x;
+  const int k_eff = min(k, n);
+  uint64_t* dst = sorted ? sort_buf : out;
+  const int dst_len = sorted ? next_pow2(max(k, 1)) : k;
+  for (int i = tid; i < dst_len; i += kSelThreads) dst[i] = 0;
+  if (tid == 0) sc.count = 0;
+  __syncthreads();
+  if (n <= k) {
+    for (int i = tid; i < n; i += kSelThreads) dst[i] = keys[i];
+  } else {
+    const uint64_t kth = radix_kth_largest(keys, n, k, sc);
+    for (int i = tid; i < n; i += kSelThreads) {
+      const uint64_t key = keys[i];
+      if (key > kth) dst[atomicAdd(&sc.count, 1)] = key;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kSelThreads) {
+      if (keys[i] == kth) {
+        const int slot = atomicAdd(&sc.count, 1);
+        if (slot < k_eff) dst[slot] = kth;
+      }
+    }
+  }
+  __syncthreads();
+  if (sorted) {
+    bitonic_sort_desc(sort_buf, dst_len);
+    for (int i = tid; i < k; i += kSelThreads) out[i] = sort_buf[i];
+  }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_scores_kernel(const float* __restrict__ scores, const int32_t* __restrict__ ids, int64_t n,
+                     int k, int32_t id_base, uint64_t* __restrict__ out, int n_chunks, int final_sorted) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* sort_buf = keys + kChunk;
+  __shared__ SelectScratch sc;
+
+  const int chunk = blockIdx.x;
+  const int64_t row = blockIdx.y;
+  const int64_t begin = int64_t(chunk) * kChunk;
+  const int64_t left = n - begin;
+  const int cn = int(left < kChunk ? left : kChunk);
+  const float* src = scores + row * n + begin;
+  const int32_t* id_src = ids ? ids + row * n + begin : nullptr;
+  for (int i = threadIdx.x; i < cn; i += kSelThreads) {
+    const int32_t id = id_src ? id_src[i] : int32_t(id_base + begin + i);
+    keys[i] = make_key(src[i], id);
+  }
+  __syncthreads();
+  uint64_t* dst = out + (row * n_chunks + chunk) * k;
+  select_topk(keys, cn, k, dst, final_sorted != 0, sort_buf, sc);
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_keys_kernel(const uint64_t* __restrict__ keys_in, int n_in, int k, uint64_t* __restrict__ out,
+                   int n_groups, int group_len, int final_sorted) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* sort_buf = keys + group_len;
+  __shared__ SelectScratch sc;
+
+  const int group = blockIdx.x;
+  const int64_t row = blockIdx.y;
+  const int begin = group * group_len;
+  const int gn = min(group_len, n_in - begin);
+  const uint64_t* src = keys_in + row * n_in + begin;
+  for (int i = threadIdx.x; i < gn; i += kSelThreads) keys[i] = src[i];
+  __syncthreads();
+  uint64_t* dst = out + (row * n_groups + group) * k;
+  select_topk(keys, gn, k, dst, final_sorted != 0, sort_buf, sc);
+}
+
+__global__ void keys_unpack_kernel(const uint64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ ids,
+                                   float* __restrict__ scores) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t key = keys[i];
+  if (ids) ids[i] = key ? key_id(key) : -1;
+  if (scores) scores[i] = key ? key_score(key) : -INFINITY;
+}
+
+int sort_buf_bytes(int k) {
+  int p = 1;
+  while (p < k) p <<= 1;
+  return p * 8;
+}
+
+int configure_smem() {
+  static bool done = false;
+  if (done) return 0;
+  HRC_CHECK_CUDA(cudaFuncSetAttribute(select_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kChunk * 8 + kSortMax * 8));
+  HRC_CHECK_CUDA(cudaFuncSetAttribute(select_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kMergeMax * 8 + kSortMax * 8));
+  done = true;
+  return 0;
+}
+
+// levels of stage 2 over n_in keys per row; writes sorted top-k to d_out.  tmp holds intermediates.
+int run_key_levels(const uint64_t* d_in, int64_t n_in, int n_rows, int k, uint64_t* d_out, uint64_t* tmp0,
+                   uint64_t* tmp1, cudaStream_t stream) {
+  const uint64_t* cur = d_in;
+  int64_t cur_n = n_in;
+  int flip = 0;
+  while (true) {
+    const bool last = cur_n <= kMergeMax;
+    const int group_len = last ? int(cur_n) : kMergeMax;
+    const int n_groups = int((cur_n + group_len - 1) / group_len);
+    uint64_t* dst = last ? d_out : (flip ? tmp1 : tmp0);
+    HRC_REQUIRE(dst != nullptr, "top-k: %lld candidate keys per row need workspace", (long long)cur_n);
+    const size_t smem = size_t(group_len) * 8 + (last ? sort_buf_bytes(k) : 0);
+    select_keys_kernel<<<dim3(n_groups, n_rows), kSelThreads, smem, stream>>>(cur, int(cur_n), k, dst, n_groups,
+                                                                             group_len, last ? 1 : 0);
+    count_launch();
+    HRC_CHECK_CUDA(cudaGetLastError());
+    if (last) break;
+    cur = dst;
+    cur_n = int64_t(n_groups) * k;
+    flip ^= 1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+size_t topk_workspace_bytes(int64_t n, int n_rows, int k) {
+  if (n <= kChunk) return 0;
+  const int64_t n_chunks = (n + kChunk - 1) / kChunk;
+  const int64_t a = n_chunks * k;                      // stage-1 candidates per row
+  const int64_t b = ((a + kMergeMax - 1) / kMergeMax) * k;  // first merge level (if needed)
+  return size_t(n_rows) * size_t(a + 2 * b) * 8 + 256;
+}
+
+int launch_topk(const float* d_scores, const int32_t* d_ids, int64_t n, int n_rows, int k, int32_t id_base,
+                uint64_t* d_keys_out, void* d_workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (n_rows == 0 || k == 0) return 0;
+  HRC_REQUIRE(k >= 1 && k <= HRC_MAX_TOPK, "top-k: k=%d not in [1,%d]", k, HRC_MAX_TOPK);
+  HRC_REQUIRE(n_rows <= 65535, "top-k: too many rows (%d)", n_rows);
+  if (configure_smem()) return 1;
+  if (n <= 0) {
+    HRC_CHECK_CUDA(cudaMemsetAsync(d_keys_out, 0, size_t(n_rows) * k * 8, stream));
+    return 0;
+  }
+  const int64_t n_chunks = (n + kChunk - 1) / kChunk;
+  if (n_chunks == 1) {
+    select_scores_kernel<<<dim3(1, n_rows), kSelThreads, kChunk * 8 + sort_buf_bytes(k), stream>>>(
+        d_scores, d_ids, n, k, id_base, d_keys_out, 1, 1);
+    count_launch();
+    HRC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  HRC_REQUIRE(n_chunks <= 0x7fffffff, "top-k: row too long");
+  const size_t need = topk_workspace_bytes(n, n_rows, k);
+  HRC_REQUIRE(d_workspace != nullptr && workspace_bytes >= need, "top-k: workspace %zu < %zu bytes",
+              workspace_bytes, need);
+  const int64_t a = n_chunks * k;
+  const int64_t b = ((a + kMergeMax - 1) / kMergeMax) * k;
+  uint64_t* cand = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(d_workspace) + 255) & ~uintptr_t(255));
+  uint64_t* tmp0 = cand + size_t(n_rows) * a;
+  uint64_t* tmp1 = tmp0 + size_t(n_rows) * b;
+  select_scores_kernel<<<dim3((unsigned)n_chunks, n_rows), kSelThreads, kChunk * 8, stream>>>(
+      d_scores, d_ids, n, k, id_base, cand, int(n_chunks), 0);
+  count_launch();
+  HRC_CHECK_CUDA(cudaGetLastError());
+  return run_key_levels(cand, a, n_rows, k, d_keys_out, tmp0, tmp1, stream);
+}
+
+int launch_topk_merge(const uint64_t* d_keys_in, int n_in, int n_rows, int k, uint64_t* d_keys_out,
+                      cudaStream_t stream) {
+  if (n_rows == 0 || k == 0) return 0;
+  HRC_REQUIRE(k >= 1 && k <= HRC_MAX_TOPK, "top-k merge: k=%d not in [1,%d]", k, HRC_MAX_TOPK);
+  HRC_REQUIRE(n_in >= 0 && n_in <= kMergeMax, "top-k merge: n_in=%d exceeds %d", n_in, kMergeMax);
+  HRC_REQUIRE(n_rows <= 65535, "top-k merge: too many rows (%d)", n_rows);
+  if (configure_smem()) return 1;
+  if (n_in == 0) {
+    HRC_CHECK_CUDA(cudaMemsetAsync(d_keys_out, 0, size_t(n_rows) * k * 8, stream));
+    return 0;
+  }
+  return run_key_levels(d_keys_in, n_in, n_rows, k, d_keys_out, nullptr, nullptr, stream);
+}
+
+int launch_keys_unpack(const uint64_t* d_keys, int64_t n, int32_t* d_ids, float* d_scores, cudaStream_t stream) {
+  if (n == 0) return 0;
+  keys_unpack_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(d_keys, n, d_ids, d_scores);
+  count_launch();
+  HRC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace hrc

@@ -1,0 +1,439 @@
+"""Host-side mirror of the reference's retrieval classes for the MaxSim hot path.
+
+Same class names, method names, keyword arguments, return shapes and on-disk file as
+local_rag_complete.py (RAGConfig :56-86, JinaColBERTRetriever :715-831, DualIndexer :838-879,
+HybridRetriever :886-1014), so the classes drop into that script unchanged; the arithmetic runs in
+libhrc.so (hand-written sm_100a CUDA) through `_lib`.  There is no CPU fallback: scoring without a
+B200 raises.
+"""
+from __future__ import annotations
+
+import os
+import time
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _lib
+from .encoder import SyntheticEncoder
+from .store import DIM, PackedStore
+
+
+@dataclass
+class RAGConfig:
+    """Field-compatible with the reference's RAGConfig (local_rag_complete.py:56-86); `device` defaults to CUDA."""
+    db_path: str = "rag_local.db"
+    min_chunk_size: int = 256
+    max_chunk_size: int = 1024
+    chunk_overlap: int = 128
+    bm25_top_k: int = 100
+    colbert_top_k: int = 100
+    final_top_k: int = 10
+    chat_model: str = "llama3.2:3b"
+    vision_model: str = "llava:7b"
+    embedding_model: str = "jinaai/jina-colbert-v2"
+    ollama_url: str = "http://localhost:11434"
+    bm25_index_path: str = "indexes/bm25s"
+    colbert_index_path: str = "indexes/colbert"
+    images_dir: str = "extracted_images"
+    device: str = "cuda"
+    # additive knobs
+    rrf_k: int = 60                 # the constant at local_rag_complete.py:964
+    rerank_candidates: int = 50     # the slice at :916
+    score_reduction: str = "sum"    # "sum" (north_star / ColBERT) or "mean" (docstring :810-811); same ranking
+    maxsim_path: int = _lib.PATH_AUTO
+
+
+def _as_query_batch(q: torch.Tensor) -> torch.Tensor:
+    """[Lq, D] or [Bq, Lq, D] -> bf16 [Bq, Lq, D] (the unsqueeze at local_rag_complete.py:814-815)."""
+    if q.dim() == 2:
+        q = q.unsqueeze(0)
+    if q.dim() != 3 or q.shape[-1] != DIM:
+        raise IndexError(f"query embeddings must be [Lq, {DIM}] or [Bq, Lq, {DIM}], got {tuple(q.shape)}")
+    return q
+
+
+class JinaColBERTRetriever:
+    """Drop-in for local_rag_complete.py:715-831 with the scoring on B200."""
+
+    def __init__(self, config: RAGConfig, encoder=None):
+        self.config = config
+        # the reference loads SentenceTransformer(config.embedding_model) here (:720-724); weights are
+        # unavailable offline and the encoder is out of the hot path, so it is injectable.
+        self.model = encoder if encoder is not None else SyntheticEncoder()
+        self.store: Optional[PackedStore] = None
+        self.corpus: Optional[List[str]] = None
+        self._workspace: Optional[torch.Tensor] = None
+
+    # `corpus_embeddings` is the reference's attribute name for the store (:725,:735,:752)
+    @property
+    def corpus_embeddings(self):
+        return self.store
+
+    @property
+    def device(self) -> torch.device:
+        return torch.device(self.config.device)
+
+    # ------------------------------------------------------------------------------------------
+    # index build / persistence  (:728-753)
+    # ------------------------------------------------------------------------------------------
+    def _pack(self, emb) -> PackedStore:
+        if isinstance(emb, PackedStore):
+            return emb
+        if isinstance(emb, tuple) and len(emb) == 2:
+            return PackedStore.from_dense(emb[0], emb[1], device=self.device)
+        if isinstance(emb, (list, tuple)):
+            return PackedStore.from_ragged(emb, device=self.device)
+        return PackedStore.from_dense(emb, None, device=self.device)
+
+    def index(self, corpus: List[str]) -> None:
+        """Index corpus with ColBERT token embeddings (:728-746)."""
+        self.corpus = corpus
+        print(f"  Encoding {len(corpus)} documents...")
+        emb = self.model.encode(corpus, show_progress_bar=True, convert_to_tensor=True)
+        self.store = self._pack(emb)
+        self._save_index()
+
+    def index_embeddings(self, token_embeddings, lengths_or_offsets=None, corpus: Optional[List[str]] = None,
+                         packed: bool = False, save: bool = False) -> None:
+        """Build the store from token-embedding tensors directly (additive API).
+
+        token_embeddings: dense [N, Ld, 128] (+ lengths), a list of [len_i, 128], or packed [T, 128]
+        with `packed=True` and CSR offsets.
+        """
+        self.corpus = corpus
+        if packed:
+            self.store = PackedStore.from_packed(token_embeddings, lengths_or_offsets, device=self.device)
+        elif isinstance(token_embeddings, (list, tuple)):
+            self.store = PackedStore.from_ragged(token_embeddings, device=self.device)
+        else:
+            self.store = PackedStore.from_dense(token_embeddings, lengths_or_offsets, device=self.device)
+        if save:
+            self._save_index()
+
+    def _save_index(self) -> None:
+        os.makedirs(self.config.colbert_index_path, exist_ok=True)
+        torch.save({
+            'embeddings': self.store.tokens.cpu(),
+            'corpus': self.corpus,
+            'offsets': self.store.offsets.cpu(),
+            'format': 'hrc-packed-v1',
+        }, os.path.join(self.config.colbert_index_path, 'index.pt'))
+
+    def load(self) -> None:
+        """Load index from disk (:748-753).  Reads both the reference's dense file and the packed one."""
+        index_file = os.path.join(self.config.colbert_index_path, 'index.pt')
+        data = torch.load(index_file, map_location="cpu")
+        emb = data['embeddings']
+        if data.get('format') == 'hrc-packed-v1':
+            self.store = PackedStore.from_packed(emb, data['offsets'], device=self.device)
+        else:  # reference layout: dense fp32 [N, Ld, D], no mask
+            self.store = PackedStore.from_dense(emb, data.get('lengths'), device=self.device)
+        self.corpus = data['corpus']
+
+    # ------------------------------------------------------------------------------------------
+    # tensor-level API (additive): everything stays on the device
+    # ------------------------------------------------------------------------------------------
+    def _prep_queries(self, q: torch.Tensor) -> torch.Tensor:
+        return _as_query_batch(q).to(self.device, torch.bfloat16).contiguous()
+
+    def _finish_scores(self, scores: torch.Tensor, lq: int) -> torch.Tensor:
+        return scores / float(lq) if self.config.score_reduction == "mean" else scores
+
+    def score_embeddings(self, query_embeddings: torch.Tensor) -> torch.Tensor:
+        """MaxSim of every query against every stored document: fp32 [Bq, N] on the device."""
+        self._require_store()
+        q = self._prep_queries(query_embeddings)
+        s = _lib.maxsim_scores(self.store.tokens, self.store.offsets, q, path=self.config.maxsim_path)
+        return self._finish_scores(s, q.shape[1])
+
+    def search_keys(self, query_embeddings: torch.Tensor, k: int) -> torch.Tensor:
+        """Sorted top-k (score, GLOBAL doc id) keys per query: int64 [Bq, min(k, N)] on the device."""
+        self._require_store()
+        q = self._prep_queries(query_embeddings)
+        n = self.store.n_docs
+        k_eff = min(int(k), n)
+        if k_eff <= 0:
+            return torch.zeros((q.shape[0], 0), dtype=torch.int64, device=self.device)
+        scores = _lib.maxsim_scores(self.store.tokens, self.store.offsets, q, path=self.config.maxsim_path)
+        need = _lib.topk_workspace_bytes(n, q.shape[0], k_eff)
+        if need and (self._workspace is None or self._workspace.numel() < need):
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return _lib.topk(scores, k_eff, id_base=self.store.doc_id_base, workspace=self._workspace)
+
+    def search_embeddings(self, query_embeddings: torch.Tensor, k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(doc ids int32 [Bq, k'], scores fp32 [Bq, k']) with k' = min(k, N), best first."""
+        keys = self.search_keys(query_embeddings, k)
+        ids, scores = _lib.keys_unpack(keys)
+        return ids, self._finish_scores(scores, _as_query_batch(query_embeddings).shape[1])
+
+    search_batch = search_embeddings
+
+    def rerank_ids(self, query_embeddings: torch.Tensor, candidate_ids: torch.Tensor, k: int = 10
+                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Rerank stored documents by id without re-encoding them.
+
+        candidate_ids: int [Bq, C] (local ids of this store; negative = absent).
+        Returns (result_index int32 [Bq, k'], doc ids int32 [Bq, k'], scores fp32 [Bq, k']).
+        """
+        self._require_store()
+        q = self._prep_queries(query_embeddings)
+        cand = candidate_ids.to(self.device, torch.int32)
+        if cand.dim() == 1:
+            cand = cand.unsqueeze(0)
+        cand = cand.contiguous()
+        k_eff = min(int(k), cand.shape[1])
+        scores = _lib.maxsim_scores_ids(self.store.tokens, self.store.offsets, cand, q, path=self.config.maxsim_path)
+        keys = _lib.topk(scores, k_eff)             # ids = positions in the candidate list
+        pos, top_scores = _lib.keys_unpack(keys)
+        doc_ids = torch.gather(cand, 1, pos.clamp_min(0).to(torch.int64))
+        doc_ids = torch.where(pos >= 0, doc_ids, torch.full_like(doc_ids, -1))
+        return pos, doc_ids, self._finish_scores(top_scores, q.shape[1])
+
+    def _require_store(self) -> None:
+        if self.store is None:
+            raise RuntimeError("ColBERT index is empty: call index()/index_embeddings()/load() first")
+
+    # ------------------------------------------------------------------------------------------
+    # the reference's string API
+    # ------------------------------------------------------------------------------------------
+    def search(self, query: str, k: int = 10) -> List[Dict]:
+        """Search using MaxSim scoring (:755-777)."""
+        query_embedding = self.model.encode(query, convert_to_tensor=True)
+        ids, scores = self.search_embeddings(query_embedding, k)
+        ids_h, scores_h = ids[0].tolist(), scores[0].tolist()   # one device->host copy each, not k syncs
+        results = []
+        for idx, score in zip(ids_h, scores_h):
+            if idx < 0:
+                continue
+            results.append({
+                'document_id': int(idx),
+                'score': float(score),
+                'text': self.corpus[idx - self.store.doc_id_base] if self.corpus else None,
+            })
+        return results
+
+    def rerank(self, query: str, documents: List[str], k: int = 10) -> List[Dict]:
+        """Rerank documents with MaxSim (:779-800); `result_index` indexes the input list."""
+        if not documents:
+            return []
+        query_embedding = self.model.encode(query, convert_to_tensor=True)
+        doc_embeddings = self.model.encode(documents, convert_to_tensor=True)
+        tmp = self._pack(doc_embeddings)
+        q = self._prep_queries(query_embedding)
+        scores = _lib.maxsim_scores(tmp.tokens, tmp.offsets, q, path=self.config.maxsim_path)
+        keys = _lib.topk(scores, min(int(k), tmp.n_docs))
+        pos, top = _lib.keys_unpack(keys)
+        top = self._finish_scores(top, q.shape[1])
+        results = []
+        for rank, (idx, score) in enumerate(zip(pos[0].tolist(), top[0].tolist())):
+            results.append({
+                'result_index': int(idx),
+                'score': float(score),
+                'rank': rank + 1,
+                'text': documents[idx],
+            })
+        return results
+
+    def _maxsim_score(self, query_embedding: torch.Tensor, doc_embeddings: torch.Tensor) -> torch.Tensor:
+        """MaxSim between query and documents (:802-831), as the docstring (:807-812) defines it.
+
+        Shapes follow :813-817 and the squeeze at :831: query [Lq, D] or [Bq, Lq, D]; documents
+        [N, Ld, D] dense (every row a real token; a 2-D tensor is ONE document).  Returns fp32 [N],
+        [Bq, N] or a 0-d tensor, on the device.
+        """
+        q = self._prep_queries(query_embedding)
+        tmp = PackedStore.from_dense(doc_embeddings, None, device=self.device)
+        s = _lib.maxsim_scores(tmp.tokens, tmp.offsets, q, path=self.config.maxsim_path)
+        return self._finish_scores(s, q.shape[1]).squeeze()
+
+
+class DualIndexer:
+    """Manages the BM25s and ColBERT indexes (local_rag_complete.py:838-879); the BM25 half is third-party."""
+
+    def __init__(self, config: RAGConfig, encoder=None):
+        self.config = config
+        self.bm25_retriever = None
+        self.colbert_retriever = JinaColBERTRetriever(config, encoder=encoder)
+
+    def build_bm25_index(self, corpus: List[str]) -> None:
+        """BM25s index (:846-864) — delegated to the bm25s package when it is installed."""
+        import bm25s  # noqa: F401  (out of scope: third-party lexical index)
+        print("\n[BM25s] Building lexical search index...", end=' ')
+        start_time = time.time()
+        corpus_tokens = bm25s.tokenize(corpus, stopwords="en", stemmer=bm25s.stemmer.Stemmer.Stemmer("english"))
+        self.bm25_retriever = bm25s.BM25()
+        self.bm25_retriever.index(corpus_tokens)
+        os.makedirs(self.config.bm25_index_path, exist_ok=True)
+        self.bm25_retriever.save(self.config.bm25_index_path)
+        print(f"✓ {time.time() - start_time:.2f}s")
+
+    def build_colbert_index(self, corpus: List[str]) -> None:
+        """ColBERT index (:866-874)."""
+        print("\n[ColBERT] Building semantic search index...")
+        start_time = time.time()
+        self.colbert_retriever.index(corpus)
+        print(f"  ✓ {time.time() - start_time:.2f}s")
+
+    def load_indexes(self) -> None:
+        """Load indexes from disk (:876-879)."""
+        try:
+            import bm25s
+            self.bm25_retriever = bm25s.BM25.load(self.config.bm25_index_path)
+        except ImportError:
+            self.bm25_retriever = None
+        self.colbert_retriever.load()
+
+
+class HybridRetriever:
+    """Three-stage retrieval: BM25s + ColBERT -> RRF -> ColBERT rerank (local_rag_complete.py:886-1014).
+
+    `bm25_search(query, k) -> [{'chunk_id','score','source'}]` and `chunk_fetcher(ids) -> [chunk dict]`
+    replace the two out-of-scope neighbours (bm25s :937-950, SQLite :980-994) when given.
+    """
+
+    def __init__(self, config: RAGConfig, indexer: DualIndexer, db_session=None,
+                 bm25_search: Optional[Callable[[str, int], List[Dict]]] = None,
+                 chunk_fetcher: Optional[Callable[[List[int]], List[Dict]]] = None, verbose: bool = True):
+        self.config = config
+        self.indexer = indexer
+        self.db_session = db_session
+        self._bm25_search_fn = bm25_search
+        self._chunk_fetcher = chunk_fetcher
+        self.verbose = verbose
+        self.last_timings: Dict[str, float] = {}
+
+    def _log(self, msg: str) -> None:
+        if self.verbose:
+            print(msg)
+
+    def retrieve(self, query: str, top_k_final: int = None) -> List[Dict]:
+        """Three-stage hybrid retrieval (:894-935), with the reference's five stage timings."""
+        if top_k_final is None:
+            top_k_final = self.config.final_top_k
+        self._log("\n🔍 Retrieving relevant chunks...")
+        t = {}
+        start = time.time()
+        bm25_results = self._bm25_search(query, k=self.config.bm25_top_k)
+        t['bm25'] = time.time() - start
+        self._log(f"   • BM25s: {t['bm25']:.3f}s")
+
+        start = time.time()
+        colbert_results = self._colbert_search(query, k=self.config.colbert_top_k)
+        t['colbert'] = time.time() - start
+        self._log(f"   • ColBERT: {t['colbert']:.3f}s")
+
+        start = time.time()
+        fused_results = self._reciprocal_rank_fusion(bm25_results, colbert_results)
+        candidates = fused_results[:self.config.rerank_candidates]
+        t['fusion'] = time.time() - start
+        self._log(f"   • Fusion: {t['fusion']:.3f}s")
+
+        start = time.time()
+        candidate_chunks = self._fetch_chunks_from_db([r['chunk_id'] for r in candidates])
+        t['fetch'] = time.time() - start
+        self._log(f"   • Fetch: {t['fetch']:.3f}s")
+
+        start = time.time()
+        reranked_results = self._colbert_rerank(query, candidate_chunks, top_k=top_k_final)
+        t['rerank'] = time.time() - start
+        self._log(f"   • Rerank: {t['rerank']:.3f}s")
+        t['total'] = sum(t.values())
+        self._log(f"   ✓ Total retrieval: {t['total']:.3f}s")
+        self.last_timings = t
+        return reranked_results
+
+    def _bm25_search(self, query: str, k: int) -> List[Dict]:
+        """Stage 1 (:937-950): third-party lexical search; output shape is part of the boundary."""
+        if self._bm25_search_fn is not None:
+            return self._bm25_search_fn(query, k)
+        if self.indexer.bm25_retriever is None:
+            return []
+        import bm25s
+        query_tokens = bm25s.tokenize(query, stopwords="en", stemmer=bm25s.stemmer.Stemmer.Stemmer("english"))
+        results, scores = self.indexer.bm25_retriever.retrieve(query_tokens, k=k)
+        return [{'chunk_id': int(results[0][i]), 'score': float(scores[0][i]), 'source': 'bm25'}
+                for i in range(len(results[0]))]
+
+    def _colbert_search(self, query: str, k: int) -> List[Dict]:
+        """Stage 2 (:952-958)."""
+        results = self.indexer.colbert_retriever.search(query=query, k=k)
+        return [{'chunk_id': r['document_id'], 'score': r['score'], 'source': 'colbert'} for r in results]
+
+    def _reciprocal_rank_fusion(self, bm25_results: List[Dict], colbert_results: List[Dict], k: int = None
+                                ) -> List[Dict]:
+        """RRF fusion (:960-978) on the device, bit-compatible with the reference's fp64 Python arithmetic."""
+        if k is None:
+            k = self.config.rrf_k
+        dev = self.indexer.colbert_retriever.device
+        a = torch.tensor([[r['chunk_id'] for r in bm25_results]], dtype=torch.int32, device=dev).reshape(1, -1)
+        b = torch.tensor([[r['chunk_id'] for r in colbert_results]], dtype=torch.int32, device=dev).reshape(1, -1)
+        n = a.shape[1] + b.shape[1]
+        if n == 0:
+            return []
+        ids, scores, counts = _lib.rrf_fuse(a, b, k, n)
+        cnt = int(counts[0])
+        return [{'chunk_id': int(c), 'rrf_score': float(s)}
+                for c, s in zip(ids[0, :cnt].tolist(), scores[0, :cnt].tolist())]
+
+    def _fetch_chunks_from_db(self, chunk_ids: List[int]) -> List[Dict]:
+        """Fetch chunks (:980-994).  Storage is out of scope: a callable, or the retriever's corpus list."""
+        if self._chunk_fetcher is not None:
+            return self._chunk_fetcher(chunk_ids)
+        corpus = self.indexer.colbert_retriever.corpus
+        chunks = []
+        for cid in chunk_ids:
+            if corpus is not None and not (0 <= cid < len(corpus)):
+                continue  # the reference silently drops ids the DB does not hold (:985)
+            chunks.append({'chunk_id': cid, 'text': corpus[cid] if corpus else None, 'document_id': cid,
+                           'heading_path': '', 'has_images': False, 'metadata': {}})
+        return chunks
+
+    def _colbert_rerank(self, query: str, chunks: List[Dict], top_k: int) -> List[Dict]:
+        """Stage 3 (:996-1014).  Candidates' STORED token embeddings are gathered by chunk_id
+        instead of re-encoding their texts as the reference does at :783."""
+        if not chunks:
+            return []
+        retr = self.indexer.colbert_retriever
+        q = retr.model.encode(query, convert_to_tensor=True)
+        base = retr.store.doc_id_base
+        cand = torch.tensor([[c['chunk_id'] - base for c in chunks]], dtype=torch.int32)
+        pos, _, scores = retr.rerank_ids(q, cand, k=top_k)
+        final_results = []
+        for rank, (idx, score) in enumerate(zip(pos[0].tolist(), scores[0].tolist())):
+            if idx < 0:
+                continue
+            original_chunk = chunks[idx]
+            final_results.append({
+                'chunk_id': original_chunk['chunk_id'],
+                'text': original_chunk['text'],
+                'document_id': original_chunk['document_id'],
+                'heading_path': original_chunk.get('heading_path', ''),
+                'has_images': original_chunk.get('has_images', False),
+                'metadata': original_chunk['metadata'],
+                'score': float(score),
+                'rank': rank + 1,
+            })
+        return final_results
+
+    # ------------------------------------------------------------------------------------------
+    # batched, device-resident pipeline (additive)
+    # ------------------------------------------------------------------------------------------
+    def retrieve_batch(self, query_embeddings: torch.Tensor, bm25_ids: torch.Tensor,
+                       top_k_final: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """ColBERT top-k -> RRF with the given BM25 lists -> top candidates -> rerank, all on the device.
+
+        query_embeddings: [Bq, Lq, 128]; bm25_ids: int [Bq, n_bm25] ranked doc ids (negative = absent), the
+        shape bm25s.retrieve returns (:945-949).  Returns (doc ids int32 [Bq, k], scores fp32 [Bq, k]).
+        """
+        cfg = self.config
+        retr = self.indexer.colbert_retriever
+        k_final = cfg.final_top_k if top_k_final is None else top_k_final
+        col_ids, _ = retr.search_embeddings(query_embeddings, cfg.colbert_top_k)
+        a = bm25_ids.to(retr.device, torch.int32).contiguous()
+        fused_ids, _, _ = _lib.rrf_fuse(a, col_ids.contiguous(), cfg.rrf_k, cfg.rerank_candidates)
+        base = retr.store.doc_id_base
+        local = torch.where(fused_ids >= 0, fused_ids - base, fused_ids)
+        _, doc_ids, scores = retr.rerank_ids(query_embeddings, local, k=k_final)
+        return torch.where(doc_ids >= 0, doc_ids + base, doc_ids), scores

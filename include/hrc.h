@@ -1,0 +1,134 @@
+/*
+ * hrc.h — C ABI of libhrc.so: B200 (sm_100a) late-interaction MaxSim scoring, top-k and RRF fusion.
+ *
+ * This is the drop-in boundary for the ONE hot path of techmum21p/hybrid-rag-ColBERTv2:
+ * JinaColBERTRetriever's MaxSim scoring + top-k (first stage and post-RRF rerank) and the RRF step
+ * between them.  The reference has no FFI of its own (it is a single Python script that calls torch
+ * on CPU/MPS), so each entry point below cites the reference Python statement(s) it replaces
+ * (paths relative to /root/reference).  The Python classes in hybrid-rag-colbertv2_b200/retriever.py
+ * bind these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain C symbols, plain pointers and sizes; no torch / pybind types.
+ *   - every pointer named d_* is DEVICE memory owned by the caller, valid on the current device.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy stream).
+ *   - return value: 0 = ok, non-zero = error; hrc_last_error() returns a thread-local message.
+ *   - token embeddings are bf16, HRC_DIM (=128) wide, rows L2-normalised by the caller.
+ *   - corpus layout: packed, padding-free  d_tokens[total_tokens][128]  plus CSR  d_offsets[n_docs+1]
+ *     (int64, d_offsets[0] == 0, d_offsets[n_docs] == total_tokens).
+ *   - a "key" is a 64-bit totally ordered (score, doc_id) pair:
+ *         key = (uint64)orderable(score) << 32 | (uint32)~doc_id
+ *     so that larger key == higher score, and among equal scores the LOWER doc_id wins.
+ *     key 0 is the "empty slot" sentinel.
+ */
+#ifndef HRC_H_
+#define HRC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRC_DIM 128            /* embedding width (jina-colbert-v2 projects to 128)            */
+#define HRC_MAX_TOPK 2048      /* largest k the selection kernels accept                        */
+#define HRC_TC_MAX_LQ 32       /* query tokens per query slot on the tcgen05 path               */
+
+/* scoring path selector */
+#define HRC_PATH_AUTO 0
+#define HRC_PATH_SIMT 1        /* coalesced 16-byte loads + warp-shuffle reduction (CUDA cores) */
+#define HRC_PATH_TC   2        /* TMA + tcgen05.mma + TMEM, fused segmented max/sum epilogue     */
+
+/* Library / ABI version (major*10000 + minor*100 + patch). */
+int hrc_version(void);
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* hrc_last_error(void);
+
+/* Number of kernels this library has launched since load (all threads). Used by bench.py's
+ * gpu_launches claim. */
+uint64_t hrc_launch_count(void);
+
+/*
+ * MaxSim scores of every query against every document of the packed store.
+ *   d_scores[q * n_docs + d] = sum_{i < lq} max_{t in doc d} <Q[q][i], tokens[t]>      (fp32 accumulate)
+ * Replaces: JinaColBERTRetriever._maxsim_score, local_rag_complete.py:802-831 (as its docstring
+ * :807-812 and BASELINE.json's north_star define it), called from search :764.
+ *   d_queries : bf16 [n_queries][lq][128]
+ *   path      : HRC_PATH_*; AUTO picks TC when lq <= HRC_TC_MAX_LQ and the corpus is large enough.
+ * An empty document (length 0) scores -inf.
+ */
+int hrc_maxsim_scores(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs,
+                      int64_t total_tokens, const void* d_queries, int n_queries, int lq,
+                      float* d_scores, int path, void* stream);
+
+/*
+ * MaxSim scores of query q against its own candidate list (the rerank shape):
+ *   d_scores[q * n_cand + j] = maxsim(Q[q], doc d_cand_ids[q * n_cand + j])
+ * Replaces: JinaColBERTRetriever.rerank's scoring step, local_rag_complete.py:782-786 (the
+ * reference re-encodes the candidate texts; here the stored token embeddings are gathered by id).
+ * Candidate ids < 0 or >= n_docs score -inf.
+ */
+int hrc_maxsim_scores_ids(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs,
+                          int64_t total_tokens, const int32_t* d_cand_ids, int n_cand,
+                          const void* d_queries, int n_queries, int lq, float* d_scores,
+                          int path, void* stream);
+
+/* Bytes of scratch hrc_topk needs for these sizes. */
+size_t hrc_topk_workspace_bytes(int64_t n, int n_rows, int k);
+
+/*
+ * Per-row top-k of a score matrix, sorted (descending score, ascending id).
+ *   d_scores   : fp32 [n_rows][n]
+ *   d_ids      : optional int32 [n_rows][n] ids of the columns (NULL: id = id_base + column)
+ *   d_keys_out : uint64 [n_rows][k]; slots beyond min(k, n) are 0
+ * Replaces: torch.topk at local_rag_complete.py:767 and torch.argsort at :789 (+ the [:k] at :792).
+ * NaN scores order as -inf.
+ */
+int hrc_topk(const float* d_scores, const int32_t* d_ids, int64_t n, int n_rows, int k,
+             int32_t id_base, uint64_t* d_keys_out, void* d_workspace, size_t workspace_bytes,
+             void* stream);
+
+/*
+ * Merge: per-row top-k of n_in keys (e.g. the all-gathered per-GPU top-k lists), sorted.
+ *   d_keys_in  : uint64 [n_rows][n_in] (0 = empty);  d_keys_out : uint64 [n_rows][k]
+ * New step (document-sharded search); the single-GPU reference has no counterpart.
+ * n_in * 8 bytes must fit the kernel's shared memory (n_in <= 24576).
+ */
+int hrc_topk_merge(const uint64_t* d_keys_in, int n_in, int n_rows, int k, uint64_t* d_keys_out,
+                   void* stream);
+
+/* Unpack keys into ids (int32, -1 for empty) and scores (fp32, -inf for empty). */
+int hrc_keys_unpack(const uint64_t* d_keys, int64_t n, int32_t* d_ids_out, float* d_scores_out,
+                    void* stream);
+
+/*
+ * Reciprocal-rank fusion of two ranked id lists per row, bit-compatible with the reference's
+ * Python-float (IEEE fp64) arithmetic, accumulation order and stable tie order.
+ * Replaces: HybridRetriever._reciprocal_rank_fusion, local_rag_complete.py:960-978, and the
+ * [:50] slice at :916.
+ *   d_ids_a : int32 [n_rows][n_a]  first list (BM25 order), rank = position+1; id < 0 = absent
+ *   d_ids_b : int32 [n_rows][n_b]  second list (ColBERT order)
+ *   rrf_k   : the constant (60 in the reference)
+ *   d_ids_out    : int32  [n_rows][top_n]  fused ids, best first (-1 padded)
+ *   d_scores_out : double [n_rows][top_n]  fused scores (0 padded)
+ *   d_counts_out : int32  [n_rows]         number of distinct ids (may exceed top_n), optional
+ * n_a + n_b <= 4096.
+ */
+int hrc_rrf_fuse(const int32_t* d_ids_a, int n_a, const int32_t* d_ids_b, int n_b, int n_rows,
+                 int rrf_k, int top_n, int32_t* d_ids_out, double* d_scores_out,
+                 int32_t* d_counts_out, void* stream);
+
+/*
+ * Deterministic synthetic token embeddings (test/bench utility, not on the query path):
+ * row t (global token index token_begin + t) = L2-normalised N(0,1)^128 drawn from a counter-based
+ * hash of (seed, global token index, dim), rounded to bf16.  Any sharding reproduces the same corpus.
+ */
+int hrc_synth_tokens(void* d_tokens_out, int64_t token_begin, int64_t n_tokens, uint64_t seed,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HRC_H_ */

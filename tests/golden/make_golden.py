@@ -1,0 +1,151 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference in this container.
+
+    python tests/golden/make_golden.py            # needs /root/reference (not present on the GPU box)
+
+The reference script cannot be imported as shipped (5 third-party imports are absent offline,
+SURVEY.md F4), so those imports are stubbed with MagicMock exactly as in SURVEY.md §A.1; nothing in
+/root/reference is edited or copied.  Outputs (small, committed):
+  literal_maxsim.npz  inputs + outputs of the reference's `_maxsim_score` (what it literally computes)
+  api_shapes.json     search()/rerank()/index()/load() observable behaviour with a fake encoder
+  rrf.json            `_reciprocal_rank_fusion` ids + fp64 scores (repr round-trips) incl. tie order
+"""
+import importlib.util
+import json
+import os
+import sys
+import tempfile
+from unittest.mock import MagicMock
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference/local_rag_complete.py"
+
+
+def load_reference():
+    for name in ["pymupdf4llm", "fitz", "bm25s", "sentence_transformers", "sqlalchemy", "sqlalchemy.ext",
+                 "sqlalchemy.ext.declarative", "sqlalchemy.orm"]:
+        sys.modules[name] = MagicMock()
+    spec = importlib.util.spec_from_file_location("local_rag_complete", REF)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+class FakeEncoder:
+    """encode(str) -> [32,128]; encode(list) -> [N,16,128]; deterministic in the text."""
+
+    def __init__(self):
+        self.calls = []
+
+    @staticmethod
+    def _rows(text, n):
+        seed = 0
+        for ch in text:
+            seed = (seed * 131 + ord(ch)) % (2**31 - 1)
+        g = torch.Generator().manual_seed(seed)
+        return torch.nn.functional.normalize(torch.randn((n, 128), generator=g), dim=-1)
+
+    def encode(self, x, **kw):
+        self.calls.append((type(x).__name__, sorted(kw.items())))
+        if isinstance(x, str):
+            return self._rows(x, 32)
+        return torch.stack([self._rows(t, 16) for t in x])
+
+
+def main():
+    m = load_reference()
+    R = m.JinaColBERTRetriever.__new__(m.JinaColBERTRetriever)   # bypass __init__ (needs the model)
+
+    # ---- 1. literal _maxsim_score --------------------------------------------------------------
+    g = torch.Generator().manual_seed(20260101)
+    q = torch.nn.functional.normalize(torch.randn((32, 128), generator=g), dim=-1)
+    qb = torch.nn.functional.normalize(torch.randn((4, 32, 128), generator=g), dim=-1)
+    D = torch.nn.functional.normalize(torch.randn((8, 16, 128), generator=g), dim=-1)
+    np.savez_compressed(
+        os.path.join(HERE, "literal_maxsim.npz"),
+        q=q.numpy(), qb=qb.numpy(), D=D.numpy(),
+        out_q_D=R._maxsim_score(q, D).numpy(),
+        out_qb_D=R._maxsim_score(qb, D).numpy(),
+        out_q_D2d=R._maxsim_score(q, D[0]).numpy(),          # 2-D docs -> ONE document -> 0-d
+        out_q_D1=R._maxsim_score(q, D[:1]).numpy(),          # N == 1 -> 0-d
+    )
+
+    # ---- 2. API behaviour with a fake encoder ---------------------------------------------------
+    api = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        cfg = m.RAGConfig(colbert_index_path=os.path.join(tmp, "colbert"))
+        R.config = cfg
+        R.model = FakeEncoder()
+        R.corpus_embeddings = None
+        R.corpus = None
+        corpus = [f"doc {i}" for i in range(30)]
+        R.index(corpus)
+        saved = torch.load(os.path.join(cfg.colbert_index_path, "index.pt"))
+        api["index_pt_keys"] = sorted(saved.keys())
+        api["index_pt_embeddings_shape"] = list(saved["embeddings"].shape)
+        api["index_pt_embeddings_dtype"] = str(saved["embeddings"].dtype)
+        api["config_device"] = cfg.device
+        api["config_defaults"] = {"bm25_top_k": cfg.bm25_top_k, "colbert_top_k": cfg.colbert_top_k,
+                                  "final_top_k": cfg.final_top_k, "colbert_index_path": m.RAGConfig().colbert_index_path,
+                                  "embedding_model": cfg.embedding_model}
+        s5 = R.search("hello", k=5)
+        api["search_k5"] = s5
+        api["search_k1000_len"] = len(R.search("hello", k=1000))
+        api["search_default_len"] = len(R.search("hello"))
+        rr = R.rerank("hello", corpus[:12], k=4)
+        api["rerank_k4"] = rr
+        api["rerank_default_len"] = len(R.rerank("hello", corpus[:12]))
+        api["rerank_k_gt_n_len"] = len(R.rerank("hello", corpus[:3], k=10))
+        api["encode_calls"] = R.model.calls
+        R2 = m.JinaColBERTRetriever.__new__(m.JinaColBERTRetriever)
+        R2.config = cfg
+        R2.load()
+        api["load_roundtrip_equal"] = bool(torch.equal(R2.corpus_embeddings, R.corpus_embeddings)) and R2.corpus == corpus
+        # N == 1 crashes search
+        R.index(corpus[:1])
+        try:
+            R.search("hello", k=1)
+            api["search_n1"] = "ok"
+        except Exception as e:  # noqa: BLE001
+            api["search_n1"] = type(e).__name__
+        # 1-D inputs raise
+        try:
+            R._maxsim_score(torch.randn(128), torch.randn(5, 128))
+            api["maxsim_1d"] = "ok"
+        except Exception as e:  # noqa: BLE001
+            api["maxsim_1d"] = type(e).__name__
+    with open(os.path.join(HERE, "api_shapes.json"), "w") as f:
+        json.dump(api, f, indent=1, sort_keys=True)
+
+    # ---- 3. RRF ----------------------------------------------------------------------------------
+    H = m.HybridRetriever.__new__(m.HybridRetriever)
+    cases = []
+
+    def run(a, b, k=None):
+        ra = [{'chunk_id': int(i), 'score': 0.0, 'source': 'bm25'} for i in a]
+        rb = [{'chunk_id': int(i), 'score': 0.0, 'source': 'colbert'} for i in b]
+        out = H._reciprocal_rank_fusion(ra, rb) if k is None else H._reciprocal_rank_fusion(ra, rb, k=k)
+        cases.append({"a": [int(i) for i in a], "b": [int(i) for i in b], "k": 60 if k is None else k,
+                      "ids": [r['chunk_id'] for r in out], "scores": [repr(r['rrf_score']) for r in out]})
+
+    run([5, 3, 9], [7, 3, 5])                      # SURVEY.md §A.3 known answer
+    run([], [1, 2, 3])
+    run([4, 4, 4], [4])                            # an id repeated inside one list accumulates left to right
+    run([10, 11, 12, 13], [13, 12, 11, 10])        # mathematically equal sums: tie order = insertion order
+    rng = np.random.default_rng(20260104)
+    for overlap in (0, 30, 100):
+        a = rng.permutation(100000)[:100]
+        b = np.concatenate([rng.permutation(a)[:overlap], 200000 + rng.permutation(100000)[:100 - overlap]])
+        b = rng.permutation(b)
+        run(a, b)
+    a = rng.permutation(5000)[:100]
+    run(a, rng.permutation(a), k=1)               # different constant
+    with open(os.path.join(HERE, "rrf.json"), "w") as f:
+        json.dump(cases, f)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,134 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the packed
+store / sharding / synthetic-data logic, and that the product path refuses to run without a GPU."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import hybrid_rag_colbertv2_b200 as hrc
+from hybrid_rag_colbertv2_b200 import _lib
+from hybrid_rag_colbertv2_b200.store import PackedStore, lengths_to_offsets, shard_doc_ranges
+from hybrid_rag_colbertv2_b200.synth import doc_lengths, synth_queries
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "hrc.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hrc_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 11
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/hrc.h but not exported by libhrc.so"
+    assert sorted(_lib.SYMBOLS) == declared, "ctypes table and header disagree"
+    assert lib.hrc_version() == 100
+    assert lib.hrc_last_error() == b""
+    assert _lib.topk_workspace_bytes(1000, 4, 10) == 0
+    assert _lib.topk_workspace_bytes(1_000_000, 1, 100) > 123 * 100 * 8
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without the CUDA device, never fall back."""
+    tok = torch.zeros((8, 128), dtype=torch.bfloat16)
+    off = torch.tensor([0, 8])
+    q = torch.zeros((1, 32, 128), dtype=torch.bfloat16)
+    with pytest.raises(hrc.HrcError):
+        _lib.maxsim_scores(tok, off, q)
+    with pytest.raises(hrc.HrcError):
+        _lib.topk(torch.zeros((1, 4)), 2)
+    src = open(os.path.join(ROOT, "hybrid-rag-colbertv2_b200", "retriever.py")).read()
+    for mod in ("_lib.py", "retriever.py", "store.py", "sharded.py", "synth.py", "encoder.py", "__init__.py"):
+        text = open(os.path.join(ROOT, "hybrid-rag-colbertv2_b200", mod)).read()
+        assert "oracle" not in text.replace("oracle for", ""), f"{mod} must not import the oracle"
+    assert "einsum" not in src
+
+
+def test_store_from_dense_ragged_packed_agree():
+    g = torch.Generator().manual_seed(0)
+    lens = [5, 1, 7, 3]
+    dense = torch.randn((4, 7, 128), generator=g)
+    a = PackedStore.from_dense(dense, lens, device="cpu")
+    b = PackedStore.from_ragged([dense[i, :l] for i, l in enumerate(lens)], device="cpu")
+    assert a.n_docs == b.n_docs == 4 and a.total_tokens == 16
+    assert torch.equal(a.tokens, b.tokens) and torch.equal(a.offsets, b.offsets)
+    assert a.offsets.tolist() == [0, 5, 6, 13, 16]
+    full = PackedStore.from_dense(dense, None, device="cpu")            # reference layout: every row is a token
+    assert full.total_tokens == 28 and full.lengths().tolist() == [7, 7, 7, 7]
+    one = PackedStore.from_dense(dense[0], None, device="cpu")          # 2-D = ONE document (:816-817)
+    assert one.n_docs == 1 and one.total_tokens == 7
+    with pytest.raises(ValueError):
+        PackedStore.from_dense(dense, [5, 0, 7, 3], device="cpu")       # empty docs rejected at index build
+    e = PackedStore.from_dense(dense, [5, 0, 7, 3], device="cpu", allow_empty=True)
+    assert e.lengths().tolist() == [5, 0, 7, 3]
+    with pytest.raises(ValueError):
+        PackedStore.from_dense(torch.zeros(2, 3, 64), None, device="cpu")
+
+
+def test_store_save_load_and_shard_roundtrip(tmp_path):
+    g = torch.Generator().manual_seed(1)
+    lens = torch.randint(1, 40, (57,), generator=g)
+    off = lengths_to_offsets(lens)
+    tok = torch.randn((int(off[-1]), 128), generator=g)
+    s = PackedStore.from_packed(tok, off, device="cpu")
+    s.save(str(tmp_path / "st"))
+    back = PackedStore.load(str(tmp_path / "st"), device="cpu")
+    assert torch.equal(back.tokens, s.tokens) and torch.equal(back.offsets, s.offsets)
+    for world in (2, 4, 8):
+        ranges = shard_doc_ranges(off, world)
+        assert ranges[0][0] == 0 and ranges[-1][1] == 57
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+        toks = []
+        for r in range(world):
+            sh = s.shard(r, world)
+            ld = PackedStore.load(str(tmp_path / "st"), device="cpu", rank=r, world_size=world)
+            assert sh.doc_id_base == ranges[r][0] == ld.doc_id_base
+            assert torch.equal(sh.tokens, ld.tokens) and torch.equal(sh.offsets, ld.offsets)
+            assert int(sh.offsets[0]) == 0
+            toks.append(sh.total_tokens)
+        assert sum(toks) == s.total_tokens
+        assert max(toks) - min(toks) <= 2 * 40        # balanced by tokens, within one document
+
+
+def test_shard_ranges_cover_degenerate_inputs():
+    assert shard_doc_ranges(np.array([0]), 4) == [(0, 0)] * 4
+    assert shard_doc_ranges(np.array([0, 5]), 3) == [(0, 1), (1, 1), (1, 1)]
+    off = np.arange(0, 129 * 10, 128)
+    assert shard_doc_ranges(off, 2) == [(0, 5), (5, 10)]
+
+
+def test_synthetic_lengths_are_shard_invariant():
+    a = doc_lengths(1000, 32, 512, 7)
+    b = doc_lengths(2000, 32, 512, 7)
+    assert (a == b[:1000]).all() and a.min() >= 32 and a.max() <= 512 and 200 < a.mean() < 340
+    assert (doc_lengths(10, 128, 128, 1) == 128).all()
+    q = synth_queries(3, 32)
+    assert q.shape == (3, 32, 128) and q.dtype == torch.bfloat16
+    assert torch.allclose(q.float().norm(dim=-1), torch.ones(3, 32), atol=2e-2)
+
+
+def test_synthetic_encoder_is_deterministic_and_normalised():
+    enc = hrc.SyntheticEncoder()
+    a = enc.encode("what is late interaction", convert_to_tensor=True)
+    b = enc.encode("what is late interaction", convert_to_tensor=True)
+    assert a.shape == (32, 128) and torch.equal(a, b)
+    docs = enc.encode(["late interaction scoring", "x"], show_progress_bar=True, convert_to_tensor=True)
+    assert [d.shape[0] for d in docs] == [3, 1]
+    assert torch.allclose(docs[0].norm(dim=-1), torch.ones(3), atol=1e-5)
+    fixed = hrc.SyntheticEncoder(doc_tokens=8).encode(["a b", "c"], convert_to_tensor=True)
+    assert fixed.shape == (2, 8, 128)
+
+
+def test_config_matches_reference_defaults(golden_dir):
+    api = json.load(open(os.path.join(golden_dir, "api_shapes.json")))
+    cfg = hrc.RAGConfig()
+    for k, v in api["config_defaults"].items():
+        assert getattr(cfg, k) == v
+    assert cfg.device == "cuda" and cfg.rrf_k == 60 and cfg.rerank_candidates == 50
