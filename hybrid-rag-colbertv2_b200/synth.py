@@ -70,8 +70,8 @@ def plant(store: PackedStore, queries: torch.Tensor, n_planted: int = 200, seed:
                 continue
             gg = torch.Generator(device="cpu").manual_seed(seed * 1000003 + gid)
             n_tok = min(int(lens[d]), lq)
-            sigma = 0.15 + 0.85 * (j / max(n_planted - 1, 1))     # graded noise -> graded scores
-            rows = qf[qi, :n_tok] + sigma * torch.randn((n_tok, DIM), generator=gg) / (DIM ** 0.5) * 4.0
+            noise_norm = 0.5 + 1.5 * (j / max(n_planted - 1, 1))  # cos 0.89 .. 0.45: graded, well above background
+            rows = qf[qi, :n_tok] + noise_norm * torch.randn((n_tok, DIM), generator=gg) / (DIM ** 0.5)
             rows = torch.nn.functional.normalize(rows, dim=-1).to(torch.bfloat16)
             t0 = int(off[d])
             store.tokens[t0:t0 + n_tok] = rows.to(store.device)

@@ -1,0 +1,355 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the
+same bf16-rounded inputs.  Tolerance (north_star): fp32-accumulated scores within 1e-3 relative;
+returned ids and their order exact wherever oracle score gaps exceed that tolerance; integer work
+(keys, RRF ids, fp64 RRF scores) bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import maxsim_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-3
+
+
+def _lib():
+    from hybrid_rag_colbertv2_b200 import _lib
+    return _lib
+
+
+def _case(seed, n_docs, min_len, max_len, bq, lq, lens=None):
+    g = torch.Generator().manual_seed(seed)
+    if lens is None:
+        lens = torch.randint(min_len, max_len + 1, (n_docs,), generator=g)
+    else:
+        lens = torch.as_tensor(lens, dtype=torch.int64)
+    off = torch.zeros(lens.numel() + 1, dtype=torch.int64)
+    off[1:] = torch.cumsum(lens, 0)
+    tok = torch.nn.functional.normalize(torch.randn((int(off[-1]), 128), generator=g), dim=-1).to(torch.bfloat16)
+    q = torch.nn.functional.normalize(torch.randn((bq, lq, 128), generator=g), dim=-1).to(torch.bfloat16)
+    return q, tok, off
+
+
+def _assert_scores(got: torch.Tensor, exp: torch.Tensor, what=""):
+    got = got.float().cpu()
+    fin = torch.isfinite(exp)
+    assert torch.equal(torch.isfinite(got), fin), f"{what}: finite pattern differs"
+    assert torch.equal(got[~fin], exp[~fin]), f"{what}: non-finite values differ"
+    scale = exp[fin].abs().max().clamp_min(1e-6) if fin.any() else 1.0
+    err = ((got[fin] - exp[fin]).abs().max() / scale).item() if fin.any() else 0.0
+    assert err <= RTOL, f"{what}: max relative error {err:.3e} > {RTOL}"
+
+
+SHAPES = [
+    # (n_docs, min_len, max_len, bq, lq)           what it exercises
+    (50, 32, 512, 1, 32),      # C1 rerank shape
+    (300, 128, 128, 1, 32),    # C2 shape, tile-aligned documents
+    (257, 1, 1, 1, 32),        # one-token documents: a boundary at every column
+    (1, 700, 700, 1, 32),      # N == 1 (the reference crashes here), document spanning 6 tiles
+    (40, 1, 300, 3, 32),       # ragged, several queries in one M tile
+    (64, 32, 512, 9, 32),      # > 8 queries: two query groups on the MT=2 kernel + a partial group
+    (33, 127, 129, 5, 32),     # documents straddling tile boundaries by one token, MT=2
+    (20, 5, 90, 2, 17),        # lq < 32: query rows zero-filled by TMA
+    (10, 3, 40, 1, 1),         # single query token
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("path", ["tc", "simt"])
+def test_maxsim_scores_match_oracle(cuda_dev, shape, path):
+    L = _lib()
+    q, tok, off = _case(hash(shape) % 10_000, *shape)
+    exp = o.maxsim_scores(q.float(), tok.float(), off)
+    got = L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev),
+                          path=L.PATH_TC if path == "tc" else L.PATH_SIMT)
+    torch.cuda.synchronize()
+    _assert_scores(got, exp, f"{path} {shape}")
+
+
+def test_simt_handles_long_queries(cuda_dev):
+    L = _lib()
+    q, tok, off = _case(11, 25, 1, 70, 2, 77)
+    exp = o.maxsim_scores(q.float(), tok.float(), off)
+    _assert_scores(L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev)), exp, "auto lq=77")
+    with pytest.raises(Exception):
+        L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev), path=L.PATH_TC)
+
+
+def test_empty_documents_score_minus_inf(cuda_dev):
+    L = _lib()
+    q, tok, off = _case(12, 0, 0, 0, 2, 32, lens=[0, 5, 0, 0, 130, 1, 0])
+    exp = o.maxsim_scores(q.float(), tok.float(), off)
+    for path in (L.PATH_TC, L.PATH_SIMT):
+        _assert_scores(L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev), path=path), exp, str(path))
+
+
+def test_many_segments_cover_every_document_once(cuda_dev):
+    """More tiles than SMs: every CTA owns a run of whole documents; none may be dropped or doubled."""
+    L = _lib()
+    q, tok, off = _case(13, 3000, 16, 200, 1, 32)
+    exp = o.maxsim_scores(q.float(), tok.float(), off)
+    out = torch.full((1, 3000), float("nan"), device=cuda_dev)
+    L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev), path=L.PATH_TC, out=out)
+    _assert_scores(out, exp, "3000 ragged docs")
+
+
+def test_tc_and_simt_agree_on_candidates(cuda_dev):
+    L = _lib()
+    q, tok, off = _case(14, 400, 1, 512, 4, 32)
+    g = torch.Generator().manual_seed(3)
+    cand = torch.randint(0, 400, (4, 50), generator=g, dtype=torch.int32)
+    cand[1, 7] = -1
+    cand[2, 9] = 400                                      # out of range -> -inf
+    full = o.maxsim_scores(q.float(), tok.float(), off)
+    exp = torch.gather(full, 1, cand.clamp(0, 399).to(torch.int64))
+    exp[1, 7] = float("-inf")
+    exp[2, 9] = float("-inf")
+    for path in (L.PATH_TC, L.PATH_SIMT):
+        got = L.maxsim_scores_ids(tok.to(cuda_dev), off.to(cuda_dev), cand.to(cuda_dev), q.to(cuda_dev), path=path)
+        _assert_scores(got, exp, f"candidates path {path}")
+
+
+@pytest.mark.parametrize("n,k,rows", [(50, 10, 1), (50, 100, 2), (8192, 100, 3), (8193, 100, 1), (100_000, 100, 4),
+                                      (300_000, 1000, 1), (70_000, 2048, 2), (5, 1, 1)])
+def test_topk_is_exact(cuda_dev, n, k, rows):
+    L = _lib()
+    g = torch.Generator().manual_seed(n + k)
+    s = torch.randn((rows, n), generator=g)
+    s[:, : n // 3] = torch.round(s[:, : n // 3] * 4) / 4          # many exact ties
+    if n > 10:
+        s[0, 3] = float("nan")
+        s[0, 4] = float("-inf")
+        s[0, 5] = float("inf")
+    keys = L.topk(s.to(cuda_dev), k, id_base=7)
+    ids, sc = L.keys_unpack(keys)
+    ref = o.merge_keys(o.make_keys(s.numpy(), np.broadcast_to(np.arange(n) + 7, s.shape)), k)
+    assert (keys.cpu().numpy().view(np.uint64) == ref).all()
+    ri, rs = o.unpack_keys(ref)
+    assert (ids.cpu().numpy() == ri).all() and (sc.cpu().numpy() == rs).all()
+    # against torch.topk: same values; ids may differ only inside ties
+    kk = min(k, n)
+    clean = torch.nan_to_num(s, nan=float("-inf"))
+    tv = torch.topk(clean, kk).values
+    assert torch.equal(sc.cpu()[:, :kk], tv)
+
+
+def test_topk_with_explicit_ids_and_merge(cuda_dev):
+    L = _lib()
+    g = torch.Generator().manual_seed(9)
+    s = torch.randn((3, 500), generator=g)
+    ids = torch.stack([torch.randperm(10_000, generator=g)[:500] for _ in range(3)]).to(torch.int32)
+    keys = L.topk(s.to(cuda_dev), 40, ids=ids.to(cuda_dev))
+    ref = o.merge_keys(o.make_keys(s.numpy(), ids.numpy()), 40)
+    assert (keys.cpu().numpy().view(np.uint64) == ref).all()
+    # merge of 8 "ranks" of 100 keys, some empty
+    parts = []
+    for r in range(8):
+        sr = torch.randn((3, 100), generator=g)
+        kr = o.make_keys(sr.numpy(), np.broadcast_to(np.arange(100) + 1000 * r, sr.shape))
+        if r == 5:
+            kr[:, 50:] = 0
+        parts.append(kr)
+    allk = np.concatenate(parts, 1)
+    got = L.topk_merge(torch.from_numpy(allk.view(np.int64).copy()).to(cuda_dev), 100)
+    assert (got.cpu().numpy().view(np.uint64) == o.merge_keys(allk, 100)).all()
+    few = L.topk_merge(torch.from_numpy(allk[:, :30].view(np.int64).copy()).to(cuda_dev), 100)
+    assert (few.cpu().numpy().view(np.uint64) == o.merge_keys(allk[:, :30], 100)).all()
+
+
+def test_rrf_bit_exact_against_reference_fixtures(cuda_dev, golden_dir):
+    L = _lib()
+    cases = json.load(open(os.path.join(golden_dir, "rrf.json")))
+    for c in cases:
+        a = torch.tensor([c["a"]], dtype=torch.int32, device=cuda_dev).reshape(1, -1)
+        b = torch.tensor([c["b"]], dtype=torch.int32, device=cuda_dev).reshape(1, -1)
+        n = len(c["a"]) + len(c["b"])
+        ids, scores, counts = L.rrf_fuse(a, b, c["k"], n)
+        cnt = int(counts[0])
+        assert cnt == len(c["ids"])
+        assert ids[0, :cnt].tolist() == c["ids"]
+        assert [repr(x) for x in scores[0, :cnt].tolist()] == c["scores"]      # fp64 bit-exact
+        assert (ids[0, cnt:] == -1).all()
+        top = L.rrf_fuse(a, b, c["k"], 50)[0]                                 # the [:50] slice at :916
+        assert top[0, : min(50, cnt)].tolist() == c["ids"][:50]
+
+
+def test_rrf_batched_random_against_oracle(cuda_dev):
+    L = _lib()
+    rng = np.random.default_rng(4)
+    a = rng.integers(0, 300, (64, 100)).astype(np.int32)           # repeats inside a list are legal
+    b = rng.integers(0, 300, (64, 100)).astype(np.int32)
+    a[3, 10:20] = -1
+    ids, scores, counts = L.rrf_fuse(torch.from_numpy(a).to(cuda_dev), torch.from_numpy(b).to(cuda_dev), 60, 200)
+    for r in range(64):
+        ri, rs = o.rrf_ids(a[r].tolist(), b[r].tolist(), 60)
+        assert int(counts[r]) == len(ri)
+        assert ids[r, : len(ri)].tolist() == ri
+        assert scores[r, : len(ri)].tolist() == rs
+
+
+def test_synthetic_corpus_is_shard_invariant_and_normalised(cuda_dev):
+    from hybrid_rag_colbertv2_b200.synth import synth_store
+    full = synth_store(1000, 32, 512, seed=5, device=cuda_dev)
+    assert full.n_docs == 1000
+    n = full.tokens.float().norm(dim=-1)
+    assert float((n - 1).abs().max()) < 2e-2
+    parts = [synth_store(1000, 32, 512, seed=5, device=cuda_dev, rank=r, world_size=4) for r in range(4)]
+    assert sum(p.n_docs for p in parts) == 1000
+    assert torch.equal(torch.cat([p.tokens for p in parts]), full.tokens)
+    assert [p.doc_id_base for p in parts] == [0] + list(np.cumsum([p.n_docs for p in parts])[:-1])
+    other = synth_store(1000, 32, 512, seed=6, device=cuda_dev)
+    assert not torch.equal(other.tokens[:100], full.tokens[:100])
+    assert abs(float(full.tokens.float().mean())) < 1e-2
+
+
+def test_sharded_search_equals_single_gpu(cuda_dev):
+    """G shards simulated sequentially on one GPU: merged top-k == unsharded top-k, bit-exact."""
+    import hybrid_rag_colbertv2_b200 as hrc
+    from hybrid_rag_colbertv2_b200.synth import plant, synth_queries, synth_store
+    L = _lib()
+    full = synth_store(20_000, 32, 200, seed=21, device=cuda_dev)
+    q = synth_queries(3, 32, device=cuda_dev)
+    plant(full, q, n_planted=40)
+    cfg = hrc.RAGConfig()
+    one = hrc.JinaColBERTRetriever(cfg)
+    one.store = full
+    ref = one.search_keys(q, 100)
+    for world in (2, 4, 8):
+        gathered = []
+        for r in range(world):
+            rr = hrc.JinaColBERTRetriever(cfg)
+            rr.store = full.shard(r, world)
+            gathered.append(rr.search_keys(q, 100))
+        merged = L.topk_merge(torch.cat(gathered, 1).contiguous(), 100)
+        assert torch.equal(merged, ref), f"world={world}"
+
+
+def test_retriever_api_shapes_and_ranking(cuda_dev, tmp_path):
+    """search / rerank / _maxsim_score through the reference-shaped API, checked against the oracle."""
+    import hybrid_rag_colbertv2_b200 as hrc
+    cfg = hrc.RAGConfig(colbert_index_path=str(tmp_path / "colbert"))
+    r = hrc.JinaColBERTRetriever(cfg)
+    corpus = [f"document number {i} about topic {i % 7} and late interaction {i * 3}" for i in range(120)]
+    r.index(corpus)
+    assert os.path.exists(os.path.join(cfg.colbert_index_path, "index.pt"))
+    res = r.search(query="late interaction topic 3", k=10)
+    assert len(res) == 10 and all(sorted(x) == ["document_id", "score", "text"] for x in res)
+    assert all(isinstance(x["document_id"], int) and isinstance(x["score"], float) for x in res)
+    assert all(x["text"] == corpus[x["document_id"]] for x in res)
+    qe = r.model.encode("late interaction topic 3", convert_to_tensor=True)
+    exp = o.maxsim_scores(o.round_bf16(qe), r.store.tokens.float().cpu(), r.store.offsets.cpu())[0]
+    assert o.check_ranking([x["document_id"] for x in res], [x["score"] for x in res], exp, 10, RTOL) is None
+    assert len(r.search("anything", k=1000)) == 120                                  # k > N clamps (:767)
+    # rerank: result_index indexes the input list
+    docs = [corpus[i] for i in (5, 80, 33, 3, 17, 110)]
+    rr = r.rerank(query="late interaction topic 3", documents=docs, k=4)
+    assert len(rr) == 4 and [x["rank"] for x in rr] == [1, 2, 3, 4]
+    assert all(sorted(x) == ["rank", "result_index", "score", "text"] for x in rr)
+    assert all(x["text"] == docs[x["result_index"]] for x in rr)
+    sub = exp[[5, 80, 33, 3, 17, 110]]
+    assert o.check_ranking([x["result_index"] for x in rr], [x["score"] for x in rr], sub, 4, RTOL) is None
+    assert len(r.rerank("q", docs[:3], k=10)) == 3
+    # load() round trip, and the reference's dense index.pt layout
+    r2 = hrc.JinaColBERTRetriever(cfg)
+    r2.load()
+    assert torch.equal(r2.store.tokens, r.store.tokens) and r2.corpus == corpus
+    dense = torch.nn.functional.normalize(torch.randn(30, 16, 128), dim=-1)
+    os.makedirs(tmp_path / "ref", exist_ok=True)
+    torch.save({"embeddings": dense, "corpus": [f"doc {i}" for i in range(30)]}, tmp_path / "ref" / "index.pt")
+    r3 = hrc.JinaColBERTRetriever(hrc.RAGConfig(colbert_index_path=str(tmp_path / "ref")))
+    r3.load()
+    assert r3.store.n_docs == 30 and r3.store.total_tokens == 480
+    # _maxsim_score: shapes and squeeze of :813-831, values = true MaxSim
+    q1 = torch.nn.functional.normalize(torch.randn(32, 128), dim=-1)
+    s = r3._maxsim_score(q1, dense)
+    assert s.shape == (30,)
+    _assert_scores(s, o.maxsim_dense(o.round_bf16(q1), o.round_bf16(dense)), "_maxsim_score")
+    assert r3._maxsim_score(torch.stack([q1, q1]), dense).shape == (2, 30)
+    assert r3._maxsim_score(q1, dense[0]).dim() == 0                                 # 2-D docs = one document
+    with pytest.raises(IndexError):
+        r3._maxsim_score(torch.randn(128), dense)
+    # N == 1 works here (the reference raises TypeError)
+    r3.index_embeddings(dense[:1])
+    assert len(r3.search("x", k=5)) == 1
+
+
+def test_hybrid_retrieve_matches_stagewise_oracle(cuda_dev, tmp_path):
+    import hybrid_rag_colbertv2_b200 as hrc
+    cfg = hrc.RAGConfig(colbert_index_path=str(tmp_path / "colbert"), colbert_top_k=30, bm25_top_k=30,
+                        rerank_candidates=20, final_top_k=5)
+    idx = hrc.DualIndexer(cfg)
+    corpus = [f"chunk {i} alpha beta {i % 11} gamma {i % 5}" for i in range(200)]
+    idx.build_colbert_index(corpus)
+    rng = np.random.default_rng(8)
+    bm25_ids = rng.permutation(200)[:30].tolist()
+
+    def bm25(query, k):
+        return [{"chunk_id": int(i), "score": 1.0 / (j + 1), "source": "bm25"} for j, i in enumerate(bm25_ids[:k])]
+
+    h = hrc.HybridRetriever(cfg, idx, None, bm25_search=bm25, verbose=False)
+    out = h.retrieve("alpha gamma 3")
+    assert len(out) == 5 and [x["rank"] for x in out] == [1, 2, 3, 4, 5]
+    assert all(sorted(x) == sorted(["chunk_id", "text", "document_id", "heading_path", "has_images", "metadata",
+                                    "score", "rank"]) for x in out)
+    assert set(h.last_timings) == {"bm25", "colbert", "fusion", "fetch", "rerank", "total"}
+    # stage-wise oracle
+    retr = idx.colbert_retriever
+    qe = o.round_bf16(retr.model.encode("alpha gamma 3", convert_to_tensor=True))
+    scores = o.maxsim_scores(qe, retr.store.tokens.float().cpu(), retr.store.offsets.cpu())[0]
+    col = h._colbert_search("alpha gamma 3", 30)
+    assert o.check_ranking([c["chunk_id"] for c in col], [c["score"] for c in col], scores, 30, RTOL) is None
+    fused = h._reciprocal_rank_fusion(bm25("q", 30), col)
+    assert fused == o.rrf_reference(bm25("q", 30), col)                          # ids, fp64 scores, order
+    cand = [f["chunk_id"] for f in fused[:20]]
+    assert o.check_ranking([cand.index(x["chunk_id"]) for x in out], [x["score"] for x in out],
+                           scores[cand], 5, RTOL) is None
+    # batched device pipeline gives the same ids
+    ids, sc = h.retrieve_batch(qe.unsqueeze(0), torch.tensor([bm25_ids], dtype=torch.int32), top_k_final=5)
+    assert ids[0].tolist() == [x["chunk_id"] for x in out]
+
+
+def test_full_size_properties_c2(cuda_dev):
+    """BASELINE config C2 at full size (1M docs x 128 tokens, 32.8 GB): size-independent checks."""
+    import hybrid_rag_colbertv2_b200 as hrc
+    from hybrid_rag_colbertv2_b200.synth import plant, synth_queries, synth_store
+    L = _lib()
+    free, _ = torch.cuda.mem_get_info()
+    n_docs = 1_000_000 if free > 60e9 else 100_000
+    store = synth_store(n_docs, 128, 128, seed=20260102, device=cuda_dev)
+    q = synth_queries(1, 32, device=cuda_dev)
+    planted = plant(store, q, n_planted=200)
+    r = hrc.JinaColBERTRetriever(hrc.RAGConfig())
+    r.store = store
+    scores = r.score_embeddings(q)
+    assert scores.shape == (1, n_docs) and bool(torch.isfinite(scores).all())
+    # (1) a random sample of documents + all planted ones re-scored by the oracle
+    g = torch.Generator().manual_seed(1)
+    sample = torch.cat([torch.randint(0, n_docs, (3000,), generator=g), planted[0]])
+    sub_tok = store.tokens.view(n_docs, 128, 128)[sample.to(cuda_dev)].reshape(-1, 128).float().cpu()
+    exp = o.maxsim_scores(q.float().cpu(), sub_tok, torch.arange(0, sample.numel() * 128 + 1, 128))[0]
+    _assert_scores(scores[0, sample.to(cuda_dev)], exp, "C2 sample")
+    # (2) SIMT path agrees on the same sample through the candidate entry point
+    simt = L.maxsim_scores_ids(store.tokens, store.offsets, sample.to(torch.int32).unsqueeze(0).to(cuda_dev), q,
+                               path=L.PATH_SIMT)
+    _assert_scores(simt[0], exp, "C2 sample simt")
+    # (3) top-100: sorted, unique, scores equal the score array, nothing outside beats the k-th
+    ids, sc = r.search_embeddings(q, 100)
+    ids_c, sc_c = ids[0].cpu(), sc[0].cpu()
+    assert len(set(ids_c.tolist())) == 100 and bool((sc_c[:-1] >= sc_c[1:]).all())
+    assert torch.equal(scores[0, ids[0].to(torch.int64)].cpu(), sc_c)
+    assert int((scores[0] > sc_c[-1]).sum()) <= 99
+    tv, ti = torch.topk(scores[0], 100)
+    assert torch.equal(tv.cpu(), sc_c)
+    # (4) the planted documents dominate the ranking, in the oracle's order
+    top_planted = [i for i in ids_c.tolist() if i in set(planted[0].tolist())]
+    assert len(top_planted) >= 90
+    full_exp = torch.full((n_docs,), float('-inf'))
+    full_exp[sample] = exp
+    assert o.check_ranking(ids_c.tolist()[:50], sc_c.tolist()[:50], full_exp, 50, RTOL) is None
+    # (5) shard invariance: scores of a 4-way document split are bit-identical
+    parts = [L.maxsim_scores(s.tokens, s.offsets, q) for s in (store.shard(rk, 4) for rk in range(4))]
+    assert torch.equal(torch.cat(parts, 1), scores)
