@@ -34,6 +34,7 @@ constexpr int kTileN = 128;                       // document tokens per tile (M
 constexpr int kTileBytes = kTileN * HRC_DIM * 2;  // 32 KB
 constexpr int kHalfTileBytes = kTileBytes / 2;    // one 64-dim (128-byte-row) slab
 constexpr int kQTileBytes = 128 * HRC_DIM * 2;    // 128 query rows x 128 dims, 32 KB
+constexpr int kSlotBytes = 32 * 128;              // one 32-row query slot inside a 64-dim slab
 constexpr int kTmemCols = 512;
 constexpr int kThreads = 192;
 constexpr int kEpiWarp0 = 2;
@@ -51,6 +52,7 @@ struct TcParams {
   int n_segments;           // corpus mode: CTAs along the corpus
   int n_qgroups;            // corpus mode: query groups (4*MT queries each)
   int n_stages;             // smem ring depth
+  int slots_used;           // distinct queries per A tile: 1, 2 or 4 (each replicated 4/slots_used times)
   uint64_t doc_policy;      // L2 policy for document tiles (evict-first when read once)
 };
 
@@ -81,6 +83,31 @@ __device__ __forceinline__ int64_t lower_bound_doc(const int64_t* __restrict__ o
     if (offsets[mid] < target) lo = mid + 1; else hi = mid;
   }
   return lo;
+}
+
+// max of 32 accumulator columns as a balanced tree (no 32-deep dependent chain)
+__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
+  float t[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) t[i] = fmaxf(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+#pragma unroll
+  for (int w = 8; w > 0; w >>= 1) {
+#pragma unroll
+    for (int i = 0; i < w; ++i) t[i] = fmaxf(t[i], t[i + w]);
+  }
+  return t[0];
+}
+// same, over the columns whose bit is set (a document that starts or ends inside the chunk)
+__device__ __forceinline__ float max32_masked(const uint32_t (&v)[32], uint32_t bits) {
+  float t[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) t[i] = ((bits >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY;
+#pragma unroll
+  for (int w = 16; w > 0; w >>= 1) {
+#pragma unroll
+    for (int i = 0; i < w; ++i) t[i] = fmaxf(t[i], t[i + w]);
+  }
+  return t[0];
 }
 
 template <int MT>
@@ -162,8 +189,15 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
       mbar_arrive_expect_tx(qfull, MT * kQTileBytes);
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        tma_load_3d(sQ + mt * kQTileBytes, &tmap_q, qfull, 0, 0, q_base + 4 * mt, kEvictLast);
-        tma_load_3d(sQ + mt * kQTileBytes + kQTileBytes / 2, &tmap_q, qfull, 64, 0, q_base + 4 * mt, kEvictLast);
+        // slot g (32 rows of the A tile) holds query (g % slots_used): with fewer than 4 queries the
+        // query is REPLICATED, so every epilogue warp sees complete rows and takes its own documents.
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int q = q_base + 4 * mt + (g % p.slots_used);
+          uint8_t* dst = sQ + mt * kQTileBytes + g * kSlotBytes;
+          tma_load_3d(dst, &tmap_q, qfull, 0, 0, q, kEvictLast);
+          tma_load_3d(dst + kQTileBytes / 2, &tmap_q, qfull, 64, 0, q, kEvictLast);
+        }
       }
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < n_tiles; ++t) {
@@ -210,98 +244,116 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     }
   } else {
     // =============================== epilogue ==================================================
-    const int slot = warp & 3;                 // TMEM lanes 32*slot .. 32*slot+31
+    // Warp w owns TMEM lanes 32*slot.. (slot = w % 4).  slots_used (1, 2 or 4) queries occupy the A tile
+    // and each is replicated rep = 4 / slots_used times; the warp of slot g scores query g % slots_used
+    // for the documents whose local index is congruent to g / slots_used modulo rep.  A warp therefore
+    // always owns WHOLE documents: no cross-warp combine, boundaries are warp-uniform.
+    const int slot = warp & 3;
     const uint32_t lane_base = uint32_t(slot * 32) << 16;
+    const int rep = 4 / p.slots_used;
+    const int residue = slot / p.slots_used;
     bool active[MT];
     int64_t out_row[MT];
     bool any_active = false;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      const int q = q_base + 4 * mt + slot;
-      active[mt] = (p.cand_ids == nullptr) ? (q < p.n_queries) : (mt == 0 && slot == 0);
+      const int q = q_base + 4 * mt + (slot % p.slots_used);
+      active[mt] = q < p.n_queries;
       out_row[mt] = int64_t(q) * p.n_items;
       any_active |= active[mt];
     }
     const int n_docs_seg = int(doc_end - doc_begin);
-    // document-boundary walk state; token positions are relative to tok_begin
-    int cur = 0;       // local index of the document being accumulated
-    int bj = 0;        // position of `cur` inside the 32-entry register batch of doc ends
+
+    // Document ends (token positions relative to tok_begin) are fetched 32 at a time, one per lane,
+    // one batch ahead, and broadcast with a shuffle.
+    int batch = 0;
     int ends = INT_MAX, ends_next = INT_MAX;
-    auto load_ends = [&](int batch) -> int {
-      const int d = batch * 32 + lane;
+    auto load_ends = [&](int b) -> int {
+      const int d = b * 32 + lane;
       return (d < n_docs_seg) ? int(p.offsets[doc_begin + d + 1] - tok_begin) : INT_MAX;
     };
+    auto end_of = [&](int d) -> int {   // d non-decreasing over calls, -1 <= d < n_docs_seg
+      if (d < 0) return 0;
+      while ((d >> 5) > batch) {
+        ends = ends_next;
+        ++batch;
+        ends_next = load_ends(batch + 1);
+      }
+      return __shfl_sync(0xffffffffu, ends, d & 31);
+    };
+
+    int my = residue;                       // local index of the document this warp is accumulating
+    bool have_doc = any_active && my < n_docs_seg;
+    int s_tok = 0, e_tok = 0;               // its token range
     if (any_active) {
       ends = load_ends(0);
       ends_next = load_ends(1);
     }
-    int cur_end = __shfl_sync(0xffffffffu, ends, 0);
+    if (have_doc) {
+      s_tok = end_of(my - 1);
+      e_tok = end_of(my);
+    }
     float m[MT];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) m[mt] = -INFINITY;
 
-    auto flush = [&]() {   // document `cur` is complete: emit its score(s), move to the next one
+    auto finish_doc = [&]() {   // emit the score(s) of document `my`, move to this warp's next document
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        const float s = warp_sum(m[mt]);
+        const float sc = warp_sum(m[mt]);
         if (lane == 0 && active[mt]) {
-          const int64_t col = (p.cand_ids == nullptr) ? (doc_begin + cur) : item;
-          p.scores[out_row[mt] + col] = s;
+          const int64_t col = (p.cand_ids == nullptr) ? (doc_begin + my) : item;
+          p.scores[out_row[mt] + col] = sc;
         }
         m[mt] = -INFINITY;
       }
-      ++cur;
-      if (++bj == 32) {
-        bj = 0;
-        ends = ends_next;
-        ends_next = load_ends(cur / 32 + 1);
+      my += rep;
+      have_doc = my < n_docs_seg;
+      if (have_doc) {
+        s_tok = end_of(my - 1);
+        e_tok = end_of(my);
       }
-      cur_end = __shfl_sync(0xffffffffu, ends, bj);
     };
 
     int ts = 0; uint32_t tphase = 0;
     for (int t = 0; t < n_tiles; ++t) {
       mbar_wait_wd(&tfull[ts], tphase);
       tc_fence_after_sync();
-      if (any_active) {
-#pragma unroll 1
-        for (int c32 = 0; c32 < kTileN / 32; ++c32) {
-          uint32_t v[MT][32];
+      const int tile0 = t * kTileN, tile1 = tile0 + kTileN;
+      int cached = -1;                      // 32-column chunk currently held in v[]
+      uint32_t v[MT][32];
+      while (have_doc && s_tok < tile1) {
+        const int lo = max(s_tok, tile0), hi = min(e_tok, tile1);
+        if (hi > lo) {
+          const int c_first = (lo - tile0) >> 5, c_last = (hi - 1 - tile0) >> 5;
+          for (int c32 = c_first; c32 <= c_last; ++c32) {
+            if (c32 != cached) {
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt)
-            tmem_ld_32x32(tmem_base + lane_base + uint32_t((ts * MT + mt) * kTileN + c32 * 32), v[mt]);
-          tmem_ld_wait();
-          const int col0 = t * kTileN + c32 * 32;
-          while (cur_end <= col0 && cur < n_docs_seg) flush();
-          if (cur_end >= col0 + 32) {
-            // no document boundary inside this 32-column chunk
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              float x = m[mt];
-#pragma unroll
-              for (int c = 0; c < 32; ++c) x = fmaxf(x, __uint_as_float(v[mt][c]));
-              m[mt] = x;
+              for (int mt = 0; mt < MT; ++mt)
+                tmem_ld_32x32(tmem_base + lane_base + uint32_t((ts * MT + mt) * kTileN + c32 * 32), v[mt]);
+              tmem_ld_wait();
+              cached = c32;
             }
-          } else {
+            const int cbase = tile0 + c32 * 32;
+            const int a = max(lo - cbase, 0), b = min(hi - cbase, 32);
+            if (a == 0 && b == 32) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              if (c > 0) {
-                while (cur_end == col0 + c && cur < n_docs_seg) flush();
-              }
+              for (int mt = 0; mt < MT; ++mt) m[mt] = fmaxf(m[mt], max32(v[mt]));
+            } else {
+              const uint32_t bits = (b >= 32 ? 0xffffffffu : ((1u << b) - 1u)) & ~((1u << a) - 1u);
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) m[mt] = fmaxf(m[mt], __uint_as_float(v[mt][c]));
+              for (int mt = 0; mt < MT; ++mt) m[mt] = fmaxf(m[mt], max32_masked(v[mt], bits));
             }
           }
         }
+        if (e_tok <= tile1) finish_doc(); else break;   // else: the document continues in the next tile
       }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[ts]);
       if (++ts == kTileStages) { ts = 0; tphase ^= 1; }
     }
-    if (any_active) {
-      while (cur < n_docs_seg) flush();
-    }
+    while (have_doc) finish_doc();          // trailing empty documents (no tokens, no tile): -inf
   }
 
   tc_fence_before_sync();
@@ -384,7 +436,7 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
   {
     cuuint64_t dims[3] = {HRC_DIM, (cuuint64_t)lq, (cuuint64_t)n_queries};
     cuuint64_t strides[2] = {HRC_DIM * 2, (cuuint64_t)lq * HRC_DIM * 2};
-    cuuint32_t box[3] = {64, 32, 4};
+    cuuint32_t box[3] = {64, 32, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&tmap_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d_queries), dims, strides,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -402,6 +454,7 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
   p.n_queries = n_queries;
   p.n_segments = 1;
   p.n_qgroups = 1;
+  p.slots_used = 1;
   p.doc_policy = kEvictFirst;
 
   if (d_cand_ids != nullptr) {
@@ -414,9 +467,11 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
   if (n_queries <= 4) {
     p.n_qgroups = 1;
     p.n_stages = 6;
+    p.slots_used = n_queries == 1 ? 1 : (n_queries == 2 ? 2 : 4);
     return launch_mt<1>(tmap_d, tmap_q, p, dim3((unsigned)p.n_segments), stream);
   }
   p.n_qgroups = (n_queries + 7) / 8;
+  p.slots_used = 4;
   p.doc_policy = kEvictNormal;  // the other query groups re-read this tile from L2
   p.n_stages = 5;
   return launch_mt<2>(tmap_d, tmap_q, p, dim3((unsigned)(p.n_segments * p.n_qgroups)), stream);
