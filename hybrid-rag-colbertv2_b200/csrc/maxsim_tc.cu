@@ -22,6 +22,7 @@
 // query tokens per BASELINE.json north_star.  Algorithmic traffic: 256 B per document token.
 #include <cuda.h>
 #include <climits>
+#include <cstdlib>
 #include <cstdio>
 
 #include "hrc_common.cuh"
@@ -36,7 +37,10 @@ constexpr int kHalfTileBytes = kTileBytes / 2;    // one 64-dim (128-byte-row) s
 constexpr int kQTileBytes = 128 * HRC_DIM * 2;    // 128 query rows x 128 dims, 32 KB
 constexpr int kSlotBytes = 32 * 128;              // one 32-row query slot inside a 64-dim slab
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 192;
+// epilogue warps: 4 (one per TMEM lane group) for the HBM-bound MT=1 kernel, 8 (two per lane group,
+// splitting documents) for the tensor-bound MT=2 kernel whose epilogue handles two accumulators per tile
+__host__ __device__ constexpr int epi_warps(int mt) { return mt == 1 ? 4 : 8; }
+__host__ __device__ constexpr int cta_threads(int mt) { return (2 + epi_warps(mt)) * 32; }
 constexpr int kEpiWarp0 = 2;
 constexpr int kMaxSmem = 232448;                  // 227 KB opt-in limit per CTA
 constexpr uint32_t kIdesc = make_idesc_bf16_f32(128, kTileN);
@@ -53,6 +57,7 @@ struct TcParams {
   int n_qgroups;            // corpus mode: query groups (4*MT queries each)
   int n_stages;             // smem ring depth
   int slots_used;           // distinct queries per A tile: 1, 2 or 4 (each replicated 4/slots_used times)
+  int col_split;            // warps sharing a lane group split columns (1) or documents (0)
   uint64_t doc_policy;      // L2 policy for document tiles (evict-first when read once)
 };
 
@@ -111,10 +116,11 @@ __device__ __forceinline__ float max32_masked(const uint32_t (&v)[32], uint32_t 
 }
 
 template <int MT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(cta_threads(MT), 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_q,
                  const TcParams p) {
   constexpr int kTileStages = 4 / MT;  // accumulator ring: tiles in flight between MMA and epilogue
+  constexpr int kEpiWarps = epi_warps(MT);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -128,6 +134,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   uint64_t* qfull = bars + 24;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
   int64_t* seg = reinterpret_cast<int64_t*>(bars + 26);  // [0]=doc_begin [1]=doc_end [2]=tok_begin [3]=tok_end
+  float* xbuf = reinterpret_cast<float*>(bars + 32);     // [2][4][MT][32] partial maxima exchanged inside a lane group
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -167,7 +174,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     tma_prefetch_desc(&tmap_d);
     tma_prefetch_desc(&tmap_q);
     for (int i = 0; i < p.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < kTileStages; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < kTileStages; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
     mbar_init(qfull, 1);
     fence_mbar_init();
   }
@@ -250,8 +257,11 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     // always owns WHOLE documents: no cross-warp combine, boundaries are warp-uniform.
     const int slot = warp & 3;
     const uint32_t lane_base = uint32_t(slot * 32) << 16;
-    const int rep = 4 / p.slots_used;
-    const int residue = slot / p.slots_used;
+    constexpr int kSplit = kEpiWarps / 4;                // warps sharing one lane group split each tile's columns
+    const int sub = (warp - kEpiWarp0) >> 2;             // which column share this warp takes
+    const bool col_split = kSplit > 1 && p.col_split != 0;
+    const int rep = (4 / p.slots_used) * ((kSplit > 1 && !col_split) ? kSplit : 1);
+    const int residue = (kSplit > 1 && !col_split) ? (slot / p.slots_used) * kSplit + sub : slot / p.slots_used;
     bool active[MT];
     int64_t out_row[MT];
     bool any_active = false;
@@ -297,13 +307,30 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) m[mt] = -INFINITY;
 
+    int xpar = 0;                           // exchange-buffer parity (double buffered: one barrier per document)
     auto finish_doc = [&]() {   // emit the score(s) of document `my`, move to this warp's next document
+      if (col_split) {
+        // the warps of this lane group hold maxima over disjoint column shares: combine through smem
+        float* xb = xbuf + ((xpar * 4 + slot) * MT) * 32;
+        if (sub != 0) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) xb[mt * 32 + lane] = m[mt];
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(32 * kSplit) : "memory");
+        if (sub == 0) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) m[mt] = fmaxf(m[mt], xb[mt * 32 + lane]);
+        }
+        xpar ^= 1;
+      }
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        const float sc = warp_sum(m[mt]);
-        if (lane == 0 && active[mt]) {
-          const int64_t col = (p.cand_ids == nullptr) ? (doc_begin + my) : item;
-          p.scores[out_row[mt] + col] = sc;
+        if (sub == 0 || !col_split) {
+          const float sc = warp_sum(m[mt]);
+          if (lane == 0 && active[mt]) {
+            const int64_t col = (p.cand_ids == nullptr) ? (doc_begin + my) : item;
+            p.scores[out_row[mt] + col] = sc;
+          }
         }
         m[mt] = -INFINITY;
       }
@@ -327,6 +354,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
         if (hi > lo) {
           const int c_first = (lo - tile0) >> 5, c_last = (hi - 1 - tile0) >> 5;
           for (int c32 = c_first; c32 <= c_last; ++c32) {
+            if (col_split && ((c32 * kSplit) >> 2) != sub) continue;   // another warp's column share
             if (c32 != cached) {
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt)
@@ -384,14 +412,14 @@ EncodeTiledFn get_encode_fn() {
 template <int MT>
 int launch_mt(const CUtensorMap& tmap_d, const CUtensorMap& tmap_q, const TcParams& p, dim3 grid,
               cudaStream_t stream) {
-  const int smem_bytes = 1024 + MT * kQTileBytes + p.n_stages * kTileBytes + 512;
+  const int smem_bytes = 1024 + MT * kQTileBytes + p.n_stages * kTileBytes + 256 + (epi_warps(MT) > 4 ? 2 * 4 * MT * 32 * 4 : 0);
   static bool configured = false;
   if (!configured) {
     HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kMaxSmem));
     configured = true;
   }
-  maxsim_tc_kernel<MT><<<grid, kThreads, smem_bytes, stream>>>(tmap_d, tmap_q, p);
+  maxsim_tc_kernel<MT><<<grid, cta_threads(MT), smem_bytes, stream>>>(tmap_d, tmap_q, p);
   count_launch();
   HRC_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -455,6 +483,8 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
   p.n_segments = 1;
   p.n_qgroups = 1;
   p.slots_used = 1;
+  p.col_split = 0;   // measured: splitting documents beats splitting columns (1052 vs 970 TFLOP/s on C3)
+  if (const char* e = getenv("HRC_TC_COL_SPLIT")) p.col_split = atoi(e);
   p.doc_policy = kEvictFirst;
 
   if (d_cand_ids != nullptr) {
@@ -473,7 +503,7 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
   p.n_qgroups = (n_queries + 7) / 8;
   p.slots_used = 4;
   p.doc_policy = kEvictNormal;  // the other query groups re-read this tile from L2
-  p.n_stages = 5;
+  p.n_stages = 4;
   return launch_mt<2>(tmap_d, tmap_q, p, dim3((unsigned)(p.n_segments * p.n_qgroups)), stream);
 }
 

@@ -31,6 +31,22 @@ def timed(fn, steps, warmup=3):
     return e0.elapsed_time(e1) / steps
 
 
+class Clocks:
+    def __enter__(self):
+        import subprocess
+        self.p = subprocess.Popen(["nvidia-smi", "--id=0", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits",
+                                   "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        return self
+
+    def __exit__(self, *a):
+        import statistics
+        self.p.terminate()
+        rows = [l.split(",") for l in self.p.stdout.read().strip().splitlines() if "," in l]
+        sm = [float(r[0]) for r in rows] or [0.0]
+        pw = [float(r[1]) for r in rows] or [0.0]
+        self.sm_mhz, self.power_w, self.n = statistics.median(sm), statistics.median(pw), len(rows)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -87,12 +103,15 @@ def main():
                 q = synth_queries(nq, 32, device=dev)
                 out = torch.empty((nq, store.n_docs), dtype=torch.float32, device=dev)
                 steps = 3 if nq >= 64 else 5
-                ms = timed(lambda: _lib.maxsim_scores(store.tokens, store.offsets, q, out=out), steps, warmup=3)
+                with Clocks() as ck:
+                    ms = timed(lambda: _lib.maxsim_scores(store.tokens, store.offsets, q, out=out), steps, warmup=3)
                 ms_s = timed(lambda: r.search_keys(q, 100), steps, warmup=1)
                 flops = 2.0 * 32 * 128 * nq * tokens
                 tfs = flops / (ms * 1e-3) / 1e12
                 print(json.dumps({"config": f"C3 batched: {nq} queries x 32 over {args.docs} docs x U(32..512)",
                                   "tokens": tokens, "kernel_ms": ms, "search_ms": ms_s, "useful_TFLOPs": tfs,
+                                  "sm_mhz": ck.sm_mhz, "power_w": ck.power_w, "col_split": os.environ.get("HRC_TC_COL_SPLIT", "1"),
+                                  "frac_of_clock_peak": tfs / (8192 * 148 * ck.sm_mhz * 1e6 / 1e12) if ck.sm_mhz else None,
                                   "frac_tensor_sustained": tfs / tf_sus, "frac_tensor_burst": tfs / tf_burst,
                                   "pairs_per_s": nq * store.n_docs / (ms_s * 1e-3),
                                   "corpus_GB": tokens * 256 / 1e9,
