@@ -4,26 +4,35 @@
 // Data layout in HBM
 //   tokens  : bf16 [total_tokens][128], packed, padding-free           (TMA map: 2-D, 128B swizzle)
 //   offsets : int64 [n_docs + 1] CSR document boundaries
-//   queries : bf16 [n_queries][lq][128], lq <= 32                      (TMA map: 3-D, zero-filled
-//             out of bounds, so each query lands in a 32-row "slot" of the 128-row A tile)
+//   queries : bf16 [n_queries][lq][128], lq <= 32
 //
 // One CTA = one contiguous run of whole documents ("segment") x one group of 4*MT queries.
-//   warp 0      : TMA producer  — streams 128-token x 128-dim tiles (32 KB) through a ring
-//   warp 1      : MMA issuer    — per tile and M-tile: 8 x tcgen05.mma (M=128, N=128, K=16),
-//                                 accumulator = 128 TMEM columns; owns TMEM alloc/dealloc
-//   warps 2..5  : epilogue      — warp w owns TMEM lanes 32*(w%4).. = query slot (w%4): thread i
-//                                 holds query token i of that query, so the max over document
-//                                 tokens is a per-thread reduction over TMEM columns and document
-//                                 boundaries are warp-uniform; a doc's score is one warp_sum.
-// MMA orientation: A = queries (M = 4 slots x 32 tokens), B = document tokens (N), so that
+//   warp 0      : TMA producer  — streams TN-token x 128-dim tiles through a shared-memory ring
+//   warp 1      : MMA issuer    — per tile and M-tile: 8 x tcgen05.mma (M=128, N=TN, K=16), accumulator =
+//                                 TN TMEM columns; owns TMEM alloc/dealloc
+//   warps 2..   : epilogue      — a warp owns TMEM lanes 32*(w%4).. = one query slot: thread i holds query
+//                                 token i, so the max over a document's tokens is a per-thread reduction
+//                                 over TMEM columns, document boundaries are warp-uniform, and a document's
+//                                 score is one warp_sum.  Every warp owns WHOLE documents (no combine).
+// MMA orientation: A = queries (M = 4 slots x 32 tokens), B = document tokens (N):
 // D[row = query token][col = doc token].
+//
+// Two instantiations:
+//   <MT=1, TN=128, TS=false>  HBM-bound (<= 4 queries): A and B from shared memory (SS), 6-stage ring,
+//        4 accumulator stages; with fewer than 4 queries the query is REPLICATED over the free slots so
+//        all four epilogue warps work (each takes every rep-th document).
+//   <MT=2, TN=128, TS=false>  tensor-bound (batched, 8 queries per CTA pass): 8 epilogue warps (two per lane
+//        group, splitting documents), 2 x 2 accumulators.  This is the default batched kernel.
+//   <MT=2, TN=96,  TS=true>   alternative (env HRC_TC_TS=1): the query tiles live in TMEM (A operand from
+//        TMEM, written with tcgen05.st), TMEM = 128 (Q) + 2 x 2 x 96 (acc).  Halves the operand traffic from
+//        shared memory, but measured slower on C3 (1069 vs 1123 TFLOP/s), so it is not the default.
 //
 // Reference semantics: local_rag_complete.py:807-812 (docstring), :813-817 (shapes), summed over
 // query tokens per BASELINE.json north_star.  Algorithmic traffic: 256 B per document token.
 #include <cuda.h>
 #include <climits>
-#include <cstdlib>
 #include <cstdio>
+#include <cstdlib>
 
 #include "hrc_common.cuh"
 
@@ -31,33 +40,30 @@ namespace hrc {
 
 namespace {
 
-constexpr int kTileN = 128;                       // document tokens per tile (MMA N)
-constexpr int kTileBytes = kTileN * HRC_DIM * 2;  // 32 KB
-constexpr int kHalfTileBytes = kTileBytes / 2;    // one 64-dim (128-byte-row) slab
-constexpr int kQTileBytes = 128 * HRC_DIM * 2;    // 128 query rows x 128 dims, 32 KB
+constexpr int kQTileBytes = 128 * HRC_DIM * 2;    // 128 query rows x 128 dims, 32 KB (SS mode only)
 constexpr int kSlotBytes = 32 * 128;              // one 32-row query slot inside a 64-dim slab
 constexpr int kTmemCols = 512;
-// epilogue warps: 4 (one per TMEM lane group) for the HBM-bound MT=1 kernel, 8 (two per lane group,
-// splitting documents) for the tensor-bound MT=2 kernel whose epilogue handles two accumulators per tile
-__host__ __device__ constexpr int epi_warps(int mt) { return mt == 1 ? 4 : 8; }
-__host__ __device__ constexpr int cta_threads(int mt) { return (2 + epi_warps(mt)) * 32; }
 constexpr int kEpiWarp0 = 2;
 constexpr int kMaxSmem = 232448;                  // 227 KB opt-in limit per CTA
-constexpr uint32_t kIdesc = make_idesc_bf16_f32(128, kTileN);
+
+__host__ __device__ constexpr int epi_warps(int mt) { return mt == 1 ? 4 : 8; }
+__host__ __device__ constexpr int cta_threads(int mt) { return (2 + epi_warps(mt)) * 32; }
 
 struct TcParams {
   const int64_t* offsets;
   const int32_t* cand_ids;  // nullptr: corpus mode
+  const __nv_bfloat16* queries;
   float* scores;
   int64_t n_docs;
   int64_t total_tokens;
   int64_t n_items;          // row stride of scores (n_docs, or n_cand)
   int n_queries;
+  int lq;
   int n_segments;           // corpus mode: CTAs along the corpus
   int n_qgroups;            // corpus mode: query groups (4*MT queries each)
   int n_stages;             // smem ring depth
   int slots_used;           // distinct queries per A tile: 1, 2 or 4 (each replicated 4/slots_used times)
-  int col_split;            // warps sharing a lane group split columns (1) or documents (0)
+  int debug;                // perf experiments only (env HRC_TC_DEBUG): 1 = skip epilogue math, 2 = skip TMA of documents
   uint64_t doc_policy;      // L2 policy for document tiles (evict-first when read once)
 };
 
@@ -115,26 +121,65 @@ __device__ __forceinline__ float max32_masked(const uint32_t (&v)[32], uint32_t 
   return t[0];
 }
 
-template <int MT>
+// D[tmem] (+)= A[tmem] * B[smem]^T : the A operand (queries) is read from tensor memory.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 64 consecutive 32-bit columns, registers -> TMEM: thread i writes lane (base_lane + i).
+__device__ __forceinline__ void tmem_st_32x64(uint32_t taddr, const uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x64.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, "
+      "%33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, "
+      "%49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63, %64};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]), "r"(v[32]), "r"(v[33]), "r"(v[34]), "r"(v[35]), "r"(v[36]),
+      "r"(v[37]), "r"(v[38]), "r"(v[39]), "r"(v[40]), "r"(v[41]), "r"(v[42]), "r"(v[43]), "r"(v[44]), "r"(v[45]),
+      "r"(v[46]), "r"(v[47]), "r"(v[48]), "r"(v[49]), "r"(v[50]), "r"(v[51]), "r"(v[52]), "r"(v[53]), "r"(v[54]),
+      "r"(v[55]), "r"(v[56]), "r"(v[57]), "r"(v[58]), "r"(v[59]), "r"(v[60]), "r"(v[61]), "r"(v[62]), "r"(v[63])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+template <int MT, int TN, bool TS>
 __global__ void __launch_bounds__(cta_threads(MT), 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_q,
                  const TcParams p) {
-  constexpr int kTileStages = 4 / MT;  // accumulator ring: tiles in flight between MMA and epilogue
   constexpr int kEpiWarps = epi_warps(MT);
+  constexpr int kSplit = kEpiWarps / 4;                 // warps sharing one TMEM lane group split the documents
+  constexpr int kTileBytes = TN * HRC_DIM * 2;
+  constexpr int kHalfTileBytes = kTileBytes / 2;        // one 64-dim (128-byte-row) slab
+  constexpr int kQCols = TS ? MT * 64 : 0;              // TMEM columns holding the query tiles (bf16 pairs)
+  constexpr int kTileStages = (kTmemCols - kQCols) / (MT * TN);   // tiles in flight between MMA and epilogue
+  constexpr uint32_t kIdesc = make_idesc_bf16_f32(128, TN);
+  static_assert(TN % 32 == 0 && TN % 16 == 0 && TN <= 256 && kTileStages >= 2, "bad tile configuration");
+  static_assert(kTileBytes % 2048 == 0, "tile slabs must stay 1024-byte aligned for the 128B swizzle");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                              // MT x 32 KB
-  uint8_t* sD = smem + MT * kQTileBytes;           // n_stages x 32 KB
+  uint8_t* sQ = smem;                                        // SS: MT x 32 KB query tiles
+  uint8_t* sD = smem + (TS ? 0 : MT * kQTileBytes);          // n_stages x tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + p.n_stages * kTileBytes);
-  uint64_t* full = bars;                           // [n_stages]   TMA -> MMA
-  uint64_t* empty = bars + 8;                      // [n_stages]   MMA -> TMA
-  uint64_t* tfull = bars + 16;                     // [kTileStages] MMA -> epilogue
-  uint64_t* tempty = bars + 20;                    // [kTileStages] epilogue -> MMA
-  uint64_t* qfull = bars + 24;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
-  int64_t* seg = reinterpret_cast<int64_t*>(bars + 26);  // [0]=doc_begin [1]=doc_end [2]=tok_begin [3]=tok_end
-  float* xbuf = reinterpret_cast<float*>(bars + 32);     // [2][4][MT][32] partial maxima exchanged inside a lane group
+  uint64_t* full = bars;                           // [n_stages]    TMA -> MMA
+  uint64_t* empty = bars + 10;                     // [n_stages]    MMA -> TMA
+  uint64_t* tfull = bars + 20;                     // [kTileStages] MMA -> epilogue
+  uint64_t* tempty = bars + 24;                    // [kTileStages] epilogue -> MMA
+  uint64_t* qfull = bars + 28;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+  int64_t* seg = reinterpret_cast<int64_t*>(bars + 30);  // [0]=doc_begin [1]=doc_end [2]=tok_begin [3]=tok_end
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -172,10 +217,10 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_d);
-    tma_prefetch_desc(&tmap_q);
+    if (!TS) tma_prefetch_desc(&tmap_q);
     for (int i = 0; i < p.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < kTileStages; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
-    mbar_init(qfull, 1);
+    mbar_init(qfull, TS ? 4 : 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -187,39 +232,52 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   tc_fence_after_sync();
 
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_base = tmem_base + kQCols;
   const int64_t doc_begin = seg[0], doc_end = seg[1], tok_begin = seg[2], tok_end = seg[3];
-  const int n_tiles = int((tok_end - tok_begin + kTileN - 1) / kTileN);
+  const int n_tiles = int((tok_end - tok_begin + TN - 1) / TN);
 
   if (warp == 0) {
     // =============================== TMA producer =============================================
-    if (lane == 0 && n_tiles > 0) {
-      mbar_arrive_expect_tx(qfull, MT * kQTileBytes);
+    // (elect.sync, not `lane == 0`: the compiler then knows a single thread runs this and feeds the
+    //  uniform datapath directly instead of emitting a per-instruction uniformisation loop)
+    if (n_tiles > 0 && elect_one()) {
+      if constexpr (!TS) {
+        mbar_arrive_expect_tx(qfull, MT * kQTileBytes);
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        // slot g (32 rows of the A tile) holds query (g % slots_used): with fewer than 4 queries the
-        // query is REPLICATED, so every epilogue warp sees complete rows and takes its own documents.
+        for (int mt = 0; mt < MT; ++mt) {
+          // slot g (32 rows of the A tile) holds query (g % slots_used): with fewer than 4 queries the
+          // query is REPLICATED, so every epilogue warp sees complete rows and takes its own documents.
+          // Rows >= lq and queries >= n_queries are out of bounds of the map and arrive as zeros.
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int q = q_base + 4 * mt + (g % p.slots_used);
-          uint8_t* dst = sQ + mt * kQTileBytes + g * kSlotBytes;
-          tma_load_3d(dst, &tmap_q, qfull, 0, 0, q, kEvictLast);
-          tma_load_3d(dst + kQTileBytes / 2, &tmap_q, qfull, 64, 0, q, kEvictLast);
+          for (int g = 0; g < 4; ++g) {
+            const int q = q_base + 4 * mt + (g % p.slots_used);
+            uint8_t* dst = sQ + mt * kQTileBytes + g * kSlotBytes;
+            tma_load_3d(dst, &tmap_q, qfull, 0, 0, q, kEvictLast);
+            tma_load_3d(dst + kQTileBytes / 2, &tmap_q, qfull, 64, 0, q, kEvictLast);
+          }
         }
       }
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < n_tiles; ++t) {
         mbar_wait_wd(&empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full[stage], kTileBytes);
-        const int row = int(tok_begin + int64_t(t) * kTileN);
-        uint8_t* dst = sD + stage * kTileBytes;
-        tma_load_2d(dst, &tmap_d, &full[stage], 0, row, p.doc_policy);
-        tma_load_2d(dst + kHalfTileBytes, &tmap_d, &full[stage], 64, row, p.doc_policy);
+        if (p.debug & 2) {
+          mbar_arrive(&full[stage]);
+        } else {
+          mbar_arrive_expect_tx(&full[stage], kTileBytes);
+          const int row = int(tok_begin + int64_t(t) * TN);
+          uint8_t* dst = sD + stage * kTileBytes;
+          tma_load_2d(dst, &tmap_d, &full[stage], 0, row, p.doc_policy);
+          tma_load_2d(dst + kHalfTileBytes, &tmap_d, &full[stage], 64, row, p.doc_policy);
+        }
         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================================
-    if (lane == 0 && n_tiles > 0) {
+    // The whole warp walks the tile loop and waits on the barriers; one elected lane issues.  Gating with
+    // elect.sync (rather than `lane == 0`) matters: otherwise every tcgen05.mma is preceded by an
+    // ELECT/R2UR.BROADCAST loop and the issue rate, not the tensor core, bounds the kernel.
+    if (n_tiles > 0) {
       mbar_wait_wd(qfull, 0);
       tc_fence_after_sync();
       const uint32_t sQ_addr = smem_u32(sQ);
@@ -230,38 +288,42 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
         mbar_wait_wd(&tempty[ts], tphase ^ 1);
         mbar_wait_wd(&full[stage], phase);
         tc_fence_after_sync();
-        const uint32_t b_addr = sD_addr + stage * kTileBytes;
+        if (elect_one()) {
+          const uint32_t b_addr = sD_addr + stage * kTileBytes;
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const uint32_t a_addr = sQ_addr + mt * kQTileBytes;
-          const uint32_t d_tmem = tmem_base + uint32_t((ts * MT + mt) * kTileN);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint32_t d_tmem = acc_base + uint32_t((ts * MT + mt) * TN);
 #pragma unroll
-          for (int k = 0; k < HRC_DIM / 16; ++k) {
-            // k-th 16-element K slice: slab (k / 4), 32 bytes per slice inside the 128-byte row
-            const uint32_t koff = (k >> 2) * kHalfTileBytes + (k & 3) * 32;
-            umma_bf16_ss(d_tmem, make_kmajor_sw128_desc(a_addr + koff),
-                         make_kmajor_sw128_desc(b_addr + koff), kIdesc, k > 0 ? 1u : 0u);
+            for (int k = 0; k < HRC_DIM / 16; ++k) {
+              // k-th 16-element K slice of B: slab (k / 4), 32 bytes per slice inside the 128-byte row
+              const uint64_t b_desc = make_kmajor_sw128_desc(b_addr + (k >> 2) * kHalfTileBytes + (k & 3) * 32);
+              if constexpr (TS) {
+                // A from TMEM: lane = query row, 8 columns (16 bf16) per K slice
+                umma_bf16_ts(d_tmem, tmem_base + uint32_t(mt * 64 + k * 8), b_desc, kIdesc, k > 0 ? 1u : 0u);
+              } else {
+                const uint32_t a_addr = sQ_addr + mt * kQTileBytes + (k >> 2) * (kQTileBytes / 2) + (k & 3) * 32;
+                umma_bf16_ss(d_tmem, make_kmajor_sw128_desc(a_addr), b_desc, kIdesc, k > 0 ? 1u : 0u);
+              }
+            }
           }
+          umma_commit(&empty[stage]);   // smem slot reusable once these MMAs have read it
+          umma_commit(&tfull[ts]);      // accumulators ready for the epilogue
         }
-        umma_commit(&empty[stage]);   // smem slot reusable once these MMAs have read it
-        umma_commit(&tfull[ts]);      // accumulators ready for the epilogue
+        __syncwarp();
         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         if (++ts == kTileStages) { ts = 0; tphase ^= 1; }
       }
     }
   } else {
     // =============================== epilogue ==================================================
-    // Warp w owns TMEM lanes 32*slot.. (slot = w % 4).  slots_used (1, 2 or 4) queries occupy the A tile
-    // and each is replicated rep = 4 / slots_used times; the warp of slot g scores query g % slots_used
-    // for the documents whose local index is congruent to g / slots_used modulo rep.  A warp therefore
-    // always owns WHOLE documents: no cross-warp combine, boundaries are warp-uniform.
-    const int slot = warp & 3;
+    // slots_used (1, 2 or 4) queries occupy an A tile and each is replicated 4 / slots_used times; the
+    // kSplit warps sharing a lane group split further.  The warp of (slot g, share `sub`) scores query
+    // g % slots_used for the documents whose local index is congruent to `residue` modulo `rep`.
+    const int slot = warp & 3;                           // TMEM lanes 32*slot .. 32*slot+31
     const uint32_t lane_base = uint32_t(slot * 32) << 16;
-    constexpr int kSplit = kEpiWarps / 4;                // warps sharing one lane group split each tile's columns
-    const int sub = (warp - kEpiWarp0) >> 2;             // which column share this warp takes
-    const bool col_split = kSplit > 1 && p.col_split != 0;
-    const int rep = (4 / p.slots_used) * ((kSplit > 1 && !col_split) ? kSplit : 1);
-    const int residue = (kSplit > 1 && !col_split) ? (slot / p.slots_used) * kSplit + sub : slot / p.slots_used;
+    const int sub = (warp - kEpiWarp0) >> 2;
+    const int rep = (4 / p.slots_used) * kSplit;
+    const int residue = (slot / p.slots_used) * kSplit + sub;
     bool active[MT];
     int64_t out_row[MT];
     bool any_active = false;
@@ -272,8 +334,35 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
       out_row[mt] = int64_t(q) * p.n_items;
       any_active |= active[mt];
     }
-    const int n_docs_seg = int(doc_end - doc_begin);
 
+    if constexpr (TS) {
+      // Stage the query tiles in TMEM (A operand): this thread owns row (slot, lane) = query token `lane`.
+      if (sub == 0 && n_tiles > 0) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          uint32_t qv[64];
+          const int q = q_base + 4 * mt + (slot % p.slots_used);
+          if (q < p.n_queries && lane < p.lq) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.queries + (int64_t(q) * p.lq + lane) * HRC_DIM);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint4 x = __ldg(src + i);
+              qv[4 * i] = x.x; qv[4 * i + 1] = x.y; qv[4 * i + 2] = x.z; qv[4 * i + 3] = x.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) qv[i] = 0u;
+          }
+          tmem_st_32x64(tmem_base + lane_base + uint32_t(mt * 64), qv);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(qfull);
+      }
+    }
+
+    const int n_docs_seg = int(doc_end - doc_begin);
     // Document ends (token positions relative to tok_begin) are fetched 32 at a time, one per lane,
     // one batch ahead, and broadcast with a shuffle.
     int batch = 0;
@@ -307,30 +396,13 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) m[mt] = -INFINITY;
 
-    int xpar = 0;                           // exchange-buffer parity (double buffered: one barrier per document)
     auto finish_doc = [&]() {   // emit the score(s) of document `my`, move to this warp's next document
-      if (col_split) {
-        // the warps of this lane group hold maxima over disjoint column shares: combine through smem
-        float* xb = xbuf + ((xpar * 4 + slot) * MT) * 32;
-        if (sub != 0) {
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) xb[mt * 32 + lane] = m[mt];
-        }
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(32 * kSplit) : "memory");
-        if (sub == 0) {
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) m[mt] = fmaxf(m[mt], xb[mt * 32 + lane]);
-        }
-        xpar ^= 1;
-      }
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        if (sub == 0 || !col_split) {
-          const float sc = warp_sum(m[mt]);
-          if (lane == 0 && active[mt]) {
-            const int64_t col = (p.cand_ids == nullptr) ? (doc_begin + my) : item;
-            p.scores[out_row[mt] + col] = sc;
-          }
+        const float sc = warp_sum(m[mt]);
+        if (lane == 0 && active[mt]) {
+          const int64_t col = (p.cand_ids == nullptr) ? (doc_begin + my) : item;
+          p.scores[out_row[mt] + col] = sc;
         }
         m[mt] = -INFINITY;
       }
@@ -346,19 +418,18 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     for (int t = 0; t < n_tiles; ++t) {
       mbar_wait_wd(&tfull[ts], tphase);
       tc_fence_after_sync();
-      const int tile0 = t * kTileN, tile1 = tile0 + kTileN;
+      const int tile0 = t * TN, tile1 = tile0 + TN;
       int cached = -1;                      // 32-column chunk currently held in v[]
       uint32_t v[MT][32];
       while (have_doc && s_tok < tile1) {
         const int lo = max(s_tok, tile0), hi = min(e_tok, tile1);
-        if (hi > lo) {
+        if (hi > lo && !(p.debug & 1)) {
           const int c_first = (lo - tile0) >> 5, c_last = (hi - 1 - tile0) >> 5;
           for (int c32 = c_first; c32 <= c_last; ++c32) {
-            if (col_split && ((c32 * kSplit) >> 2) != sub) continue;   // another warp's column share
             if (c32 != cached) {
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt)
-                tmem_ld_32x32(tmem_base + lane_base + uint32_t((ts * MT + mt) * kTileN + c32 * 32), v[mt]);
+                tmem_ld_32x32(acc_base + lane_base + uint32_t((ts * MT + mt) * TN + c32 * 32), v[mt]);
               tmem_ld_wait();
               cached = c32;
             }
@@ -409,22 +480,6 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int MT>
-int launch_mt(const CUtensorMap& tmap_d, const CUtensorMap& tmap_q, const TcParams& p, dim3 grid,
-              cudaStream_t stream) {
-  const int smem_bytes = 1024 + MT * kQTileBytes + p.n_stages * kTileBytes + 256 + (epi_warps(MT) > 4 ? 2 * 4 * MT * 32 * 4 : 0);
-  static bool configured = false;
-  if (!configured) {
-    HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kMaxSmem));
-    configured = true;
-  }
-  maxsim_tc_kernel<MT><<<grid, cta_threads(MT), smem_bytes, stream>>>(tmap_d, tmap_q, p);
-  count_launch();
-  HRC_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -434,6 +489,48 @@ int sm_count() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+template <int MT, int TN, bool TS>
+int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries, TcParams p, dim3 grid,
+               cudaStream_t stream) {
+  constexpr int kTileBytes = TN * HRC_DIM * 2;
+  CUtensorMap tmap_d, tmap_q;
+  {
+    cuuint64_t dims[2] = {HRC_DIM, (cuuint64_t)p.total_tokens};
+    cuuint64_t strides[1] = {HRC_DIM * 2};
+    cuuint32_t box[2] = {64, TN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmap_d, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d_tokens), dims, strides,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    HRC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(tokens) failed: %d", int(r));
+  }
+  {
+    cuuint64_t dims[3] = {HRC_DIM, (cuuint64_t)p.lq, (cuuint64_t)p.n_queries};
+    cuuint64_t strides[2] = {HRC_DIM * 2, (cuuint64_t)p.lq * HRC_DIM * 2};
+    cuuint32_t box[3] = {64, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&tmap_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d_queries), dims, strides,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    HRC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(queries) failed: %d", int(r));
+  }
+  const int q_bytes = TS ? 0 : MT * kQTileBytes;
+  int stages = (kMaxSmem - 1024 - 512 - q_bytes) / kTileBytes;
+  if (stages > 8) stages = 8;
+  p.n_stages = stages;
+  const int smem_bytes = 1024 + q_bytes + stages * kTileBytes + 512;
+  static bool configured = false;
+  if (!configured) {
+    HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT, TN, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kMaxSmem));
+    configured = true;
+  }
+  maxsim_tc_kernel<MT, TN, TS><<<grid, cta_threads(MT), smem_bytes, stream>>>(tmap_d, tmap_q, p);
+  count_launch();
+  HRC_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace
@@ -450,61 +547,50 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
   EncodeTiledFn encode = get_encode_fn();
   HRC_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled not available from the driver");
 
-  CUtensorMap tmap_d, tmap_q;
-  {
-    cuuint64_t dims[2] = {HRC_DIM, (cuuint64_t)total_tokens};
-    cuuint64_t strides[1] = {HRC_DIM * 2};
-    cuuint32_t box[2] = {64, kTileN};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmap_d, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d_tokens), dims, strides,
-                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    HRC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(tokens) failed: %d", int(r));
-  }
-  {
-    cuuint64_t dims[3] = {HRC_DIM, (cuuint64_t)lq, (cuuint64_t)n_queries};
-    cuuint64_t strides[2] = {HRC_DIM * 2, (cuuint64_t)lq * HRC_DIM * 2};
-    cuuint32_t box[3] = {64, 32, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(&tmap_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d_queries), dims, strides,
-                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    HRC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(queries) failed: %d", int(r));
-  }
-
   TcParams p;
   p.offsets = d_offsets;
   p.cand_ids = d_cand_ids;
+  p.queries = static_cast<const __nv_bfloat16*>(d_queries);
   p.scores = d_scores;
   p.n_docs = n_docs;
   p.total_tokens = total_tokens;
   p.n_items = n_items;
   p.n_queries = n_queries;
+  p.lq = lq;
   p.n_segments = 1;
   p.n_qgroups = 1;
+  p.n_stages = 0;
   p.slots_used = 1;
-  p.col_split = 0;   // measured: splitting documents beats splitting columns (1052 vs 970 TFLOP/s on C3)
-  if (const char* e = getenv("HRC_TC_COL_SPLIT")) p.col_split = atoi(e);
+  p.debug = 0;
+  if (const char* e = getenv("HRC_TC_DEBUG")) p.debug = atoi(e);
   p.doc_policy = kEvictFirst;
 
   if (d_cand_ids != nullptr) {
     HRC_REQUIRE(n_queries <= 65535, "tc path: too many queries for a candidate launch (%d)", n_queries);
-    p.n_stages = 6;
-    return launch_mt<1>(tmap_d, tmap_q, p, dim3((unsigned)n_items, (unsigned)n_queries), stream);
+    return launch_cfg<1, 128, false>(encode, d_tokens, d_queries, p, dim3((unsigned)n_items, (unsigned)n_queries),
+                                     stream);
   }
-  const int64_t tiles = (total_tokens + kTileN - 1) / kTileN;
-  p.n_segments = int(tiles < sm_count() ? tiles : sm_count());
   if (n_queries <= 4) {
-    p.n_qgroups = 1;
-    p.n_stages = 6;
+    const int64_t tiles = (total_tokens + 127) / 128;
+    p.n_segments = int(tiles < sm_count() ? tiles : sm_count());
     p.slots_used = n_queries == 1 ? 1 : (n_queries == 2 ? 2 : 4);
-    return launch_mt<1>(tmap_d, tmap_q, p, dim3((unsigned)p.n_segments), stream);
+    return launch_cfg<1, 128, false>(encode, d_tokens, d_queries, p, dim3((unsigned)p.n_segments), stream);
   }
   p.n_qgroups = (n_queries + 7) / 8;
   p.slots_used = 4;
   p.doc_policy = kEvictNormal;  // the other query groups re-read this tile from L2
-  p.n_stages = 4;
-  return launch_mt<2>(tmap_d, tmap_q, p, dim3((unsigned)(p.n_segments * p.n_qgroups)), stream);
+  // Batched default: SS operands, N=128.  Measured on C3 (256 queries, power-capped at ~990 W): SS 1123 TFLOP/s,
+  // TS (A in TMEM, N=96) 1069 TFLOP/s; with TMA and epilogue disabled both reach the cuBLAS burst rate.
+  const bool use_ts = getenv("HRC_TC_TS") != nullptr && atoi(getenv("HRC_TC_TS")) != 0;
+  if (!use_ts) {
+    const int64_t tiles = (total_tokens + 127) / 128;
+    p.n_segments = int(tiles < sm_count() ? tiles : sm_count());
+    return launch_cfg<2, 128, false>(encode, d_tokens, d_queries, p, dim3((unsigned)(p.n_segments * p.n_qgroups)),
+                                     stream);
+  }
+  const int64_t tiles = (total_tokens + 95) / 96;
+  p.n_segments = int(tiles < sm_count() ? tiles : sm_count());
+  return launch_cfg<2, 96, true>(encode, d_tokens, d_queries, p, dim3((unsigned)(p.n_segments * p.n_qgroups)), stream);
 }
 
 }  // namespace hrc
