@@ -29,6 +29,12 @@ SYMBOLS = {
                                      _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "hrc_maxsim_scores_ids": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int,
                                          _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p]),
+    "hrc_search": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
+                              _c.c_int32, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                              _c.c_int, _c.c_void_p]),
+    "hrc_rerank": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_void_p,
+                              _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                              _c.c_void_p, _c.c_int, _c.c_void_p]),
     "hrc_topk_workspace_bytes": (_c.c_size_t, [_c.c_int64, _c.c_int, _c.c_int]),
     "hrc_topk": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int32, _c.c_void_p,
                             _c.c_void_p, _c.c_size_t, _c.c_void_p]),
@@ -138,6 +144,66 @@ def maxsim_scores_ids(tokens: torch.Tensor, offsets: torch.Tensor, cand_ids: tor
                                           n_cand, _ptr(queries), nq, lq, _ptr(out), path, _stream(dev))
     _check(rc, "hrc_maxsim_scores_ids")
     return out
+
+
+class SearchBuffers:
+    """Reusable device scratch for `search` (scores matrix, top-k workspace, outputs): no per-call allocation."""
+
+    def __init__(self):
+        self.key = None
+
+    def ensure(self, dev, nq: int, n_docs: int, k: int):
+        key = (str(dev), nq, n_docs, k)
+        if self.key != key:
+            self.scores = torch.empty((nq, n_docs), dtype=torch.float32, device=dev)
+            need = topk_workspace_bytes(n_docs, nq, k)
+            self.ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+            self.ws_bytes = need
+            self.key = key
+        return self
+
+
+def search(tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.Tensor, k: int, *, id_base: int = 0,
+           path: int = PATH_AUTO, buffers: Optional[SearchBuffers] = None, unpack: bool = True):
+    """Fused MaxSim + top-k (+ unpack) in one C call.  Returns (keys int64 [nq,k], ids int32 | None, scores fp32 | None).
+    `buffers.scores` holds the full score matrix afterwards."""
+    dev = _require_cuda(tokens, offsets, queries)
+    assert tokens.dtype == torch.bfloat16 and queries.dtype == torch.bfloat16 and offsets.dtype == torch.int64
+    n_docs = offsets.numel() - 1
+    nq, lq = int(queries.shape[0]), int(queries.shape[1])
+    buf = (buffers or SearchBuffers()).ensure(dev, nq, n_docs, k)
+    keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    ids = torch.empty((nq, k), dtype=torch.int32, device=dev) if unpack else None
+    scores = torch.empty((nq, k), dtype=torch.float32, device=dev) if unpack else None
+    with torch.cuda.device(dev):
+        rc = load().hrc_search(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), _ptr(queries), nq, lq, k,
+                               id_base, _ptr(buf.scores), _ptr(buf.ws), buf.ws_bytes, _ptr(keys), _ptr(ids),
+                               _ptr(scores), path, _stream(dev))
+    _check(rc, "hrc_search")
+    return keys, ids, scores
+
+
+def rerank(tokens: torch.Tensor, offsets: torch.Tensor, cand_ids: torch.Tensor, queries: torch.Tensor, k: int, *,
+           path: int = PATH_AUTO):
+    """Fused candidate MaxSim + sorted top-k in one C call.
+    Returns (pos int32 [nq,k], doc ids int32 [nq,k], scores fp32 [nq,k], candidate scores fp32 [nq,n_cand])."""
+    dev = _require_cuda(tokens, offsets, cand_ids, queries)
+    assert cand_ids.dtype == torch.int32 and cand_ids.dim() == 2 and cand_ids.shape[0] == queries.shape[0]
+    assert tokens.dtype == torch.bfloat16 and queries.dtype == torch.bfloat16 and offsets.dtype == torch.int64
+    n_docs = offsets.numel() - 1
+    nq, lq = int(queries.shape[0]), int(queries.shape[1])
+    n_cand = int(cand_ids.shape[1])
+    cand_scores = torch.empty((nq, n_cand), dtype=torch.float32, device=dev)
+    keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    pos = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = load().hrc_rerank(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), _ptr(cand_ids), n_cand,
+                               _ptr(queries), nq, lq, k, _ptr(cand_scores), _ptr(keys), _ptr(pos), _ptr(ids),
+                               _ptr(scores), path, _stream(dev))
+    _check(rc, "hrc_rerank")
+    return pos, ids, scores, cand_scores
 
 
 def topk_workspace_bytes(n: int, n_rows: int, k: int) -> int:

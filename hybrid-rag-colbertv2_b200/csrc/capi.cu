@@ -28,6 +28,7 @@ size_t topk_workspace_bytes(int64_t, int, int);
 int launch_topk(const float*, const int32_t*, int64_t, int, int, int32_t, uint64_t*, void*, size_t, cudaStream_t);
 int launch_topk_merge(const uint64_t*, int, int, int, uint64_t*, cudaStream_t);
 int launch_keys_unpack(const uint64_t*, int64_t, int32_t*, float*, cudaStream_t);
+int launch_rerank_unpack(const uint64_t*, int, int, const int32_t*, int, int32_t*, int32_t*, float*, cudaStream_t);
 int launch_rrf(const int32_t*, int, const int32_t*, int, int, int, int, int32_t*, double*, int32_t*, cudaStream_t);
 int launch_synth(void*, int64_t, int64_t, uint64_t, cudaStream_t);
 
@@ -91,6 +92,38 @@ int hrc_maxsim_scores_ids(const void* d_tokens, const int64_t* d_offsets, int64_
   HRC_REQUIRE(n_cand == 0 || d_cand_ids != nullptr, "maxsim_ids: null candidate list");
   return maxsim_dispatch(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_cand, d_queries, n_queries, lq,
                          d_scores, path, static_cast<cudaStream_t>(stream));
+}
+
+int hrc_search(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens, const void* d_queries,
+               int n_queries, int lq, int k, int32_t id_base, float* d_scores_ws, void* d_topk_ws, size_t topk_ws_bytes,
+               uint64_t* d_keys_out, int32_t* d_ids_out, float* d_scores_out, int path, void* stream) {
+  HRC_REQUIRE(k >= 0 && k <= n_docs, "search: k=%d must be in [0, n_docs]", k);
+  HRC_REQUIRE(n_queries == 0 || k == 0 || (d_scores_ws != nullptr && d_keys_out != nullptr), "search: null buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = maxsim_dispatch(d_tokens, d_offsets, n_docs, total_tokens, nullptr, n_docs, d_queries, n_queries, lq,
+                               d_scores_ws, path, st))
+    return rc;
+  if (int rc = launch_topk(d_scores_ws, nullptr, n_docs, n_queries, k, id_base, d_keys_out, d_topk_ws, topk_ws_bytes, st))
+    return rc;
+  if (d_ids_out != nullptr || d_scores_out != nullptr)
+    return launch_keys_unpack(d_keys_out, int64_t(n_queries) * k, d_ids_out, d_scores_out, st);
+  return 0;
+}
+
+int hrc_rerank(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+               const int32_t* d_cand_ids, int n_cand, const void* d_queries, int n_queries, int lq, int k,
+               float* d_scores_ws, uint64_t* d_keys_ws, int32_t* d_pos_out, int32_t* d_ids_out, float* d_scores_out,
+               int path, void* stream) {
+  HRC_REQUIRE(n_cand >= 0 && n_cand <= 8192, "rerank: n_cand=%d not in [0, 8192]", n_cand);
+  HRC_REQUIRE(k >= 0 && k <= n_cand, "rerank: k=%d must be in [0, n_cand]", k);
+  HRC_REQUIRE(n_queries == 0 || k == 0 || (d_cand_ids != nullptr && d_scores_ws != nullptr && d_keys_ws != nullptr),
+              "rerank: null buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = maxsim_dispatch(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_cand, d_queries, n_queries, lq,
+                               d_scores_ws, path, st))
+    return rc;
+  if (int rc = launch_topk(d_scores_ws, nullptr, n_cand, n_queries, k, 0, d_keys_ws, nullptr, 0, st)) return rc;
+  return launch_rerank_unpack(d_keys_ws, k, n_queries, d_cand_ids, n_cand, d_pos_out, d_ids_out, d_scores_out, st);
 }
 
 size_t hrc_topk_workspace_bytes(int64_t n, int n_rows, int k) { return topk_workspace_bytes(n, n_rows, k); }

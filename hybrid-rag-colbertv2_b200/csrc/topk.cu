@@ -198,6 +198,20 @@ __global__ void keys_unpack_kernel(const uint64_t* __restrict__ keys, int64_t n,
   if (scores) scores[i] = key ? key_score(key) : -INFINITY;
 }
 
+// keys of a rerank (id = position in the candidate list) -> position, candidate doc id, score
+__global__ void rerank_unpack_kernel(const uint64_t* __restrict__ keys, int k, int n_rows, const int32_t* __restrict__ cand,
+                                     int n_cand, int32_t* __restrict__ pos_out, int32_t* __restrict__ ids_out,
+                                     float* __restrict__ scores_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k * n_rows) return;
+  const int row = i / k;
+  const uint64_t key = keys[i];
+  const int32_t pos = key ? key_id(key) : -1;
+  if (pos_out) pos_out[i] = pos;
+  if (ids_out) ids_out[i] = pos >= 0 ? cand[int64_t(row) * n_cand + pos] : -1;
+  if (scores_out) scores_out[i] = key ? key_score(key) : -INFINITY;
+}
+
 int sort_buf_bytes(int k) {
   int p = 1;
   while (p < k) p <<= 1;
@@ -296,6 +310,16 @@ int launch_topk_merge(const uint64_t* d_keys_in, int n_in, int n_rows, int k, ui
     return 0;
   }
   return run_key_levels(d_keys_in, n_in, n_rows, k, d_keys_out, nullptr, nullptr, stream);
+}
+
+int launch_rerank_unpack(const uint64_t* d_keys, int k, int n_rows, const int32_t* d_cand, int n_cand, int32_t* d_pos,
+                         int32_t* d_ids, float* d_scores, cudaStream_t stream) {
+  if (k == 0 || n_rows == 0) return 0;
+  const int n = k * n_rows;
+  rerank_unpack_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_keys, k, n_rows, d_cand, n_cand, d_pos, d_ids, d_scores);
+  count_launch();
+  HRC_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int launch_keys_unpack(const uint64_t* d_keys, int64_t n, int32_t* d_ids, float* d_scores, cudaStream_t stream) {

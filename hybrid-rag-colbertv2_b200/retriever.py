@@ -64,7 +64,7 @@ class JinaColBERTRetriever:
         self.model = encoder if encoder is not None else SyntheticEncoder()
         self.store: Optional[PackedStore] = None
         self.corpus: Optional[List[str]] = None
-        self._workspace: Optional[torch.Tensor] = None
+        self._buffers = _lib.SearchBuffers()
 
     # `corpus_embeddings` is the reference's attribute name for the store (:725,:735,:752)
     @property
@@ -150,22 +150,21 @@ class JinaColBERTRetriever:
 
     def search_keys(self, query_embeddings: torch.Tensor, k: int) -> torch.Tensor:
         """Sorted top-k (score, GLOBAL doc id) keys per query: int64 [Bq, min(k, N)] on the device."""
+        return self._search(query_embeddings, k, unpack=False)[0]
+
+    def _search(self, query_embeddings: torch.Tensor, k: int, unpack: bool):
         self._require_store()
         q = self._prep_queries(query_embeddings)
-        n = self.store.n_docs
-        k_eff = min(int(k), n)
+        k_eff = min(int(k), self.store.n_docs)
         if k_eff <= 0:
-            return torch.zeros((q.shape[0], 0), dtype=torch.int64, device=self.device)
-        scores = _lib.maxsim_scores(self.store.tokens, self.store.offsets, q, path=self.config.maxsim_path)
-        need = _lib.topk_workspace_bytes(n, q.shape[0], k_eff)
-        if need and (self._workspace is None or self._workspace.numel() < need):
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return _lib.topk(scores, k_eff, id_base=self.store.doc_id_base, workspace=self._workspace)
+            z = torch.zeros((q.shape[0], 0), dtype=torch.int64, device=self.device)
+            return z, z.to(torch.int32), z.to(torch.float32)
+        return _lib.search(self.store.tokens, self.store.offsets, q, k_eff, id_base=self.store.doc_id_base,
+                           path=self.config.maxsim_path, buffers=self._buffers, unpack=unpack)
 
     def search_embeddings(self, query_embeddings: torch.Tensor, k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
         """(doc ids int32 [Bq, k'], scores fp32 [Bq, k']) with k' = min(k, N), best first."""
-        keys = self.search_keys(query_embeddings, k)
-        ids, scores = _lib.keys_unpack(keys)
+        _, ids, scores = self._search(query_embeddings, k, unpack=True)
         return ids, self._finish_scores(scores, _as_query_batch(query_embeddings).shape[1])
 
     search_batch = search_embeddings
@@ -184,11 +183,8 @@ class JinaColBERTRetriever:
             cand = cand.unsqueeze(0)
         cand = cand.contiguous()
         k_eff = min(int(k), cand.shape[1])
-        scores = _lib.maxsim_scores_ids(self.store.tokens, self.store.offsets, cand, q, path=self.config.maxsim_path)
-        keys = _lib.topk(scores, k_eff)             # ids = positions in the candidate list
-        pos, top_scores = _lib.keys_unpack(keys)
-        doc_ids = torch.gather(cand, 1, pos.clamp_min(0).to(torch.int64))
-        doc_ids = torch.where(pos >= 0, doc_ids, torch.full_like(doc_ids, -1))
+        pos, doc_ids, top_scores, _ = _lib.rerank(self.store.tokens, self.store.offsets, cand, q, k_eff,
+                                                  path=self.config.maxsim_path)
         return pos, doc_ids, self._finish_scores(top_scores, q.shape[1])
 
     def _require_store(self) -> None:

@@ -75,6 +75,32 @@ int hrc_maxsim_scores_ids(const void* d_tokens, const int64_t* d_offsets, int64_
                           const void* d_queries, int n_queries, int lq, float* d_scores,
                           int path, void* stream);
 
+/*
+ * Fused search: MaxSim of every query against the whole store, per-query top-k, optional unpacking —
+ * the body of JinaColBERTRetriever.search (local_rag_complete.py:764-775) in one call.
+ *   d_scores_ws  : fp32 [n_queries][n_docs] scratch (holds the full score matrix on return)
+ *   d_topk_ws    : hrc_topk_workspace_bytes(n_docs, n_queries, k) bytes of scratch
+ *   d_keys_out   : uint64 [n_queries][k]; d_ids_out / d_scores_out optional int32 / fp32 [n_queries][k]
+ */
+int hrc_search(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+               const void* d_queries, int n_queries, int lq, int k, int32_t id_base, float* d_scores_ws,
+               void* d_topk_ws, size_t topk_ws_bytes, uint64_t* d_keys_out, int32_t* d_ids_out,
+               float* d_scores_out, int path, void* stream);
+
+/*
+ * Fused rerank: MaxSim of query q against its candidate list, sorted top-k — the body of
+ * JinaColBERTRetriever.rerank (local_rag_complete.py:786-798) on stored embeddings.
+ *   d_cand_ids   : int32 [n_queries][n_cand] (n_cand <= 8192)
+ *   d_scores_ws  : fp32 [n_queries][n_cand] scratch (candidate scores on return)
+ *   d_pos_out    : int32 [n_queries][k] position in the candidate list ("result_index"), -1 = empty
+ *   d_ids_out    : int32 [n_queries][k] the candidate's document id, optional
+ *   d_scores_out : fp32  [n_queries][k]
+ */
+int hrc_rerank(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+               const int32_t* d_cand_ids, int n_cand, const void* d_queries, int n_queries, int lq, int k,
+               float* d_scores_ws, uint64_t* d_keys_ws, int32_t* d_pos_out, int32_t* d_ids_out,
+               float* d_scores_out, int path, void* stream);
+
 /* Bytes of scratch hrc_topk needs for these sizes. */
 size_t hrc_topk_workspace_bytes(int64_t n, int n_rows, int k);
 

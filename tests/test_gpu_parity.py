@@ -70,6 +70,41 @@ def test_maxsim_scores_match_oracle(cuda_dev, shape, path):
     _assert_scores(got, exp, f"{path} {shape}")
 
 
+@pytest.mark.parametrize("shape", [(64, 32, 512, 9, 32), (33, 95, 97, 5, 32), (300, 1, 40, 16, 20)])
+def test_batched_ts_kernel_matches_oracle(cuda_dev, shape, monkeypatch):
+    """The optional A-operand-in-TMEM batched kernel (env HRC_TC_TS=1, 96-token tiles)."""
+    L = _lib()
+    monkeypatch.setenv("HRC_TC_TS", "1")
+    q, tok, off = _case(77, *shape)
+    exp = o.maxsim_scores(q.float(), tok.float(), off)
+    got = L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev), path=L.PATH_TC)
+    torch.cuda.synchronize()
+    _assert_scores(got, exp, f"ts {shape}")
+
+
+def test_fused_search_and_rerank_calls(cuda_dev):
+    """hrc_search / hrc_rerank (one C call each) equal the staged calls bit for bit."""
+    L = _lib()
+    q, tok, off = _case(31, 20_000, 8, 64, 3, 32)
+    tok_d, off_d, q_d = tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev)
+    keys, ids, sc = L.search(tok_d, off_d, q_d, 100, id_base=5)
+    staged = L.topk(L.maxsim_scores(tok_d, off_d, q_d), 100, id_base=5)
+    assert torch.equal(keys, staged)
+    si, ss = L.keys_unpack(staged)
+    assert torch.equal(ids, si) and torch.equal(sc, ss)
+    g = torch.Generator().manual_seed(2)
+    cand = torch.randint(0, 20_000, (3, 50), generator=g, dtype=torch.int32).to(cuda_dev)
+    cand[1, 4] = -1
+    pos, dids, rs, cs = L.rerank(tok_d, off_d, cand, q_d, 10)
+    cs2 = L.maxsim_scores_ids(tok_d, off_d, cand, q_d)
+    assert torch.equal(cs, cs2)
+    p2, s2 = L.keys_unpack(L.topk(cs2, 10))
+    assert torch.equal(pos, p2) and torch.equal(rs, s2)
+    assert torch.equal(dids, torch.gather(cand, 1, pos.long()))
+    with pytest.raises(Exception):
+        L.search(tok_d, off_d, q_d, 20_001)
+
+
 def test_simt_handles_long_queries(cuda_dev):
     L = _lib()
     q, tok, off = _case(11, 25, 1, 70, 2, 77)

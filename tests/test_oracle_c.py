@@ -1,0 +1,64 @@
+"""The plain-C oracle (oracle/maxsim_oracle.c) against the Python oracle and the reference's golden vectors."""
+import ctypes
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import maxsim_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def clib():
+    path = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not os.path.exists(path):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True)
+    lib = ctypes.CDLL(path)
+    lib.oracle_rrf.restype = ctypes.c_int
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_c_maxsim_matches_python_oracle(clib):
+    g = torch.Generator().manual_seed(3)
+    lens = torch.randint(0, 12, (15,), generator=g)
+    off = np.concatenate([[0], np.cumsum(lens.numpy())]).astype(np.int64)
+    tok = o.round_bf16(torch.nn.functional.normalize(torch.randn((int(off[-1]), 128), generator=g), dim=-1)).numpy()
+    q = o.round_bf16(torch.nn.functional.normalize(torch.randn((2, 9, 128), generator=g), dim=-1)).numpy()
+    out = np.empty((2, 15), dtype=np.float32)
+    clib.oracle_maxsim_scores(_p(q), 2, 9, _p(tok), _p(off), ctypes.c_int64(15), _p(out))
+    exp = o.maxsim_scores(torch.from_numpy(q), torch.from_numpy(tok), torch.from_numpy(off)).numpy()
+    fin = np.isfinite(exp)
+    assert (np.isfinite(out) == fin).all() and (out[~fin] == exp[~fin]).all()
+    np.testing.assert_allclose(out[fin], exp[fin], rtol=1e-5, atol=1e-6)
+
+
+def test_c_rrf_bit_equal_to_reference_fixtures(clib, golden_dir):
+    for c in json.load(open(os.path.join(golden_dir, "rrf.json"))):
+        a = np.asarray(c["a"], dtype=np.int32)
+        b = np.asarray(c["b"], dtype=np.int32)
+        ids = np.empty(len(a) + len(b) + 1, dtype=np.int32)
+        sc = np.empty(len(a) + len(b) + 1, dtype=np.float64)
+        n = clib.oracle_rrf(_p(a), len(a), _p(b), len(b), c["k"], _p(ids), _p(sc))
+        assert ids[:n].tolist() == c["ids"]
+        assert [repr(float(x)) for x in sc[:n]] == c["scores"]
+
+
+def test_c_topk_keys_match_python_keys(clib):
+    g = torch.Generator().manual_seed(5)
+    s = torch.randn(500, generator=g)
+    s[:100] = torch.round(s[:100])
+    s[7] = float("nan")
+    sn = s.numpy()
+    out = np.empty(40, dtype=np.uint64)
+    clib.oracle_topk_keys(_p(sn), None, ctypes.c_int64(500), 40, 11, _p(out))
+    ref = o.merge_keys(o.make_keys(sn, np.arange(500) + 11)[None], 40)[0]
+    assert (out == ref).all()
