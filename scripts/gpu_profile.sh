@@ -9,4 +9,9 @@ echo "launch list exit $?"
 $CMD > gpurun_out/plain2.log 2>&1 &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:maxsim_tc -s 3 -c 1 -f -o gpurun_out/prof_maxsim_tc $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture exit $?"
-tail -n 3 gpurun_out/plain.log | cut -c1-400
+python scripts/fmt_bench.py gpurun_out/plain.log
+# batched kernel (C3 shape, reduced corpus so the replay passes stay short)
+CMD3="python scripts/bench_configs.py --configs c3 --docs 150000 --c3-queries 64"
+$CMD3 > gpurun_out/c3_plain.log 2>&1 &&
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:maxsim_tc -s 20 -c 1 -f -o gpurun_out/prof_c3 $CMD3 > gpurun_out/ncu_c3.log 2>&1
+echo "c3 capture exit $?"
