@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhrc.so")
+LIB_PATH = os.environ.get("HRC_LIB_PATH") or os.path.join(_HERE, "libhrc.so")   # override: A/B of library builds
 
 PATH_AUTO, PATH_SIMT, PATH_TC = 0, 1, 2
 DIM = 128

@@ -51,8 +51,9 @@ SHAPES = [
     (257, 1, 1, 1, 32),        # one-token documents: a boundary at every column
     (1, 700, 700, 1, 32),      # N == 1 (the reference crashes here), document spanning 6 tiles
     (40, 1, 300, 3, 32),       # ragged, several queries in one M tile
-    (64, 32, 512, 9, 32),      # > 8 queries: two query groups on the MT=2 kernel + a partial group
+    (64, 32, 512, 9, 32),      # > 8 queries: two query groups on the MT=2 kernel, the second nearly empty
     (33, 127, 129, 5, 32),     # documents straddling tile boundaries by one token, MT=2
+    (120, 1, 200, 21, 32),     # 21 queries: three 8-query groups on the batched kernel, the last partial
     (20, 5, 90, 2, 17),        # lq < 32: query rows zero-filled by TMA
     (10, 3, 40, 1, 1),         # single query token
 ]
