@@ -47,7 +47,13 @@ constexpr int kEpiWarp0 = 2;
 constexpr int kMaxSmem = 232448;                  // 227 KB opt-in limit per CTA
 
 __host__ __device__ constexpr int epi_warps(int mt) { return mt == 1 ? 4 : 8; }
-__host__ __device__ constexpr int cta_threads(int mt) { return (2 + epi_warps(mt)) * 32; }
+// ZP ("zero padded") variant for <= 4 queries: with slots_used = 1, 2 or 4 queries the other rows of the A tile
+// stay ZERO (measured: replicating the query instead costs ~10 % under sustained load, because the extra
+// tensor-core switching power pushes the GPU into its 1 kW cap), and the 4 epilogue warps are stacked on the
+// USED TMEM lane groups: a warp can only read lanes 32*(warp%4).., so with one query they are warps 4, 8, 12, 16
+// (all on lane group 0, splitting the documents 4 ways), with two queries warps 4, 5, 8, 9, with four 4..7.
+// The warps in between have no role and exit.
+__host__ __device__ constexpr int cta_threads(int mt, bool zp = false) { return zp ? 17 * 32 : (2 + epi_warps(mt)) * 32; }
 
 struct TcParams {
   const int64_t* offsets;
@@ -63,7 +69,7 @@ struct TcParams {
   int n_qgroups;            // corpus mode: query groups (4*MT queries each)
   int n_stages;             // smem ring depth
   int slots_used;           // distinct queries per A tile: 1, 2 or 4 (each replicated 4/slots_used times)
-  int debug;                // perf experiments only (env HRC_TC_DEBUG): 1 = skip epilogue math, 2 = skip TMA of documents
+  int debug;                // perf experiments only (env HRC_TC_DEBUG): 1 = skip epilogue math, 2 = skip TMA of documents, 4 = skip MMA
   uint64_t doc_policy;      // L2 policy for document tiles (evict-first when read once)
 };
 
@@ -154,8 +160,8 @@ __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-template <int MT, int TN, bool TS>
-__global__ void __launch_bounds__(cta_threads(MT), 1)
+template <int MT, int TN, bool TS, bool ZP = false>
+__global__ void __launch_bounds__(cta_threads(MT, ZP), 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_q,
                  const TcParams p) {
   constexpr int kEpiWarps = epi_warps(MT);
@@ -167,6 +173,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   constexpr uint32_t kIdesc = make_idesc_bf16_f32(128, TN);
   static_assert(TN % 32 == 0 && TN % 16 == 0 && TN <= 256 && kTileStages >= 2, "bad tile configuration");
   static_assert(kTileBytes % 2048 == 0, "tile slabs must stay 1024-byte aligned for the 128B swizzle");
+  static_assert(!ZP || (MT == 1 && !TS), "ZP is a single-query variant");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -250,7 +257,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
           // Rows >= lq and queries >= n_queries are out of bounds of the map and arrive as zeros.
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const int q = q_base + 4 * mt + (g % p.slots_used);
+            const int q = (ZP && g >= p.slots_used) ? p.n_queries : q_base + 4 * mt + (g % p.slots_used);   // ZP: out of bounds -> zeros
             uint8_t* dst = sQ + mt * kQTileBytes + g * kSlotBytes;
             tma_load_3d(dst, &tmap_q, qfull, 0, 0, q, kEvictLast);
             tma_load_3d(dst + kQTileBytes / 2, &tmap_q, qfull, 64, 0, q, kEvictLast);
@@ -295,6 +302,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
             const uint32_t d_tmem = acc_base + uint32_t((ts * MT + mt) * TN);
 #pragma unroll
             for (int k = 0; k < HRC_DIM / 16; ++k) {
+              if (p.debug & 4) break;   // perf experiment: no tensor work at all (results are garbage)
               // k-th 16-element K slice of B: slab (k / 4), 32 bytes per slice inside the 128-byte row
               const uint64_t b_desc = make_kmajor_sw128_desc(b_addr + (k >> 2) * kHalfTileBytes + (k & 3) * 32);
               if constexpr (TS) {
@@ -314,16 +322,16 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
         if (++ts == kTileStages) { ts = 0; tphase ^= 1; }
       }
     }
-  } else {
+  } else if (!ZP || (warp >= 4 && (warp & 3) < p.slots_used && (warp >> 2) - 1 < 4 / p.slots_used)) {
     // =============================== epilogue ==================================================
     // slots_used (1, 2 or 4) queries occupy an A tile and each is replicated 4 / slots_used times; the
     // kSplit warps sharing a lane group split further.  The warp of (slot g, share `sub`) scores query
     // g % slots_used for the documents whose local index is congruent to `residue` modulo `rep`.
     const int slot = warp & 3;                           // TMEM lanes 32*slot .. 32*slot+31
     const uint32_t lane_base = uint32_t(slot * 32) << 16;
-    const int sub = (warp - kEpiWarp0) >> 2;
-    const int rep = (4 / p.slots_used) * kSplit;
-    const int residue = (slot / p.slots_used) * kSplit + sub;
+    const int sub = ZP ? (warp >> 2) - 1 : (warp - kEpiWarp0) >> 2;
+    const int rep = ZP ? 4 / p.slots_used : (4 / p.slots_used) * kSplit;
+    const int residue = ZP ? sub : (slot / p.slots_used) * kSplit + sub;
     bool active[MT];
     int64_t out_row[MT];
     bool any_active = false;
@@ -491,7 +499,7 @@ int sm_count() {
   return n;
 }
 
-template <int MT, int TN, bool TS>
+template <int MT, int TN, bool TS, bool ZP = false>
 int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries, TcParams p, dim3 grid,
                cudaStream_t stream) {
   constexpr int kTileBytes = TN * HRC_DIM * 2;
@@ -523,11 +531,11 @@ int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries
   const int smem_bytes = 1024 + q_bytes + stages * kTileBytes + 512;
   static bool configured = false;
   if (!configured) {
-    HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT, TN, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT, TN, TS, ZP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kMaxSmem));
     configured = true;
   }
-  maxsim_tc_kernel<MT, TN, TS><<<grid, cta_threads(MT), smem_bytes, stream>>>(tmap_d, tmap_q, p);
+  maxsim_tc_kernel<MT, TN, TS, ZP><<<grid, cta_threads(MT, ZP), smem_bytes, stream>>>(tmap_d, tmap_q, p);
   count_launch();
   HRC_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -567,13 +575,15 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
 
   if (d_cand_ids != nullptr) {
     HRC_REQUIRE(n_queries <= 65535, "tc path: too many queries for a candidate launch (%d)", n_queries);
-    return launch_cfg<1, 128, false>(encode, d_tokens, d_queries, p, dim3((unsigned)n_items, (unsigned)n_queries),
-                                     stream);
+    return launch_cfg<1, 128, false, true>(encode, d_tokens, d_queries, p,
+                                           dim3((unsigned)n_items, (unsigned)n_queries), stream);
   }
   if (n_queries <= 4) {
     const int64_t tiles = (total_tokens + 127) / 128;
     p.n_segments = int(tiles < sm_count() ? tiles : sm_count());
     p.slots_used = n_queries == 1 ? 1 : (n_queries == 2 ? 2 : 4);
+    const bool zp = getenv("HRC_TC_ZP") == nullptr || atoi(getenv("HRC_TC_ZP")) != 0;   // default; 0 = replicate (A/B)
+    if (zp) return launch_cfg<1, 128, false, true>(encode, d_tokens, d_queries, p, dim3((unsigned)p.n_segments), stream);
     return launch_cfg<1, 128, false>(encode, d_tokens, d_queries, p, dim3((unsigned)p.n_segments), stream);
   }
   p.n_qgroups = (n_queries + 7) / 8;

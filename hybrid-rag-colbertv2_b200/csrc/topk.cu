@@ -6,8 +6,8 @@
 // deterministic, which torch.topk's tie order is not.
 //
 //   stage 1  select_scores_kernel : grid (chunks, rows); each CTA turns <= 8192 scores into keys in
-//            shared memory, radix-selects the chunk's top-k (8 passes of 8 bits, MSB first, with
-//            warp-aggregated histogram atomics) and writes k unsorted candidates.  When the row is
+//            shared memory, radix-selects the chunk's top-k (11-bit digits, MSB first, early exit: 3
+//            passes for distinct scores, warp-aggregated histogram atomics) and writes k unsorted candidates.  When the row is
 //            a single chunk it sorts and writes the final answer itself.
 //   stage 2  select_keys_kernel : per row (and per group while the candidate list is too long for
 //            shared memory) the same select over candidate keys; the last level bitonic-sorts.
@@ -24,10 +24,13 @@ constexpr int kChunk = 8192;          // scores per stage-1 CTA (64 KB of keys)
 constexpr int kMergeMax = 24576;      // keys per stage-2 CTA (192 KB)
 constexpr int kSortMax = HRC_MAX_TOPK;
 
+constexpr int kBins = 2048;           // 11-bit digits: 64-bit keys in at most 6 passes, usually 3
+
 struct SelectScratch {
-  uint32_t hist[256];
+  uint32_t hist[kBins];
   uint64_t prefix;
   int k_rem;
+  int done;
   int count;
 };
 
@@ -37,35 +40,39 @@ __device__ __forceinline__ int next_pow2(int v) {
   return p;
 }
 
-// Exact k-th largest key among keys[0..n) (n > k >= 1, all threads of the CTA call this).
+// A threshold T such that exactly k keys of keys[0..n) are >= T or, when keys repeat, at least k are >= T and
+// fewer than k are > T (n > k >= 1; all threads of the CTA call this).  MSB-first radix select with 11-bit
+// digits; stops as soon as the bucket holding the k-th key is needed in full, which for distinct scores is
+// after the 32 score bits (3 passes).
 __device__ uint64_t radix_kth_largest(const uint64_t* keys, int n, int k, SelectScratch& sc) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   uint64_t prefix = 0, mask = 0;
   int k_rem = k;
   const int n_pad = (n + 31) & ~31;
-  for (int shift = 56; shift >= 0; shift -= 8) {
-    if (tid < 256) sc.hist[tid] = 0;
+#pragma unroll 1
+  for (int pass = 0; pass < 6; ++pass) {
+    // digits of 11, 11, 10 bits over the score half, then 11, 11, 10 over the id half
+    const int half_pos = pass % 3;
+    const int shift = (pass < 3 ? 32 : 0) + (half_pos == 0 ? 21 : (half_pos == 1 ? 10 : 0));
+    const uint32_t dmask = half_pos == 2 ? 1023u : 2047u;
+    for (int i = tid; i < kBins; i += kSelThreads) sc.hist[i] = 0;
     __syncthreads();
     for (int i = tid; i < n_pad; i += kSelThreads) {
       uint32_t digit = 0xffffffffu;
       if (i < n) {
         const uint64_t key = keys[i];
-        if ((key & mask) == prefix) digit = uint32_t(key >> shift) & 255u;
+        if ((key & mask) == prefix) digit = uint32_t(key >> shift) & dmask;
       }
       const uint32_t peers = __match_any_sync(0xffffffffu, digit);
       if (digit != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&sc.hist[digit], __popc(peers));
     }
     __syncthreads();
     if (tid < 32) {
-      // lane l owns bins [255 - 8l - 7, 255 - 8l], i.e. lanes walk the digits from high to low
-      uint32_t local[8];
+      // lane l owns the 64 bins [kBins-64l-64, kBins-64l): lanes walk the digits from high to low
+      const int top = kBins - 1 - 64 * lane;
       uint32_t sum = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        local[j] = sc.hist[255 - 8 * lane - j];
-        sum += local[j];
-      }
+      for (int j = 0; j < 64; ++j) sum += sc.hist[top - j];
       uint32_t incl = sum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -75,22 +82,23 @@ __device__ uint64_t radix_kth_largest(const uint64_t* keys, int n, int k, Select
       const uint32_t excl = incl - sum;  // keys with a digit above this lane's bins
       if (excl < uint32_t(k_rem) && incl >= uint32_t(k_rem)) {
         uint32_t above = excl;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (above < uint32_t(k_rem) && above + local[j] >= uint32_t(k_rem)) {
-            sc.prefix = prefix | (uint64_t(255 - 8 * lane - j) << shift);
+        for (int j = 0; j < 64; ++j) {
+          const uint32_t c = sc.hist[top - j];
+          if (above + c >= uint32_t(k_rem)) {
+            sc.prefix = prefix | (uint64_t(top - j) << shift);
             sc.k_rem = k_rem - int(above);
-            above = 0xffffffffu;  // done
-          } else if (above != 0xffffffffu) {
-            above += local[j];
+            sc.done = (c == uint32_t(k_rem) - above) ? 1 : 0;   // the whole bucket is needed: no need to refine
+            break;
           }
+          above += c;
         }
       }
     }
     __syncthreads();
     prefix = sc.prefix;
     k_rem = sc.k_rem;
-    mask |= uint64_t(255) << shift;
+    mask |= uint64_t(dmask) << shift;
+    if (sc.done) break;
   }
   return prefix;
 }
