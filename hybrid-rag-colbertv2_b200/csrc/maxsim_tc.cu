@@ -53,7 +53,13 @@ __host__ __device__ constexpr int epi_warps(int mt) { return mt == 1 ? 4 : 8; }
 // USED TMEM lane groups: a warp can only read lanes 32*(warp%4).., so with one query they are warps 4, 8, 12, 16
 // (all on lane group 0, splitting the documents 4 ways), with two queries warps 4, 5, 8, 9, with four 4..7.
 // The warps in between have no role and exit.
-__host__ __device__ constexpr int cta_threads(int mt, bool zp = false) { return zp ? 17 * 32 : (2 + epi_warps(mt)) * 32; }
+// ZP == 2 additionally uses an M=64 MMA for <= 2 queries (half the tensor work and A-operand traffic).  Its
+// accumulator layout puts rows 0-15 / 16-31 / 32-47 / 48-63 in lanes 0-15 of lane groups 0 / 1 / 2 / 3, so a
+// query's tokens 0-15 and 16-31 are summed by two different warps, which each atomicAdd their half into the
+// (zero-initialised) score: two commutative additions, hence still deterministic.  8 epilogue warps.
+__host__ __device__ constexpr int cta_threads(int mt, int zp = 0) {
+  return zp == 2 ? 18 * 32 : (zp == 1 ? 17 * 32 : (2 + epi_warps(mt)) * 32);
+}
 
 struct TcParams {
   const int64_t* offsets;
@@ -160,25 +166,27 @@ __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-template <int MT, int TN, bool TS, bool ZP = false>
+template <int MT, int TN, bool TS, int ZP = 0>
 __global__ void __launch_bounds__(cta_threads(MT, ZP), 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_q,
                  const TcParams p) {
-  constexpr int kEpiWarps = epi_warps(MT);
+  constexpr int kEpiWarps = ZP == 2 ? 8 : epi_warps(MT);
+  constexpr int kM = ZP == 2 ? 64 : 128;               // MMA M (rows of the A tile)
+  constexpr int kQBytes = kM * HRC_DIM * 2;            // one A tile in shared memory (SS mode)
   constexpr int kSplit = kEpiWarps / 4;                 // warps sharing one TMEM lane group split the documents
   constexpr int kTileBytes = TN * HRC_DIM * 2;
   constexpr int kHalfTileBytes = kTileBytes / 2;        // one 64-dim (128-byte-row) slab
   constexpr int kQCols = TS ? MT * 64 : 0;              // TMEM columns holding the query tiles (bf16 pairs)
   constexpr int kTileStages = (kTmemCols - kQCols) / (MT * TN);   // tiles in flight between MMA and epilogue
-  constexpr uint32_t kIdesc = make_idesc_bf16_f32(128, TN);
+  constexpr uint32_t kIdesc = make_idesc_bf16_f32(kM, TN);
   static_assert(TN % 32 == 0 && TN % 16 == 0 && TN <= 256 && kTileStages >= 2, "bad tile configuration");
   static_assert(kTileBytes % 2048 == 0, "tile slabs must stay 1024-byte aligned for the 128B swizzle");
-  static_assert(!ZP || (MT == 1 && !TS), "ZP is a single-query variant");
+  static_assert(ZP == 0 || (MT == 1 && !TS), "ZP is a few-query variant");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                        // SS: MT x 32 KB query tiles
-  uint8_t* sD = smem + (TS ? 0 : MT * kQTileBytes);          // n_stages x tile
+  uint8_t* sD = smem + (TS ? 0 : MT * kQBytes);              // n_stages x tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + p.n_stages * kTileBytes);
   uint64_t* full = bars;                           // [n_stages]    TMA -> MMA
   uint64_t* empty = bars + 10;                     // [n_stages]    MMA -> TMA
@@ -249,18 +257,18 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     //  uniform datapath directly instead of emitting a per-instruction uniformisation loop)
     if (n_tiles > 0 && elect_one()) {
       if constexpr (!TS) {
-        mbar_arrive_expect_tx(qfull, MT * kQTileBytes);
+        mbar_arrive_expect_tx(qfull, MT * kQBytes);
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           // slot g (32 rows of the A tile) holds query (g % slots_used): with fewer than 4 queries the
           // query is REPLICATED, so every epilogue warp sees complete rows and takes its own documents.
           // Rows >= lq and queries >= n_queries are out of bounds of the map and arrive as zeros.
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < kM / 32; ++g) {
             const int q = (ZP && g >= p.slots_used) ? p.n_queries : q_base + 4 * mt + (g % p.slots_used);   // ZP: out of bounds -> zeros
-            uint8_t* dst = sQ + mt * kQTileBytes + g * kSlotBytes;
+            uint8_t* dst = sQ + mt * kQBytes + g * kSlotBytes;
             tma_load_3d(dst, &tmap_q, qfull, 0, 0, q, kEvictLast);
-            tma_load_3d(dst + kQTileBytes / 2, &tmap_q, qfull, 64, 0, q, kEvictLast);
+            tma_load_3d(dst + kQBytes / 2, &tmap_q, qfull, 64, 0, q, kEvictLast);
           }
         }
       }
@@ -309,7 +317,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
                 // A from TMEM: lane = query row, 8 columns (16 bf16) per K slice
                 umma_bf16_ts(d_tmem, tmem_base + uint32_t(mt * 64 + k * 8), b_desc, kIdesc, k > 0 ? 1u : 0u);
               } else {
-                const uint32_t a_addr = sQ_addr + mt * kQTileBytes + (k >> 2) * (kQTileBytes / 2) + (k & 3) * 32;
+                const uint32_t a_addr = sQ_addr + mt * kQBytes + (k >> 2) * (kQBytes / 2) + (k & 3) * 32;
                 umma_bf16_ss(d_tmem, make_kmajor_sw128_desc(a_addr), b_desc, kIdesc, k > 0 ? 1u : 0u);
               }
             }
@@ -322,7 +330,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
         if (++ts == kTileStages) { ts = 0; tphase ^= 1; }
       }
     }
-  } else if (!ZP || (warp >= 4 && (warp & 3) < p.slots_used && (warp >> 2) - 1 < 4 / p.slots_used)) {
+  } else if (ZP == 0 || (warp >= 4 && (warp & 3) < (ZP == 2 ? 2 : 1) * p.slots_used && (warp >> 2) - 1 < 4 / p.slots_used)) {
     // =============================== epilogue ==================================================
     // slots_used (1, 2 or 4) queries occupy an A tile and each is replicated 4 / slots_used times; the
     // kSplit warps sharing a lane group split further.  The warp of (slot g, share `sub`) scores query
@@ -337,7 +345,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     bool any_active = false;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      const int q = q_base + 4 * mt + (slot % p.slots_used);
+      const int q = ZP == 2 ? q_base + (slot >> 1) : q_base + 4 * mt + (slot % p.slots_used);
       active[mt] = q < p.n_queries;
       out_row[mt] = int64_t(q) * p.n_items;
       any_active |= active[mt];
@@ -407,10 +415,12 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     auto finish_doc = [&]() {   // emit the score(s) of document `my`, move to this warp's next document
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        const float sc = warp_sum(m[mt]);
+        // M=64: only lanes 0-15 of a lane group hold accumulator rows (16 query tokens)
+        const float sc = warp_sum((ZP == 2 && lane >= 16) ? 0.f : m[mt]);
         if (lane == 0 && active[mt]) {
           const int64_t col = (p.cand_ids == nullptr) ? (doc_begin + my) : item;
-          p.scores[out_row[mt] + col] = sc;
+          if constexpr (ZP == 2) atomicAdd(&p.scores[out_row[mt] + col], sc);   // the other token half adds its part
+          else p.scores[out_row[mt] + col] = sc;
         }
         m[mt] = -INFINITY;
       }
@@ -499,7 +509,7 @@ int sm_count() {
   return n;
 }
 
-template <int MT, int TN, bool TS, bool ZP = false>
+template <int MT, int TN, bool TS, int ZP = 0>
 int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries, TcParams p, dim3 grid,
                cudaStream_t stream) {
   constexpr int kTileBytes = TN * HRC_DIM * 2;
@@ -524,7 +534,7 @@ int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     HRC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(queries) failed: %d", int(r));
   }
-  const int q_bytes = TS ? 0 : MT * kQTileBytes;
+  const int q_bytes = TS ? 0 : MT * (ZP == 2 ? kQTileBytes / 2 : kQTileBytes);
   int stages = (kMaxSmem - 1024 - 512 - q_bytes) / kTileBytes;
   if (stages > 8) stages = 8;
   p.n_stages = stages;
@@ -535,6 +545,8 @@ int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries
                                         kMaxSmem));
     configured = true;
   }
+  if (ZP == 2)   // both token halves of a query accumulate into the score
+    HRC_CHECK_CUDA(cudaMemsetAsync(p.scores, 0, size_t(p.n_queries) * size_t(p.n_items) * sizeof(float), stream));
   maxsim_tc_kernel<MT, TN, TS, ZP><<<grid, cta_threads(MT, ZP), smem_bytes, stream>>>(tmap_d, tmap_q, p);
   count_launch();
   HRC_CHECK_CUDA(cudaGetLastError());
@@ -575,15 +587,17 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
 
   if (d_cand_ids != nullptr) {
     HRC_REQUIRE(n_queries <= 65535, "tc path: too many queries for a candidate launch (%d)", n_queries);
-    return launch_cfg<1, 128, false, true>(encode, d_tokens, d_queries, p,
-                                           dim3((unsigned)n_items, (unsigned)n_queries), stream);
+    return launch_cfg<1, 128, false, 1>(encode, d_tokens, d_queries, p,
+                                        dim3((unsigned)n_items, (unsigned)n_queries), stream);
   }
   if (n_queries <= 4) {
     const int64_t tiles = (total_tokens + 127) / 128;
     p.n_segments = int(tiles < sm_count() ? tiles : sm_count());
     p.slots_used = n_queries == 1 ? 1 : (n_queries == 2 ? 2 : 4);
     const bool zp = getenv("HRC_TC_ZP") == nullptr || atoi(getenv("HRC_TC_ZP")) != 0;   // default; 0 = replicate (A/B)
-    if (zp) return launch_cfg<1, 128, false, true>(encode, d_tokens, d_queries, p, dim3((unsigned)p.n_segments), stream);
+    const bool m64 = n_queries <= 2 && getenv("HRC_TC_M64") != nullptr && atoi(getenv("HRC_TC_M64")) != 0;
+    if (zp && m64) return launch_cfg<1, 128, false, 2>(encode, d_tokens, d_queries, p, dim3((unsigned)p.n_segments), stream);
+    if (zp) return launch_cfg<1, 128, false, 1>(encode, d_tokens, d_queries, p, dim3((unsigned)p.n_segments), stream);
     return launch_cfg<1, 128, false>(encode, d_tokens, d_queries, p, dim3((unsigned)p.n_segments), stream);
   }
   p.n_qgroups = (n_queries + 7) / 8;
