@@ -437,30 +437,39 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
       mbar_wait_wd(&tfull[ts], tphase);
       tc_fence_after_sync();
       const int tile0 = t * TN, tile1 = tile0 + TN;
-      int cached = -1;                      // 32-column chunk currently held in v[]
+      // accumulator columns of this tile for M-tile mt: tacc + mt * TN + (token position - tile0)
+      const uint32_t tacc = acc_base + lane_base + uint32_t(ts * MT * TN);
       uint32_t v[MT][32];
       while (have_doc && s_tok < tile1) {
         const int lo = max(s_tok, tile0), hi = min(e_tok, tile1);
-        if (hi > lo && !(p.debug & 1)) {
-          const int c_first = (lo - tile0) >> 5, c_last = (hi - 1 - tile0) >> 5;
-          for (int c32 = c_first; c32 <= c_last; ++c32) {
-            if (c32 != cached) {
+        const int len = hi - lo;              // this document's tokens inside this tile
+        if (len > 0 && !(p.debug & 1)) {
+          if (len >= 32) {
+            // Whole 32-column loads that START AT the document's first column (TMEM columns are addressable one by
+            // one); the last load is pulled back so that it ENDS at the document's last column — the overlap is
+            // harmless under max — so no column is ever masked.
+            const int last = hi - 32;
+            int c = lo;
+            while (true) {
+              const uint32_t col = uint32_t(min(c, last) - tile0);
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt)
-                tmem_ld_32x32(acc_base + lane_base + uint32_t((ts * MT + mt) * TN + c32 * 32), v[mt]);
+              for (int mt = 0; mt < MT; ++mt) tmem_ld_32x32(tacc + uint32_t(mt * TN) + col, v[mt]);
               tmem_ld_wait();
-              cached = c32;
-            }
-            const int cbase = tile0 + c32 * 32;
-            const int a = max(lo - cbase, 0), b = min(hi - cbase, 32);
-            if (a == 0 && b == 32) {
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) m[mt] = fmaxf(m[mt], max32(v[mt]));
-            } else {
-              const uint32_t bits = (b >= 32 ? 0xffffffffu : ((1u << b) - 1u)) & ~((1u << a) - 1u);
-#pragma unroll
-              for (int mt = 0; mt < MT; ++mt) m[mt] = fmaxf(m[mt], max32_masked(v[mt], bits));
+              if (c >= last) break;
+              c += 32;
             }
+          } else {
+            // fewer than 32 of its tokens here (a short document, or the head / tail a tile boundary cut off)
+            const int cc = min(lo, tile1 - 32);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) tmem_ld_32x32(tacc + uint32_t(mt * TN) + uint32_t(cc - tile0), v[mt]);
+            tmem_ld_wait();
+            const int a = lo - cc, b = hi - cc;   // 0 <= a < b <= 32, b - a < 32
+            const uint32_t bits = ((1u << (b - a)) - 1u) << a;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) m[mt] = fmaxf(m[mt], max32_masked(v[mt], bits));
           }
         }
         if (e_tok <= tile1) finish_doc(); else break;   // else: the document continues in the next tile

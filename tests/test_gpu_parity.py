@@ -83,6 +83,18 @@ def test_batched_ts_kernel_matches_oracle(cuda_dev, shape, monkeypatch):
     _assert_scores(got, exp, f"ts {shape}")
 
 
+@pytest.mark.parametrize("shape", [(64, 32, 512, 9, 32), (33, 127, 129, 5, 32), (120, 1, 200, 21, 32), (300, 1, 40, 16, 20),
+                                   (3000, 16, 200, 40, 32), (1, 700, 700, 17, 32)])
+def test_batched_kernel_more_shapes(cuda_dev, shape):
+    """Batched (MT=2) kernel: 40 queries over many segments, 17 queries on one 6-tile document, short documents."""
+    L = _lib()
+    q, tok, off = _case(78, *shape)
+    exp = o.maxsim_scores(q.float(), tok.float(), off)
+    got = L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev), path=L.PATH_TC)
+    torch.cuda.synchronize()
+    _assert_scores(got, exp, f"batched {shape}")
+
+
 def test_fused_search_and_rerank_calls(cuda_dev):
     """hrc_search / hrc_rerank (one C call each) equal the staged calls bit for bit."""
     L = _lib()
