@@ -166,7 +166,7 @@ __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-template <int MT, int TN, bool TS, int ZP = 0>
+template <int MT, int TN, bool TS, int ZP = 0, int CG = 1>
 __global__ void __launch_bounds__(cta_threads(MT, ZP), 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_q,
                  const TcParams p) {
@@ -174,14 +174,18 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   constexpr int kM = ZP == 2 ? 64 : 128;               // MMA M (rows of the A tile)
   constexpr int kQBytes = kM * HRC_DIM * 2;            // one A tile in shared memory (SS mode)
   constexpr int kSplit = kEpiWarps / 4;                 // warps sharing one TMEM lane group split the documents
-  constexpr int kTileBytes = TN * HRC_DIM * 2;
+  // CG == 2 (CTA pair, cta_group::2): the pair issues one M=256 MMA per K slice; this CTA stages TN/2 tokens
+  // of every tile (its half of the B operand), its own MT query tiles and its own accumulators.
+  constexpr int kTileRows = TN / CG;                    // document tokens of a tile staged by THIS CTA
+  constexpr int kTileBytes = kTileRows * HRC_DIM * 2;
   constexpr int kHalfTileBytes = kTileBytes / 2;        // one 64-dim (128-byte-row) slab
   constexpr int kQCols = TS ? MT * 64 : 0;              // TMEM columns holding the query tiles (bf16 pairs)
   constexpr int kTileStages = (kTmemCols - kQCols) / (MT * TN);   // tiles in flight between MMA and epilogue
-  constexpr uint32_t kIdesc = make_idesc_bf16_f32(kM, TN);
+  constexpr uint32_t kIdesc = make_idesc_bf16_f32(kM * CG, TN);
   static_assert(TN % 32 == 0 && TN % 16 == 0 && TN <= 256 && kTileStages >= 2, "bad tile configuration");
   static_assert(kTileBytes % 2048 == 0, "tile slabs must stay 1024-byte aligned for the 128B swizzle");
   static_assert(ZP == 0 || (MT == 1 && !TS), "ZP is a few-query variant");
+  static_assert(CG == 1 || (CG == 2 && MT == 2 && !TS && ZP == 0), "CTA pairs: batched SS kernel only");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -198,6 +202,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;   // 0 = leader of the pair (issues the MMAs)
 
   // ---- which segment / queries does this CTA own? -------------------------------------------
   int q_base;   // first query of slot 0, M-tile 0
@@ -234,16 +239,17 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     tma_prefetch_desc(&tmap_d);
     if (!TS) tma_prefetch_desc(&tmap_q);
     for (int i = 0; i < p.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < kTileStages; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
+    for (int i = 0; i < kTileStages; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps * CG); }
     mbar_init(qfull, TS ? 4 : 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if constexpr (CG == 2) { tmem_alloc_cg2(tmem_slot, kTmemCols); tmem_relinquish_cg2(); }
+    else { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers must be initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after_sync();
 
   const uint32_t tmem_base = *tmem_slot;
@@ -257,7 +263,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     //  uniform datapath directly instead of emitting a per-instruction uniformisation loop)
     if (n_tiles > 0 && elect_one()) {
       if constexpr (!TS) {
-        mbar_arrive_expect_tx(qfull, MT * kQBytes);
+        if (cta_rank == 0) mbar_arrive_expect_tx(qfull, CG * MT * kQBytes);   // the peer's tiles count here too
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           // slot g (32 rows of the A tile) holds query (g % slots_used): with fewer than 4 queries the
@@ -267,8 +273,13 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
           for (int g = 0; g < kM / 32; ++g) {
             const int q = (ZP && g >= p.slots_used) ? p.n_queries : q_base + 4 * mt + (g % p.slots_used);   // ZP: out of bounds -> zeros
             uint8_t* dst = sQ + mt * kQBytes + g * kSlotBytes;
-            tma_load_3d(dst, &tmap_q, qfull, 0, 0, q, kEvictLast);
-            tma_load_3d(dst + kQBytes / 2, &tmap_q, qfull, 64, 0, q, kEvictLast);
+            if constexpr (CG == 2) {
+              tma_load_3d_cg2(dst, &tmap_q, qfull, 0, 0, q, kEvictLast);
+              tma_load_3d_cg2(dst + kQBytes / 2, &tmap_q, qfull, 64, 0, q, kEvictLast);
+            } else {
+              tma_load_3d(dst, &tmap_q, qfull, 0, 0, q, kEvictLast);
+              tma_load_3d(dst + kQBytes / 2, &tmap_q, qfull, 64, 0, q, kEvictLast);
+            }
           }
         }
       }
@@ -276,13 +287,20 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
       for (int t = 0; t < n_tiles; ++t) {
         mbar_wait_wd(&empty[stage], phase ^ 1);
         if (p.debug & 2) {
-          mbar_arrive(&full[stage]);
+          if (cta_rank == 0) mbar_arrive(&full[stage]);
         } else {
-          mbar_arrive_expect_tx(&full[stage], kTileBytes);
-          const int row = int(tok_begin + int64_t(t) * TN);
+          const int row = int(tok_begin + int64_t(t) * TN) + int(cta_rank) * kTileRows;
           uint8_t* dst = sD + stage * kTileBytes;
-          tma_load_2d(dst, &tmap_d, &full[stage], 0, row, p.doc_policy);
-          tma_load_2d(dst + kHalfTileBytes, &tmap_d, &full[stage], 64, row, p.doc_policy);
+          if constexpr (CG == 2) {
+            // both halves of the tile are counted on the LEADER's barrier (the MMA issuer waits there)
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * kTileBytes);
+            tma_load_2d_cg2(dst, &tmap_d, &full[stage], 0, row, p.doc_policy);
+            tma_load_2d_cg2(dst + kHalfTileBytes, &tmap_d, &full[stage], 64, row, p.doc_policy);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], kTileBytes);
+            tma_load_2d(dst, &tmap_d, &full[stage], 0, row, p.doc_policy);
+            tma_load_2d(dst + kHalfTileBytes, &tmap_d, &full[stage], 64, row, p.doc_policy);
+          }
         }
         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
       }
@@ -292,7 +310,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     // The whole warp walks the tile loop and waits on the barriers; one elected lane issues.  Gating with
     // elect.sync (rather than `lane == 0`) matters: otherwise every tcgen05.mma is preceded by an
     // ELECT/R2UR.BROADCAST loop and the issue rate, not the tensor core, bounds the kernel.
-    if (n_tiles > 0) {
+    if (n_tiles > 0 && cta_rank == 0) {
       mbar_wait_wd(qfull, 0);
       tc_fence_after_sync();
       const uint32_t sQ_addr = smem_u32(sQ);
@@ -318,12 +336,18 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
                 umma_bf16_ts(d_tmem, tmem_base + uint32_t(mt * 64 + k * 8), b_desc, kIdesc, k > 0 ? 1u : 0u);
               } else {
                 const uint32_t a_addr = sQ_addr + mt * kQBytes + (k >> 2) * (kQBytes / 2) + (k & 3) * 32;
-                umma_bf16_ss(d_tmem, make_kmajor_sw128_desc(a_addr), b_desc, kIdesc, k > 0 ? 1u : 0u);
+                if constexpr (CG == 2) umma_bf16_ss_cg2(d_tmem, make_kmajor_sw128_desc(a_addr), b_desc, kIdesc, k > 0 ? 1u : 0u);
+                else umma_bf16_ss(d_tmem, make_kmajor_sw128_desc(a_addr), b_desc, kIdesc, k > 0 ? 1u : 0u);
               }
             }
           }
-          umma_commit(&empty[stage]);   // smem slot reusable once these MMAs have read it
-          umma_commit(&tfull[ts]);      // accumulators ready for the epilogue
+          if constexpr (CG == 2) {      // multicast: the peer's producer and epilogue wait on their own copies
+            umma_commit_cg2(&empty[stage]);
+            umma_commit_cg2(&tfull[ts]);
+          } else {
+            umma_commit(&empty[stage]);   // smem slot reusable once these MMAs have read it
+            umma_commit(&tfull[ts]);      // accumulators ready for the epilogue
+          }
         }
         __syncwarp();
         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
@@ -476,15 +500,23 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[ts]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(&tempty[ts], 0);   // the leader's MMA issuer owns both accumulators
+        else mbar_arrive(&tempty[ts]);
+      }
       if (++ts == kTileStages) { ts = 0; tphase ^= 1; }
     }
     while (have_doc) finish_doc();          // trailing empty documents (no tokens, no tile): -inf
   }
 
   tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if constexpr (CG == 2) {
+    cluster_sync_all();             // the peer may still be reading operands / arriving on this CTA's barriers
+    if (warp == 1) tmem_dealloc_cg2(tmem_base, kTmemCols);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 // --- host side -------------------------------------------------------------------------------
@@ -518,15 +550,15 @@ int sm_count() {
   return n;
 }
 
-template <int MT, int TN, bool TS, int ZP = 0>
+template <int MT, int TN, bool TS, int ZP = 0, int CG = 1>
 int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries, TcParams p, dim3 grid,
                cudaStream_t stream) {
-  constexpr int kTileBytes = TN * HRC_DIM * 2;
+  constexpr int kTileBytes = (TN / CG) * HRC_DIM * 2;   // what ONE CTA stages per tile
   CUtensorMap tmap_d, tmap_q;
   {
     cuuint64_t dims[2] = {HRC_DIM, (cuuint64_t)p.total_tokens};
     cuuint64_t strides[1] = {HRC_DIM * 2};
-    cuuint32_t box[2] = {64, TN};
+    cuuint32_t box[2] = {64, TN / CG};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&tmap_d, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d_tokens), dims, strides,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -550,13 +582,29 @@ int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries
   const int smem_bytes = 1024 + q_bytes + stages * kTileBytes + 512;
   static bool configured = false;
   if (!configured) {
-    HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT, TN, TS, ZP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kMaxSmem));
+    HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT, TN, TS, ZP, CG>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     configured = true;
   }
   if (ZP == 2)   // both token halves of a query accumulate into the score
     HRC_CHECK_CUDA(cudaMemsetAsync(p.scores, 0, size_t(p.n_queries) * size_t(p.n_items) * sizeof(float), stream));
-  maxsim_tc_kernel<MT, TN, TS, ZP><<<grid, cta_threads(MT, ZP), smem_bytes, stream>>>(tmap_d, tmap_q, p);
+  if constexpr (CG == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;                                  // grid.x is even: consecutive CTAs form a pair (one TPC)
+    cfg.blockDim = dim3(cta_threads(MT, ZP));
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HRC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, maxsim_tc_kernel<MT, TN, TS, ZP, CG>, tmap_d, tmap_q, p));
+  } else {
+    maxsim_tc_kernel<MT, TN, TS, ZP, CG><<<grid, cta_threads(MT, ZP), smem_bytes, stream>>>(tmap_d, tmap_q, p);
+  }
   count_launch();
   HRC_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -615,6 +663,29 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
   // Batched default: SS operands, N=128.  Measured on C3 (256 queries, power-capped at ~990 W): SS 1123 TFLOP/s,
   // TS (A in TMEM, N=96) 1069 TFLOP/s; with TMA and epilogue disabled both reach the cuBLAS burst rate.
   const bool use_ts = getenv("HRC_TC_TS") != nullptr && atoi(getenv("HRC_TC_TS")) != 0;
+  // CTA pairs (cta_group::2, default from 2 query groups up; env HRC_TC_PAIR=0 disables): two query groups of the
+  // same corpus segment share every document tile — each CTA stages half of it — so the L2 -> shared-memory
+  // traffic and the B-operand reads per SM halve.  C3 (256 queries, 1M ragged documents, power-capped):
+  // 1233 vs 1186 TFLOP/s.  An odd last query group runs on the single-CTA kernel.
+  const bool use_pair = !use_ts && p.n_qgroups >= 2 && (getenv("HRC_TC_PAIR") == nullptr || atoi(getenv("HRC_TC_PAIR")) != 0);
+  if (use_pair) {
+    const int64_t tiles = (total_tokens + 127) / 128;
+    p.n_segments = int(tiles < sm_count() ? tiles : sm_count());
+    const int paired = p.n_qgroups & ~1;                // query groups handled by pairs
+    TcParams pp = p;
+    pp.n_qgroups = paired;
+    pp.n_queries = n_queries < paired * 8 ? n_queries : paired * 8;
+    int rc = launch_cfg<2, 128, false, 0, 2>(encode, d_tokens, d_queries, pp, dim3((unsigned)(pp.n_segments * paired)),
+                                             stream);
+    if (rc != 0 || paired == p.n_qgroups) return rc;
+    const int done = paired * 8;                        // the odd group: queries [done, n_queries)
+    TcParams pl = p;
+    pl.n_qgroups = 1;
+    pl.n_queries = n_queries - done;
+    pl.queries = p.queries + size_t(done) * lq * HRC_DIM;
+    pl.scores = p.scores + size_t(done) * size_t(n_items);
+    return launch_cfg<2, 128, false>(encode, d_tokens, pl.queries, pl, dim3((unsigned)pl.n_segments), stream);
+  }
   if (!use_ts) {
     const int64_t tiles = (total_tokens + 127) / 128;
     p.n_segments = int(tiles < sm_count() ? tiles : sm_count());
