@@ -29,6 +29,8 @@ SYMBOLS = {
                                      _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "hrc_maxsim_scores_ids": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int,
                                          _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p]),
+    "hrc_meanpool_cosine_scores": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int,
+                                              _c.c_int, _c.c_void_p, _c.c_void_p]),
     "hrc_search": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
                               _c.c_int32, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                               _c.c_int, _c.c_void_p]),
@@ -126,6 +128,27 @@ def maxsim_scores(tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.Te
         rc = load().hrc_maxsim_scores(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), _ptr(queries),
                                       nq, lq, _ptr(out), path, _stream(dev))
     _check(rc, "hrc_maxsim_scores")
+    return out
+
+
+def meanpool_cosine_scores(tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.Tensor, *,
+                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The reference's `_maxsim_score` exactly as coded (local_rag_complete.py:821-829): cosine of the
+    mean-pooled query and document token vectors -> fp32 [n_queries, n_docs]."""
+    dev = _require_cuda(tokens, offsets, queries)
+    assert tokens.dtype == torch.bfloat16 and tokens.dim() == 2 and tokens.shape[1] == DIM
+    assert offsets.dtype == torch.int64 and offsets.dim() == 1 and offsets.numel() >= 1
+    assert queries.dtype == torch.bfloat16 and queries.dim() == 3 and queries.shape[2] == DIM
+    n_docs = offsets.numel() - 1
+    nq, lq = int(queries.shape[0]), int(queries.shape[1])
+    if out is None:
+        out = torch.empty((nq, n_docs), dtype=torch.float32, device=dev)
+    else:
+        assert out.shape == (nq, n_docs) and out.dtype == torch.float32 and out.is_contiguous()
+    with torch.cuda.device(dev):
+        rc = load().hrc_meanpool_cosine_scores(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]),
+                                               _ptr(queries), nq, lq, _ptr(out), _stream(dev))
+    _check(rc, "hrc_meanpool_cosine_scores")
     return out
 
 

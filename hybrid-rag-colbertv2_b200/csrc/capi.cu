@@ -31,6 +31,7 @@ int launch_keys_unpack(const uint64_t*, int64_t, int32_t*, float*, cudaStream_t)
 int launch_rerank_unpack(const uint64_t*, int, int, const int32_t*, int, int32_t*, int32_t*, float*, cudaStream_t);
 int launch_rrf(const int32_t*, int, const int32_t*, int, int, int, int, int32_t*, double*, int32_t*, cudaStream_t);
 int launch_synth(void*, int64_t, int64_t, uint64_t, cudaStream_t);
+int launch_meanpool_cosine(const void*, const int64_t*, int64_t, const void*, int, int, float*, cudaStream_t);
 
 static int check_device() {
   static int ok = -1;
@@ -92,6 +93,18 @@ int hrc_maxsim_scores_ids(const void* d_tokens, const int64_t* d_offsets, int64_
   HRC_REQUIRE(n_cand == 0 || d_cand_ids != nullptr, "maxsim_ids: null candidate list");
   return maxsim_dispatch(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_cand, d_queries, n_queries, lq,
                          d_scores, path, static_cast<cudaStream_t>(stream));
+}
+
+int hrc_meanpool_cosine_scores(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                               const void* d_queries, int n_queries, int lq, float* d_scores, void* stream) {
+  if (int rc = check_device()) return rc;
+  HRC_REQUIRE(n_docs >= 0 && total_tokens >= 0 && n_queries >= 0 && lq >= 1, "meanpool_cosine: negative size or lq < 1");
+  HRC_REQUIRE(n_docs == 0 || n_queries == 0 ||
+                  (d_offsets != nullptr && d_queries != nullptr && d_scores != nullptr && (total_tokens == 0 || d_tokens != nullptr)),
+              "meanpool_cosine: null pointer argument");
+  HRC_REQUIRE((reinterpret_cast<uintptr_t>(d_tokens) & 15) == 0, "meanpool_cosine: token buffer must be 16-byte aligned");
+  return launch_meanpool_cosine(d_tokens, d_offsets, n_docs, d_queries, n_queries, lq, d_scores,
+                                static_cast<cudaStream_t>(stream));
 }
 
 int hrc_search(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens, const void* d_queries,

@@ -42,6 +42,9 @@ class RAGConfig:
     rrf_k: int = 60                 # the constant at local_rag_complete.py:964
     rerank_candidates: int = 50     # the slice at :916
     score_reduction: str = "sum"    # "sum" (north_star / ColBERT) or "mean" (docstring :810-811); same ranking
+    # "maxsim": what the docstring (:807-812) and north_star define.  "reference_literal": what :821-829 actually
+    # compute (cosine of mean-pooled vectors) — for reproducing the reference's own rankings.
+    score_mode: str = "maxsim"
     maxsim_path: int = _lib.PATH_AUTO
 
 
@@ -141,12 +144,22 @@ class JinaColBERTRetriever:
     def _finish_scores(self, scores: torch.Tensor, lq: int) -> torch.Tensor:
         return scores / float(lq) if self.config.score_reduction == "mean" else scores
 
-    def score_embeddings(self, query_embeddings: torch.Tensor) -> torch.Tensor:
-        """MaxSim of every query against every stored document: fp32 [Bq, N] on the device."""
-        self._require_store()
-        q = self._prep_queries(query_embeddings)
-        s = _lib.maxsim_scores(self.store.tokens, self.store.offsets, q, path=self.config.maxsim_path)
+    def _literal(self, mode: Optional[str] = None) -> bool:
+        mode = self.config.score_mode if mode is None else mode
+        if mode not in ("maxsim", "reference_literal"):
+            raise ValueError(f"score_mode must be 'maxsim' or 'reference_literal', got {mode!r}")
+        return mode == "reference_literal"
+
+    def _score_store(self, store: PackedStore, q: torch.Tensor, mode: Optional[str] = None) -> torch.Tensor:
+        if self._literal(mode):
+            return _lib.meanpool_cosine_scores(store.tokens, store.offsets, q)
+        s = _lib.maxsim_scores(store.tokens, store.offsets, q, path=self.config.maxsim_path)
         return self._finish_scores(s, q.shape[1])
+
+    def score_embeddings(self, query_embeddings: torch.Tensor) -> torch.Tensor:
+        """Score of every query against every stored document: fp32 [Bq, N] on the device."""
+        self._require_store()
+        return self._score_store(self.store, self._prep_queries(query_embeddings))
 
     def search_keys(self, query_embeddings: torch.Tensor, k: int) -> torch.Tensor:
         """Sorted top-k (score, GLOBAL doc id) keys per query: int64 [Bq, min(k, N)] on the device."""
@@ -159,12 +172,18 @@ class JinaColBERTRetriever:
         if k_eff <= 0:
             z = torch.zeros((q.shape[0], 0), dtype=torch.int64, device=self.device)
             return z, z.to(torch.int32), z.to(torch.float32)
+        if self._literal():
+            keys = _lib.topk(self._score_store(self.store, q), k_eff, id_base=self.store.doc_id_base)
+            ids, sc = _lib.keys_unpack(keys) if unpack else (None, None)
+            return keys, ids, sc
         return _lib.search(self.store.tokens, self.store.offsets, q, k_eff, id_base=self.store.doc_id_base,
                            path=self.config.maxsim_path, buffers=self._buffers, unpack=unpack)
 
     def search_embeddings(self, query_embeddings: torch.Tensor, k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
         """(doc ids int32 [Bq, k'], scores fp32 [Bq, k']) with k' = min(k, N), best first."""
         _, ids, scores = self._search(query_embeddings, k, unpack=True)
+        if self._literal():
+            return ids, scores
         return ids, self._finish_scores(scores, _as_query_batch(query_embeddings).shape[1])
 
     search_batch = search_embeddings
@@ -183,6 +202,13 @@ class JinaColBERTRetriever:
             cand = cand.unsqueeze(0)
         cand = cand.contiguous()
         k_eff = min(int(k), cand.shape[1])
+        if self._literal():   # characterisation mode: score the whole store, gather the candidates
+            full = self._score_store(self.store, q)
+            ok = (cand >= 0) & (cand < self.store.n_docs)
+            cs = torch.gather(full, 1, cand.clamp(0, max(self.store.n_docs - 1, 0)).long())
+            cs = torch.where(ok, cs, torch.full_like(cs, float("-inf"))).contiguous()
+            pos, top_scores = _lib.keys_unpack(_lib.topk(cs, k_eff))
+            return pos, torch.gather(cand, 1, pos.clamp_min(0).long()), top_scores
         pos, doc_ids, top_scores, _ = _lib.rerank(self.store.tokens, self.store.offsets, cand, q, k_eff,
                                                   path=self.config.maxsim_path)
         return pos, doc_ids, self._finish_scores(top_scores, q.shape[1])
@@ -218,10 +244,9 @@ class JinaColBERTRetriever:
         doc_embeddings = self.model.encode(documents, convert_to_tensor=True)
         tmp = self._pack(doc_embeddings)
         q = self._prep_queries(query_embedding)
-        scores = _lib.maxsim_scores(tmp.tokens, tmp.offsets, q, path=self.config.maxsim_path)
+        scores = self._score_store(tmp, q)
         keys = _lib.topk(scores, min(int(k), tmp.n_docs))
         pos, top = _lib.keys_unpack(keys)
-        top = self._finish_scores(top, q.shape[1])
         results = []
         for rank, (idx, score) in enumerate(zip(pos[0].tolist(), top[0].tolist())):
             results.append({
@@ -232,8 +257,10 @@ class JinaColBERTRetriever:
             })
         return results
 
-    def _maxsim_score(self, query_embedding: torch.Tensor, doc_embeddings: torch.Tensor) -> torch.Tensor:
-        """MaxSim between query and documents (:802-831), as the docstring (:807-812) defines it.
+    def _maxsim_score(self, query_embedding: torch.Tensor, doc_embeddings: torch.Tensor,
+                      mode: Optional[str] = None) -> torch.Tensor:
+        """MaxSim between query and documents (:802-831), as the docstring (:807-812) defines it — or, with
+        mode="reference_literal" (default: config.score_mode), what :821-829 literally compute.
 
         Shapes follow :813-817 and the squeeze at :831: query [Lq, D] or [Bq, Lq, D]; documents
         [N, Ld, D] dense (every row a real token; a 2-D tensor is ONE document).  Returns fp32 [N],
@@ -241,8 +268,7 @@ class JinaColBERTRetriever:
         """
         q = self._prep_queries(query_embedding)
         tmp = PackedStore.from_dense(doc_embeddings, None, device=self.device)
-        s = _lib.maxsim_scores(tmp.tokens, tmp.offsets, q, path=self.config.maxsim_path)
-        return self._finish_scores(s, q.shape[1]).squeeze()
+        return self._score_store(tmp, q, mode).squeeze()
 
 
 class DualIndexer:

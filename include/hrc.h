@@ -76,6 +76,17 @@ int hrc_maxsim_scores_ids(const void* d_tokens, const int64_t* d_offsets, int64_
                           int path, void* stream);
 
 /*
+ * The reference's `_maxsim_score` EXACTLY AS CODED, local_rag_complete.py:821-829 — the cosine of the
+ * mean-pooled token vectors (its "simplified" stand-in for MaxSim):
+ *   d_scores[q * n_docs + d] = cos( mean_i Q[q][i] , mean_{t in doc d} tokens[t] ),  eps = 1e-8 (torch default)
+ * Same layouts as hrc_maxsim_scores; an empty document scores NaN (torch's mean over an empty axis).
+ * Pinned by vectors the unmodified reference produced (tests/golden/literal_maxsim.npz).
+ */
+int hrc_meanpool_cosine_scores(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs,
+                               int64_t total_tokens, const void* d_queries, int n_queries, int lq,
+                               float* d_scores, void* stream);
+
+/*
  * Fused search: MaxSim of every query against the whole store, per-query top-k, optional unpacking —
  * the body of JinaColBERTRetriever.search (local_rag_complete.py:764-775) in one call.
  *   d_scores_ws  : fp32 [n_queries][n_docs] scratch (holds the full score matrix on return)

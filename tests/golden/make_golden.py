@@ -6,6 +6,8 @@ The reference script cannot be imported as shipped (5 third-party imports are ab
 SURVEY.md F4), so those imports are stubbed with MagicMock exactly as in SURVEY.md §A.1; nothing in
 /root/reference is edited or copied.  Outputs (small, committed):
   literal_maxsim.npz  inputs + outputs of the reference's `_maxsim_score` (what it literally computes)
+  literal_bf16.npz    the same on bf16-REPRESENTABLE inputs (so the packed bf16 store loses nothing) plus the
+                      reference's own search() / rerank() results on them: pins the GPU "reference_literal" path
   api_shapes.json     search()/rerank()/index()/load() observable behaviour with a fake encoder
   rrf.json            `_reciprocal_rank_fusion` ids + fp64 scores (repr round-trips) incl. tie order
 """
@@ -70,6 +72,41 @@ def main():
         out_qb_D=R._maxsim_score(qb, D).numpy(),
         out_q_D2d=R._maxsim_score(q, D[0]).numpy(),          # 2-D docs -> ONE document -> 0-d
         out_q_D1=R._maxsim_score(q, D[:1]).numpy(),          # N == 1 -> 0-d
+    )
+
+    # ---- 1b. the same on bf16-representable inputs, plus search()/rerank() through the reference ---------
+    def bf16r(x):
+        return x.to(torch.bfloat16).to(torch.float32)
+
+    g = torch.Generator().manual_seed(20260105)
+    q2 = bf16r(torch.nn.functional.normalize(torch.randn((32, 128), generator=g), dim=-1))
+    qb2 = bf16r(torch.nn.functional.normalize(torch.randn((3, 32, 128), generator=g), dim=-1))
+    D2 = bf16r(torch.nn.functional.normalize(torch.randn((64, 24, 128), generator=g) +
+                                             0.6 * torch.randn((64, 1, 128), generator=g), dim=-1))
+
+    class FixedEncoder:                 # encode(str) -> q2; encode(list of "d<i>") -> those rows of D2
+        def encode(self, x, **kw):
+            if isinstance(x, str):
+                return q2
+            return torch.stack([D2[int(t[1:])] for t in x])
+
+    R.config = m.RAGConfig()
+    R.model = FixedEncoder()
+    R.corpus_embeddings = D2
+    R.corpus = [f"d{i}" for i in range(64)]
+    s10 = R.search("query", k=10)
+    cand = [40, 3, 17, 63, 0, 22, 9, 51, 33, 12, 5, 28]
+    r5 = R.rerank("query", [f"d{i}" for i in cand], k=5)
+    np.savez_compressed(
+        os.path.join(HERE, "literal_bf16.npz"),
+        q=q2.numpy(), qb=qb2.numpy(), D=D2.numpy(),
+        out_q_D=R._maxsim_score(q2, D2).numpy(),
+        out_qb_D=R._maxsim_score(qb2, D2).numpy(),
+        search_ids=np.array([r['document_id'] for r in s10], dtype=np.int64),
+        search_scores=np.array([r['score'] for r in s10], dtype=np.float64),
+        rerank_cand=np.array(cand, dtype=np.int64),
+        rerank_index=np.array([r['result_index'] for r in r5], dtype=np.int64),
+        rerank_scores=np.array([r['score'] for r in r5], dtype=np.float64),
     )
 
     # ---- 2. API behaviour with a fake encoder ---------------------------------------------------

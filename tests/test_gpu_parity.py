@@ -99,6 +99,52 @@ def test_batched_kernel_more_shapes(cuda_dev, shape, pair, monkeypatch):
     _assert_scores(got, exp, f"batched pair={pair} {shape}")
 
 
+def test_reference_literal_path_matches_reference_outputs(cuda_dev, golden_dir):
+    """PINNED parity: the mean-pool-cosine kernel (what the reference's `_maxsim_score` literally computes,
+    local_rag_complete.py:821-829) and the retriever in score_mode="reference_literal" against vectors the
+    UNMODIFIED reference produced (tests/golden/literal_bf16.npz, inputs exactly representable in bf16)."""
+    import hybrid_rag_colbertv2_b200 as hrc
+    L = _lib()
+    z = np.load(os.path.join(golden_dir, "literal_bf16.npz"))
+    q, qb, D = (torch.from_numpy(z[k]) for k in ("q", "qb", "D"))
+    n, ld, _ = D.shape
+    tok = D.reshape(n * ld, 128).to(torch.bfloat16).to(cuda_dev)
+    off = torch.arange(0, (n + 1) * ld, ld, dtype=torch.int64, device=cuda_dev)
+    got = L.meanpool_cosine_scores(tok, off, q.unsqueeze(0).to(torch.bfloat16).to(cuda_dev))
+    _assert_scores(got[0], torch.from_numpy(z["out_q_D"]), "literal q")
+    gotb = L.meanpool_cosine_scores(tok, off, qb.to(torch.bfloat16).to(cuda_dev))
+    _assert_scores(gotb, torch.from_numpy(z["out_qb_D"]), "literal qb")
+
+    class FixedEncoder:                       # the encoder make_golden.py gave the reference
+        def encode(self, x, **kw):
+            return q if isinstance(x, str) else torch.stack([D[int(t[1:])] for t in x])
+
+    r = hrc.JinaColBERTRetriever(hrc.RAGConfig(score_mode="reference_literal"), encoder=FixedEncoder())
+    r.index_embeddings(D, corpus=[f"d{i}" for i in range(n)])
+    res = r.search(query="query", k=10)
+    exp_scores = torch.from_numpy(z["out_q_D"])
+    assert o.check_ranking([x["document_id"] for x in res], [x["score"] for x in res], exp_scores, 10, RTOL) is None
+    assert [x["document_id"] for x in res][:5] == z["search_ids"].tolist()[:5]      # gaps there are > tolerance
+    np.testing.assert_allclose([x["score"] for x in res], z["search_scores"], rtol=0, atol=RTOL * 0.22)
+    cand = z["rerank_cand"].tolist()
+    rr = r.rerank(query="query", documents=[f"d{i}" for i in cand], k=5)
+    assert [x["result_index"] for x in rr] == z["rerank_index"].tolist()
+    np.testing.assert_allclose([x["score"] for x in rr], z["rerank_scores"], rtol=0, atol=RTOL * 0.22)
+    assert [x["rank"] for x in rr] == [1, 2, 3, 4, 5]
+    # _maxsim_score(mode=...) keeps the reference's shapes (:813-817, :831)
+    s = r._maxsim_score(q, D)
+    assert s.shape == (n,)
+    _assert_scores(s, exp_scores, "_maxsim_score literal")
+    assert r._maxsim_score(q, D, mode="maxsim").shape == (n,) and float(r._maxsim_score(q, D, mode="maxsim").min()) > 2.0
+    # ragged store + empty document: NaN like torch's mean over an empty axis
+    q3, tok3, off3 = _case(5, 0, 0, 0, 2, 32, lens=[3, 0, 130, 1, 77])
+    g3 = L.meanpool_cosine_scores(tok3.to(cuda_dev), off3.to(cuda_dev), q3.to(cuda_dev)).cpu()
+    assert bool(torch.isnan(g3[:, 1]).all())
+    for d in (0, 2, 3, 4):
+        e = o.literal_reference(q3.float(), tok3[int(off3[d]):int(off3[d + 1])].float())
+        assert float((g3[:, d] - e).abs().max()) < 1e-4
+
+
 def test_fused_search_and_rerank_calls(cuda_dev):
     """hrc_search / hrc_rerank (one C call each) equal the staged calls bit for bit."""
     L = _lib()
@@ -404,4 +450,55 @@ def test_full_size_properties_c2(cuda_dev):
     assert o.check_ranking(ids_c.tolist()[:50], sc_c.tolist()[:50], full_exp, 50, RTOL) is None
     # (5) shard invariance: scores of a 4-way document split are bit-identical
     parts = [L.maxsim_scores(s.tokens, s.offsets, q) for s in (store.shard(rk, 4) for rk in range(4))]
+    assert torch.equal(torch.cat(parts, 1), scores)
+
+
+def test_full_size_properties_c3(cuda_dev):
+    """BASELINE config C3 shape at full corpus size (1M documents of 32..512 tokens, ~70 GB) with 24 queries
+    (a CTA-pair launch for two query groups plus the odd group on the single-CTA kernel): size-independent checks."""
+    import hybrid_rag_colbertv2_b200 as hrc
+    from hybrid_rag_colbertv2_b200.synth import plant, synth_queries, synth_store
+    L = _lib()
+    free, _ = torch.cuda.mem_get_info()
+    n_docs = 1_000_000 if free > 100e9 else 100_000
+    store = synth_store(n_docs, 32, 512, seed=20260103, device=cuda_dev)
+    nq = 24
+    q = synth_queries(nq, 32, device=cuda_dev)
+    planted = plant(store, q[:2], n_planted=60)
+    r = hrc.JinaColBERTRetriever(hrc.RAGConfig())
+    r.store = store
+    scores = r.score_embeddings(q)
+    assert scores.shape == (nq, n_docs) and bool(torch.isfinite(scores).all())
+    # (1) sampled documents (+ the planted ones) re-scored by the oracle, every query
+    g = torch.Generator().manual_seed(2)
+    sample = torch.unique(torch.cat([torch.randint(0, n_docs, (1500,), generator=g), planted.reshape(-1),
+                                     torch.tensor([0, n_docs - 1])]))
+    off = store.offsets.cpu()
+    lens = (off[1:] - off[:-1])[sample]
+    rows = torch.cat([torch.arange(int(off[d]), int(off[d + 1])) for d in sample.tolist()])
+    sub_tok = store.tokens[rows.to(cuda_dev)].float().cpu()
+    sub_off = torch.zeros(sample.numel() + 1, dtype=torch.int64)
+    sub_off[1:] = torch.cumsum(lens, 0)
+    exp = o.maxsim_scores(q.float().cpu(), sub_tok, sub_off)
+    _assert_scores(scores[:, sample.to(cuda_dev)], exp, "C3 sample")
+    # (2) every query of the batch equals the single-query kernel on the same corpus (different kernels,
+    #     same fp32 accumulation): within tolerance everywhere
+    for qi in (0, 7, 8, 15, 16, 23):
+        single = L.maxsim_scores(store.tokens, store.offsets, q[qi:qi + 1])
+        scale = float(single.abs().max())
+        assert float((single[0] - scores[qi]).abs().max()) <= RTOL * scale, f"query {qi}"
+    # (3) top-100 per query: sorted, unique, consistent with the score matrix and with torch.topk's values
+    ids, sc = r.search_embeddings(q, 100)
+    for qi in range(nq):
+        ids_c, sc_c = ids[qi].cpu(), sc[qi].cpu()
+        assert len(set(ids_c.tolist())) == 100 and bool((sc_c[:-1] >= sc_c[1:]).all())
+        assert torch.equal(scores[qi, ids[qi].to(torch.int64)].cpu(), sc_c)
+        assert torch.equal(torch.topk(scores[qi], 100).values.cpu(), sc_c)
+    # (4) planted documents lead the two planted queries, in the oracle's order
+    for qi in range(2):
+        full_exp = torch.full((n_docs,), float('-inf'))
+        full_exp[sample] = exp[qi]
+        assert o.check_ranking(ids[qi].cpu().tolist()[:30], sc[qi].cpu().tolist()[:30], full_exp, 30, RTOL) is None
+    # (5) shard invariance: a 3-way document split gives bit-identical scores
+    parts = [L.maxsim_scores(s.tokens, s.offsets, q) for s in (store.shard(rk, 3) for rk in range(3))]
     assert torch.equal(torch.cat(parts, 1), scores)

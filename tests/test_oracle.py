@@ -22,6 +22,25 @@ def test_literal_reference_bit_equal_to_reference_outputs(golden_dir):
     assert o.literal_reference(q, D[0]).dim() == 0          # 2-D docs are ONE document
 
 
+def test_literal_reference_on_bf16_representable_fixture(golden_dir):
+    """literal_bf16.npz: inputs exactly representable in bf16 (the packed store loses nothing) and the
+    reference's own search()/rerank() results on them — the fixture that pins the GPU reference_literal path."""
+    z = np.load(os.path.join(golden_dir, "literal_bf16.npz"))
+    q, qb, D = (torch.from_numpy(z[k]) for k in ("q", "qb", "D"))
+    for t in (q, qb, D):
+        assert torch.equal(o.round_bf16(t), t)
+    s = o.literal_reference(q, D)
+    assert torch.equal(s, torch.from_numpy(z["out_q_D"]))
+    assert torch.equal(o.literal_reference(qb, D), torch.from_numpy(z["out_qb_D"]))
+    res = o.search_reference(s, None, 10)
+    assert [r["document_id"] for r in res] == z["search_ids"].tolist()
+    assert [r["score"] for r in res] == z["search_scores"].tolist()
+    cand = z["rerank_cand"].tolist()
+    rr = o.rerank_reference(o.literal_reference(q, D[cand]), [f"d{i}" for i in cand], 5)
+    assert [r["result_index"] for r in rr] == z["rerank_index"].tolist()
+    assert [r["score"] for r in rr] == z["rerank_scores"].tolist()
+
+
 def test_reference_is_not_maxsim(golden_dir):
     """what the reference computes differs from MaxSim, hence the restated oracle."""
     z = np.load(os.path.join(golden_dir, "literal_maxsim.npz"))
