@@ -222,8 +222,10 @@ def run_ours(args):
 
     def step_e2e(i):
         qh = q_host[i % n_q]
+        if searcher is None:                      # one C call: H2D, bf16, MaxSim, top-k, unpack, D2H; one sync
+            return retr.search_host(qh, K)
         q = qh.to(dev, non_blocking=True)
-        keys = searcher.search_keys(q, K) if searcher else retr.search_keys(q, K)
+        keys = searcher.search_keys(q, K)
         ids, scores = _lib.keys_unpack(keys)
         return ids.cpu(), scores.cpu()
 
@@ -309,7 +311,9 @@ def run_ours(args):
         "e2e": {"value": docs_per_step / (e2e_ms_total / args.steps * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": int(q_host[0].numel() * 4), "d2h_bytes_per_step": K * 8,
                 "ms_per_step": e2e_ms_total / args.steps,
-                "api": "host fp32 query (pinned) -> search_keys -> keys_unpack -> ids/scores .cpu()"},
+                "api": ("JinaColBERTRetriever.search_host: pinned fp32 query -> hrc_search_host (H2D, bf16, MaxSim, top-k, "
+                        "unpack, D2H) -> ids/scores on the host" if world == 1 else
+                        "host fp32 query (pinned) -> ShardedSearcher.search_keys -> keys_unpack -> ids/scores .cpu()")},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
     }

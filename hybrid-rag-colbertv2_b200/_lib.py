@@ -34,6 +34,10 @@ SYMBOLS = {
     "hrc_search": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
                               _c.c_int32, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                               _c.c_int, _c.c_void_p]),
+    "hrc_search_host_workspace_bytes": (_c.c_size_t, [_c.c_int64, _c.c_int, _c.c_int, _c.c_int]),
+    "hrc_search_host": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int,
+                                   _c.c_int, _c.c_int32, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_int,
+                                   _c.c_void_p]),
     "hrc_rerank": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_void_p,
                               _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                               _c.c_void_p, _c.c_int, _c.c_void_p]),
@@ -204,6 +208,50 @@ def search(tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.Tensor, k
                                _ptr(scores), path, _stream(dev))
     _check(rc, "hrc_search")
     return keys, ids, scores
+
+
+class HostSearch:
+    """End-to-end search with host buffers (hrc_search_host): pinned fp32 queries in, pinned ids / scores out,
+    one C call and one stream synchronisation per search.  Buffers are kept between calls."""
+
+    def __init__(self):
+        self.key = None
+
+    def _ensure(self, dev, nq: int, lq: int, n_docs: int, k: int):
+        key = (str(dev), nq, lq, n_docs, k)
+        if self.key != key:
+            need = int(load().hrc_search_host_workspace_bytes(n_docs, nq, lq, k))
+            self.ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+            self.ws_bytes = need
+            self.q_pinned = torch.empty((nq, lq, DIM), dtype=torch.float32).pin_memory()
+            self.ids = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+            self.scores = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+            self.key = key
+
+    def __call__(self, tokens: torch.Tensor, offsets: torch.Tensor, queries_host: torch.Tensor, k: int, *,
+                 id_base: int = 0, path: int = PATH_AUTO):
+        """queries_host: fp32 CPU tensor [nq, lq, 128] (pinned: used in place; pageable: staged through a pinned
+        buffer).  Returns (ids int32 [nq, k], scores fp32 [nq, k]) as PINNED CPU tensors owned by this object
+        (valid until the next call)."""
+        dev = _require_cuda(tokens, offsets)
+        assert tokens.dtype == torch.bfloat16 and offsets.dtype == torch.int64
+        assert not queries_host.is_cuda and queries_host.dtype == torch.float32 and queries_host.dim() == 3
+        assert queries_host.shape[2] == DIM and queries_host.is_contiguous()
+        n_docs = offsets.numel() - 1
+        nq, lq = int(queries_host.shape[0]), int(queries_host.shape[1])
+        self._ensure(dev, nq, lq, n_docs, k)
+        src = queries_host
+        if not src.is_pinned():
+            self.q_pinned.copy_(src)
+            src = self.q_pinned
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            rc = load().hrc_search_host(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), src.data_ptr(), nq,
+                                        lq, k, id_base, _ptr(self.ws), self.ws_bytes, self.ids.data_ptr(),
+                                        self.scores.data_ptr(), path, stream.cuda_stream)
+            _check(rc, "hrc_search_host")
+            stream.synchronize()
+        return self.ids, self.scores
 
 
 def rerank(tokens: torch.Tensor, offsets: torch.Tensor, cand_ids: torch.Tensor, queries: torch.Tensor, k: int, *,

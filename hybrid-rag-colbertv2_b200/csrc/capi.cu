@@ -68,6 +68,32 @@ static int maxsim_dispatch(const void* d_tokens, const int64_t* d_offsets, int64
                             stream);
 }
 
+// fp32 -> bf16 (round to nearest even, what torch's .to(torch.bfloat16) does) for queries that arrive from the host
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct HostSearchLayout {
+  size_t q32, q16, scores, topk, keys, ids, out_scores, total, topk_bytes;
+};
+static HostSearchLayout host_search_layout(int64_t n_docs, int n_queries, int lq, int k) {
+  HostSearchLayout L;
+  size_t o = 0;
+  L.q32 = o; o += align256(size_t(n_queries) * lq * HRC_DIM * sizeof(float));
+  L.q16 = o; o += align256(size_t(n_queries) * lq * HRC_DIM * 2);
+  L.scores = o; o += align256(size_t(n_queries) * size_t(n_docs) * sizeof(float));
+  L.topk_bytes = topk_workspace_bytes(n_docs, n_queries, k);
+  L.topk = o; o += align256(L.topk_bytes);
+  L.keys = o; o += align256(size_t(n_queries) * k * sizeof(uint64_t));
+  L.ids = o; o += align256(size_t(n_queries) * k * sizeof(int32_t));
+  L.out_scores = o; o += align256(size_t(n_queries) * k * sizeof(float));
+  L.total = o;
+  return L;
+}
+
 }  // namespace hrc
 
 using namespace hrc;
@@ -120,6 +146,42 @@ int hrc_search(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, i
     return rc;
   if (d_ids_out != nullptr || d_scores_out != nullptr)
     return launch_keys_unpack(d_keys_out, int64_t(n_queries) * k, d_ids_out, d_scores_out, st);
+  return 0;
+}
+
+size_t hrc_search_host_workspace_bytes(int64_t n_docs, int n_queries, int lq, int k) {
+  if (n_docs < 0 || n_queries < 0 || lq < 1 || k < 0) return 0;
+  return host_search_layout(n_docs, n_queries, lq, k).total;
+}
+
+int hrc_search_host(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                    const float* h_queries, int n_queries, int lq, int k, int32_t id_base, void* d_workspace,
+                    size_t workspace_bytes, int32_t* h_ids_out, float* h_scores_out, int path, void* stream) {
+  if (int rc = check_device()) return rc;
+  HRC_REQUIRE(n_queries >= 0 && lq >= 1 && k >= 0 && k <= n_docs, "search_host: bad sizes (k=%d must be in [0, n_docs])", k);
+  if (n_queries == 0 || k == 0) return 0;
+  HRC_REQUIRE(h_queries != nullptr && h_ids_out != nullptr && h_scores_out != nullptr && d_workspace != nullptr,
+              "search_host: null buffer");
+  const HostSearchLayout L = host_search_layout(n_docs, n_queries, lq, k);
+  HRC_REQUIRE(workspace_bytes >= L.total, "search_host: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+  HRC_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, "search_host: workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+  float* q32 = reinterpret_cast<float*>(ws + L.q32);
+  __nv_bfloat16* q16 = reinterpret_cast<__nv_bfloat16*>(ws + L.q16);
+  const int64_t nq_elems = int64_t(n_queries) * lq * HRC_DIM;
+  HRC_CHECK_CUDA(cudaMemcpyAsync(q32, h_queries, size_t(nq_elems) * sizeof(float), cudaMemcpyHostToDevice, st));
+  f32_to_bf16_kernel<<<unsigned((nq_elems + 255) / 256), 256, 0, st>>>(q32, q16, nq_elems);
+  count_launch();
+  HRC_CHECK_CUDA(cudaGetLastError());
+  int32_t* d_ids = reinterpret_cast<int32_t*>(ws + L.ids);
+  float* d_sc = reinterpret_cast<float*>(ws + L.out_scores);
+  if (int rc = hrc_search(d_tokens, d_offsets, n_docs, total_tokens, q16, n_queries, lq, k, id_base,
+                          reinterpret_cast<float*>(ws + L.scores), ws + L.topk, L.topk_bytes,
+                          reinterpret_cast<uint64_t*>(ws + L.keys), d_ids, d_sc, path, stream))
+    return rc;
+  HRC_CHECK_CUDA(cudaMemcpyAsync(h_ids_out, d_ids, size_t(n_queries) * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  HRC_CHECK_CUDA(cudaMemcpyAsync(h_scores_out, d_sc, size_t(n_queries) * k * sizeof(float), cudaMemcpyDeviceToHost, st));
   return 0;
 }
 

@@ -68,6 +68,7 @@ class JinaColBERTRetriever:
         self.store: Optional[PackedStore] = None
         self.corpus: Optional[List[str]] = None
         self._buffers = _lib.SearchBuffers()
+        self._host_search = _lib.HostSearch()
 
     # `corpus_embeddings` is the reference's attribute name for the store (:725,:735,:752)
     @property
@@ -188,6 +189,22 @@ class JinaColBERTRetriever:
 
     search_batch = search_embeddings
 
+    def search_host(self, query_embeddings: torch.Tensor, k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
+        """End-to-end search from a HOST query embedding (what an encoder hands over) to HOST results: fp32 CPU
+        [Lq, 128] or [Bq, Lq, 128] in, (doc ids int32, scores fp32) CPU tensors out, one C call (hrc_search_host)."""
+        self._require_store()
+        q = _as_query_batch(query_embeddings)
+        if q.is_cuda or self._literal():
+            ids, sc = self.search_embeddings(q, k)
+            return ids.cpu(), sc.cpu()
+        q = q.to(torch.float32).contiguous()
+        k_eff = min(int(k), self.store.n_docs)
+        if k_eff <= 0:
+            return torch.zeros((q.shape[0], 0), dtype=torch.int32), torch.zeros((q.shape[0], 0))
+        ids, sc = self._host_search(self.store.tokens, self.store.offsets, q, k_eff, id_base=self.store.doc_id_base,
+                                    path=self.config.maxsim_path)
+        return ids, self._finish_scores(sc, q.shape[1])
+
     def rerank_ids(self, query_embeddings: torch.Tensor, candidate_ids: torch.Tensor, k: int = 10
                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """Rerank stored documents by id without re-encoding them.
@@ -223,8 +240,8 @@ class JinaColBERTRetriever:
     def search(self, query: str, k: int = 10) -> List[Dict]:
         """Search using MaxSim scoring (:755-777)."""
         query_embedding = self.model.encode(query, convert_to_tensor=True)
-        ids, scores = self.search_embeddings(query_embedding, k)
-        ids_h, scores_h = ids[0].tolist(), scores[0].tolist()   # one device->host copy each, not k syncs
+        ids, scores = self.search_host(query_embedding, k)      # host embedding in, host ids/scores out, one sync
+        ids_h, scores_h = ids[0].tolist(), scores[0].tolist()
         results = []
         for idx, score in zip(ids_h, scores_h):
             if idx < 0:

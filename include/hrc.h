@@ -99,6 +99,21 @@ int hrc_search(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, i
                float* d_scores_out, int path, void* stream);
 
 /*
+ * End-to-end search with HOST buffers — what JinaColBERTRetriever.search does between "the encoder returned the
+ * query embedding" (local_rag_complete.py:758-761) and "the result list is built" (:769-775), in one call:
+ * H2D copy of the fp32 query embeddings, fp32 -> bf16, MaxSim over the whole store, per-query top-k, unpack, and
+ * D2H copies of ids and scores.  Everything is enqueued on `stream`; the caller synchronises the stream before
+ * reading h_ids_out / h_scores_out.  Host buffers should be pinned (page-locked) for the copies to be asynchronous.
+ *   h_queries    : fp32 [n_queries][lq][128] host
+ *   d_workspace  : hrc_search_host_workspace_bytes(n_docs, n_queries, lq, k) bytes of device scratch, 256-B aligned
+ *   h_ids_out    : int32 [n_queries][k] host;  h_scores_out : fp32 [n_queries][k] host
+ */
+size_t hrc_search_host_workspace_bytes(int64_t n_docs, int n_queries, int lq, int k);
+int hrc_search_host(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                    const float* h_queries, int n_queries, int lq, int k, int32_t id_base, void* d_workspace,
+                    size_t workspace_bytes, int32_t* h_ids_out, float* h_scores_out, int path, void* stream);
+
+/*
  * Fused rerank: MaxSim of query q against its candidate list, sorted top-k — the body of
  * JinaColBERTRetriever.rerank (local_rag_complete.py:786-798) on stored embeddings.
  *   d_cand_ids   : int32 [n_queries][n_cand] (n_cand <= 8192)

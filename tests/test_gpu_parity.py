@@ -168,6 +168,25 @@ def test_fused_search_and_rerank_calls(cuda_dev):
         L.search(tok_d, off_d, q_d, 20_001)
 
 
+def test_search_host_equals_device_search(cuda_dev):
+    """hrc_search_host (host fp32 queries in, host ids/scores out, one C call) == the device-tensor API."""
+    import hybrid_rag_colbertv2_b200 as hrc
+    q, tok, off = _case(41, 5000, 8, 90, 3, 32)
+    r = hrc.JinaColBERTRetriever(hrc.RAGConfig())
+    r.index_embeddings(tok, off, packed=True)
+    qf = q.float()                                            # bf16-representable fp32, as an encoder would hand over
+    ids_d, sc_d = r.search_embeddings(qf, 50)
+    for host_q in (qf, qf.pin_memory()):
+        ids_h, sc_h = r.search_host(host_q, 50)
+        assert not ids_h.is_cuda and ids_h.dtype == torch.int32 and ids_h.shape == (3, 50)
+        assert torch.equal(ids_h, ids_d.cpu()) and torch.equal(sc_h, sc_d.cpu())
+    one_i, one_s = r.search_host(qf[1], 7)                    # [Lq, 128] -> one query
+    assert torch.equal(one_i[0], ids_d[1, :7].cpu()) and torch.equal(one_s[0], sc_d[1, :7].cpu())
+    small = hrc.JinaColBERTRetriever(hrc.RAGConfig())
+    small.index_embeddings(tok[: int(off[30])], off[:31], packed=True)
+    assert small.search_host(qf, 1000)[0].shape == (3, 30)    # k clamps to N (:767)
+
+
 def test_simt_handles_long_queries(cuda_dev):
     L = _lib()
     q, tok, off = _case(11, 25, 1, 70, 2, 77)
