@@ -224,10 +224,7 @@ def run_ours(args):
         qh = q_host[i % n_q]
         if searcher is None:                      # one C call: H2D, bf16, MaxSim, top-k, unpack, D2H; one sync
             return retr.search_host(qh, K)
-        q = qh.to(dev, non_blocking=True)
-        keys = searcher.search_keys(q, K)
-        ids, scores = _lib.keys_unpack(keys)
-        return ids.cpu(), scores.cpu()
+        return searcher.search_host(qh, K)        # H2D, local search, all-gather, merge, unpack, D2H; one sync
 
     def barrier():
         if world > 1:
@@ -313,7 +310,8 @@ def run_ours(args):
                 "ms_per_step": e2e_ms_total / args.steps,
                 "api": ("JinaColBERTRetriever.search_host: pinned fp32 query -> hrc_search_host (H2D, bf16, MaxSim, top-k, "
                         "unpack, D2H) -> ids/scores on the host" if world == 1 else
-                        "host fp32 query (pinned) -> ShardedSearcher.search_keys -> keys_unpack -> ids/scores .cpu()")},
+                        "ShardedSearcher.search_host: pinned fp32 query -> H2D -> local search -> NCCL all-gather -> merge -> "
+                        "unpack -> D2H (pinned) -> ids/scores on the host")},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
     }

@@ -34,20 +34,23 @@ int launch_synth(void*, int64_t, int64_t, uint64_t, cudaStream_t);
 int launch_meanpool_cosine(const void*, const int64_t*, int64_t, const void*, int, int, float*, cudaStream_t);
 
 static int check_device() {
-  static int ok = -1;
-  if (ok >= 0) return ok ? 0 : 3;
+  static int ok[64] = {};   // per device: 0 unknown, 1 sm_100, -1 other
   int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("no CUDA device available (libhrc has no CPU fallback)");
+    return 3;
+  }
+  if (dev >= 0 && dev < 64 && ok[dev] == 1) return 0;
   cudaDeviceProp prop;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
     set_error("no CUDA device available (libhrc has no CPU fallback)");
     return 3;
   }
   if (prop.major != 10) {
     set_error("libhrc is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
-    ok = 0;
     return 3;
   }
-  ok = 1;
+  if (dev >= 0 && dev < 64) ok[dev] = 1;
   return 0;
 }
 

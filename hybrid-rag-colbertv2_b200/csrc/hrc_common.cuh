@@ -27,6 +27,18 @@ void count_launch(int n = 1);
     }                                                                                     \
   } while (0)
 
+// "configure once per device" (cudaFuncSetAttribute belongs to a function ON a device; a process may drive several)
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool pending(int* dev_out) {
+    int d = 0;
+    cudaGetDevice(&d);
+    *dev_out = d;
+    return d < 0 || d >= 64 || !done[d];
+  }
+  void mark(int d) { if (d >= 0 && d < 64) done[d] = true; }
+};
+
 #define HRC_REQUIRE(cond, ...)        \
   do {                                \
     if (!(cond)) {                    \

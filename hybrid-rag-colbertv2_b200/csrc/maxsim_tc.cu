@@ -540,13 +540,14 @@ EncodeTiledFn get_encode_fn() {
 }
 
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+  int n = 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cached[dev] = n;
   return n;
 }
 
@@ -580,11 +581,12 @@ int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries
   if (stages > 8) stages = 8;
   p.n_stages = stages;
   const int smem_bytes = 1024 + q_bytes + stages * kTileBytes + 512;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  int dev;
+  if (once.pending(&dev)) {
     HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT, TN, TS, ZP, CG>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    configured = true;
+    once.mark(dev);
   }
   if (ZP == 2)   // both token halves of a query accumulate into the score
     HRC_CHECK_CUDA(cudaMemsetAsync(p.scores, 0, size_t(p.n_queries) * size_t(p.n_items) * sizeof(float), stream));

@@ -84,11 +84,12 @@ int launch_rrf(const int32_t* d_ids_a, int n_a, const int32_t* d_ids_b, int n_b,
   HRC_REQUIRE(rrf_k + 1 > 0, "rrf: k=%d must keep k + rank positive", rrf_k);
   const int len = n_a + n_b;
   const size_t smem = size_t(len) * (8 + 4 + 1) + 16;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  int dev;
+  if (once.pending(&dev)) {
     HRC_CHECK_CUDA(cudaFuncSetAttribute(rrf_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kRrfMax * 13 + 16));
-    configured = true;
+    once.mark(dev);
   }
   rrf_fuse_kernel<<<n_rows, kRrfThreads, smem, stream>>>(d_ids_a, n_a, d_ids_b, n_b, rrf_k, top_n, d_ids_out,
                                                          d_scores_out, d_counts_out);

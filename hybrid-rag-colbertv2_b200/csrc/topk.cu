@@ -227,13 +227,14 @@ int sort_buf_bytes(int k) {
 }
 
 int configure_smem() {
-  static bool done = false;
-  if (done) return 0;
+  static PerDeviceOnce once;
+  int dev;
+  if (!once.pending(&dev)) return 0;
   HRC_CHECK_CUDA(cudaFuncSetAttribute(select_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kChunk * 8 + kSortMax * 8));
   HRC_CHECK_CUDA(cudaFuncSetAttribute(select_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kMergeMax * 8 + kSortMax * 8));
-  done = true;
+  once.mark(dev);
   return 0;
 }
 

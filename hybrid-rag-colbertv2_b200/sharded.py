@@ -39,6 +39,7 @@ class ShardedSearcher:
     def __init__(self, retriever: JinaColBERTRetriever, group=None):
         self.retriever = retriever          # holds THIS rank's shard; store.doc_id_base makes ids global
         self.group = group
+        self._pinned = None
 
     def search_keys(self, query_embeddings: torch.Tensor, k: int) -> torch.Tensor:
         local = self.retriever.search_keys(query_embeddings, k)       # [Bq, min(k, n_local)]
@@ -48,3 +49,17 @@ class ShardedSearcher:
     def search_embeddings(self, query_embeddings: torch.Tensor, k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
         ids, scores = _lib.keys_unpack(self.search_keys(query_embeddings, k))
         return ids, scores
+
+    def search_host(self, query_embeddings: torch.Tensor, k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Host query embedding (fp32 CPU [Bq, Lq, 128], ideally pinned) -> host (ids, scores): asynchronous H2D,
+        the sharded search, asynchronous D2H into pinned buffers, ONE stream synchronisation."""
+        dev = self.retriever.device
+        q = query_embeddings if query_embeddings.dim() == 3 else query_embeddings.unsqueeze(0)
+        ids, scores = _lib.keys_unpack(self.search_keys(q.to(dev, non_blocking=True), k))
+        if self._pinned is None or self._pinned[0].shape != ids.shape:
+            self._pinned = (torch.empty(ids.shape, dtype=torch.int32).pin_memory(),
+                            torch.empty(scores.shape, dtype=torch.float32).pin_memory())
+        self._pinned[0].copy_(ids, non_blocking=True)
+        self._pinned[1].copy_(scores, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return self._pinned
