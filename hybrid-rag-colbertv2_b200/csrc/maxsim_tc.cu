@@ -108,29 +108,27 @@ __device__ __forceinline__ int64_t lower_bound_doc(const int64_t* __restrict__ o
   return lo;
 }
 
-// max of 32 accumulator columns as a balanced tree (no 32-deep dependent chain)
-__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
-  float t[16];
+// 3-input max: one FMNMX3
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+// max(m, 32 accumulator columns) in 16 FMNMX3 (the minimum: each removes two values), depth 4 — the ALU pipe
+// issues a warp instruction every 2 cycles, so the instruction count IS the cost of the epilogue's arithmetic
+__device__ __forceinline__ float max32_acc(const uint32_t (&v)[32], float m) {
+  float a[10];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) t[i] = fmaxf(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-#pragma unroll
-  for (int w = 8; w > 0; w >>= 1) {
-#pragma unroll
-    for (int i = 0; i < w; ++i) t[i] = fmaxf(t[i], t[i + w]);
-  }
-  return t[0];
+  for (int i = 0; i < 10; ++i)
+    a[i] = max3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+  const float b0 = max3(a[0], a[1], a[2]);
+  const float b1 = max3(a[3], a[4], a[5]);
+  const float b2 = max3(a[6], a[7], a[8]);
+  const float b3 = max3(a[9], __uint_as_float(v[30]), __uint_as_float(v[31]));
+  return max3(max3(b0, b1, b2), b3, m);
 }
-// same, over the columns whose bit is set (a document that starts or ends inside the chunk)
-__device__ __forceinline__ float max32_masked(const uint32_t (&v)[32], uint32_t bits) {
-  float t[32];
+// same, over the columns whose bit is set (a piece of a document shorter than 32 columns)
+__device__ __forceinline__ float max32_masked_acc(const uint32_t (&v)[32], uint32_t bits, float m) {
+  uint32_t t[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) t[i] = ((bits >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY;
-#pragma unroll
-  for (int w = 16; w > 0; w >>= 1) {
-#pragma unroll
-    for (int i = 0; i < w; ++i) t[i] = fmaxf(t[i], t[i + w]);
-  }
-  return t[0];
+  for (int i = 0; i < 32; ++i) t[i] = ((bits >> i) & 1u) ? v[i] : 0xff800000u;   // -inf
+  return max32_acc(t, m);
 }
 
 // D[tmem] (+)= A[tmem] * B[smem]^T : the A operand (queries) is read from tensor memory.
@@ -403,27 +401,34 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     }
 
     const int n_docs_seg = int(doc_end - doc_begin);
-    // Document ends (token positions relative to tok_begin) are fetched 32 at a time, one per lane,
-    // one batch ahead, and broadcast with a shuffle.
+    // Document ends are fetched 32 at a time, one per lane, one batch ahead, and broadcast with a shuffle.  The lanes
+    // keep the RAW low word of offsets[] and subtract tok_begin only after the shuffle, so nothing consumes a load
+    // right after it is issued (a consumer there stalls the warp for a whole global-memory latency).
+    const uint32_t tok_begin_lo = uint32_t(tok_begin);
+    const uint32_t raw_none = tok_begin_lo + uint32_t(INT_MAX);     // decodes to INT_MAX: "no such document"
     int batch = 0;
-    int ends = INT_MAX, ends_next = INT_MAX;
-    auto load_ends = [&](int b) -> int {
+    uint32_t ends = raw_none, ends_next = raw_none;
+    auto load_ends = [&](int b) -> uint32_t {
       const int d = b * 32 + lane;
-      return (d < n_docs_seg) ? int(p.offsets[doc_begin + d + 1] - tok_begin) : INT_MAX;
+      uint32_t r = raw_none;
+      if (d < n_docs_seg) r = uint32_t(p.offsets[doc_begin + d + 1]);   // predicated load, no consumer
+      return r;
     };
     auto end_of = [&](int d) -> int {   // d non-decreasing over calls, -1 <= d < n_docs_seg
       if (d < 0) return 0;
+#pragma unroll 1
       while ((d >> 5) > batch) {
         ends = ends_next;
         ++batch;
         ends_next = load_ends(batch + 1);
       }
-      return __shfl_sync(0xffffffffu, ends, d & 31);
+      return int(__shfl_sync(0xffffffffu, ends, d & 31) - tok_begin_lo);
     };
 
     int my = residue;                       // local index of the document this warp is accumulating
     bool have_doc = any_active && my < n_docs_seg;
     int s_tok = 0, e_tok = 0;               // its token range
+    int ns_tok = 0, ne_tok = 0;             // token range of this warp's NEXT document, fetched one document ahead
     if (any_active) {
       ends = load_ends(0);
       ends_next = load_ends(1);
@@ -431,28 +436,45 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     if (have_doc) {
       s_tok = end_of(my - 1);
       e_tok = end_of(my);
+      if (my + rep < n_docs_seg) {
+        ns_tok = end_of(my + rep - 1);
+        ne_tok = end_of(my + rep);
+      }
     }
     float m[MT];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) m[mt] = -INFINITY;
 
     auto finish_doc = [&]() {   // emit the score(s) of document `my`, move to this warp's next document
+      const int64_t col = (p.cand_ids == nullptr) ? (doc_begin + my) : item;
+      if constexpr (MT == 2) {
+        // both M-tiles in ONE butterfly: after the first exchange lanes 0-15 carry M-tile 0 and lanes 16-31 M-tile 1
+        const bool lo_half = lane < 16;
+        float a = lo_half ? m[0] : m[1];
+        const float b = lo_half ? m[1] : m[0];
+        a += __shfl_xor_sync(0xffffffffu, b, 16);
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
+        for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        const bool act = lo_half ? active[0] : active[1];
+        const int64_t row = lo_half ? out_row[0] : out_row[1];
+        if ((lane & 15) == 0 && act) p.scores[row + col] = a;
+        m[0] = m[1] = -INFINITY;
+      } else {
         // M=64: only lanes 0-15 of a lane group hold accumulator rows (16 query tokens)
-        const float sc = warp_sum((ZP == 2 && lane >= 16) ? 0.f : m[mt]);
-        if (lane == 0 && active[mt]) {
-          const int64_t col = (p.cand_ids == nullptr) ? (doc_begin + my) : item;
-          if constexpr (ZP == 2) atomicAdd(&p.scores[out_row[mt] + col], sc);   // the other token half adds its part
-          else p.scores[out_row[mt] + col] = sc;
+        const float sc = warp_sum((ZP == 2 && lane >= 16) ? 0.f : m[0]);
+        if (lane == 0 && active[0]) {
+          if constexpr (ZP == 2) atomicAdd(&p.scores[out_row[0] + col], sc);   // the other token half adds its part
+          else p.scores[out_row[0] + col] = sc;
         }
-        m[mt] = -INFINITY;
+        m[0] = -INFINITY;
       }
       my += rep;
       have_doc = my < n_docs_seg;
-      if (have_doc) {
-        s_tok = end_of(my - 1);
-        e_tok = end_of(my);
+      s_tok = ns_tok;
+      e_tok = ne_tok;
+      if (my + rep < n_docs_seg) {          // results are consumed one document later: the shuffle latency is hidden
+        ns_tok = end_of(my + rep - 1);
+        ne_tok = end_of(my + rep);
       }
     };
 
@@ -474,15 +496,33 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
             // harmless under max — so no column is ever masked.
             const int last = hi - 32;
             int c = lo;
-            while (true) {
-              const uint32_t col = uint32_t(min(c, last) - tile0);
-#pragma unroll
-              for (int mt = 0; mt < MT; ++mt) tmem_ld_32x32(tacc + uint32_t(mt * TN) + col, v[mt]);
-              tmem_ld_wait();
-#pragma unroll
-              for (int mt = 0; mt < MT; ++mt) m[mt] = fmaxf(m[mt], max32(v[mt]));
-              if (c >= last) break;
-              c += 32;
+            if constexpr (MT == 2) {
+              // software pipeline over (chunk, M-tile) steps: one TMEM load is in flight while the max tree of the
+              // previous step runs (v[0] always holds M-tile 0, v[1] M-tile 1)
+              uint32_t col = uint32_t(min(c, last) - tile0);
+              tmem_ld_32x32(tacc + col, v[0]);
+              while (true) {
+                tmem_ld_wait();
+                tmem_ld_32x32(tacc + uint32_t(TN) + col, v[1]);
+                m[0] = max32_acc(v[0], m[0]);
+                tmem_ld_wait();
+                const bool more = c < last;
+                if (more) {
+                  c += 32;
+                  col = uint32_t(min(c, last) - tile0);
+                  tmem_ld_32x32(tacc + col, v[0]);
+                }
+                m[1] = max32_acc(v[1], m[1]);
+                if (!more) break;
+              }
+            } else {
+              while (true) {
+                tmem_ld_32x32(tacc + uint32_t(min(c, last) - tile0), v[0]);
+                tmem_ld_wait();
+                m[0] = max32_acc(v[0], m[0]);
+                if (c >= last) break;
+                c += 32;
+              }
             }
           } else {
             // fewer than 32 of its tokens here (a short document, or the head / tail a tile boundary cut off)
@@ -493,7 +533,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
             const int a = lo - cc, b = hi - cc;   // 0 <= a < b <= 32, b - a < 32
             const uint32_t bits = ((1u << (b - a)) - 1u) << a;
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) m[mt] = fmaxf(m[mt], max32_masked(v[mt], bits));
+            for (int mt = 0; mt < MT; ++mt) m[mt] = max32_masked_acc(v[mt], bits, m[mt]);
           }
         }
         if (e_tok <= tile1) finish_doc(); else break;   // else: the document continues in the next tile
