@@ -445,29 +445,44 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) m[mt] = -INFINITY;
 
-    auto finish_doc = [&]() {   // emit the score(s) of document `my`, move to this warp's next document
-      const int64_t col = (p.cand_ids == nullptr) ? (doc_begin + my) : item;
+    // Emitting a score (a 5-step shuffle butterfly + a store, ~500 cycles of latency) is taken OFF the
+    // accumulator hand-shake: finish_doc only parks the finished maxima; they are reduced and stored after this
+    // warp has released the tile (or when the next document of the same tile finishes).
+    float pend_m[MT];
+    int64_t pend_col = 0;
+    bool pending = false;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) pend_m[mt] = 0.f;
+
+    auto emit_pending = [&]() {
       if constexpr (MT == 2) {
         // both M-tiles in ONE butterfly: after the first exchange lanes 0-15 carry M-tile 0 and lanes 16-31 M-tile 1
         const bool lo_half = lane < 16;
-        float a = lo_half ? m[0] : m[1];
-        const float b = lo_half ? m[1] : m[0];
+        float a = lo_half ? pend_m[0] : pend_m[1];
+        const float b = lo_half ? pend_m[1] : pend_m[0];
         a += __shfl_xor_sync(0xffffffffu, b, 16);
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         const bool act = lo_half ? active[0] : active[1];
         const int64_t row = lo_half ? out_row[0] : out_row[1];
-        if ((lane & 15) == 0 && act) p.scores[row + col] = a;
-        m[0] = m[1] = -INFINITY;
+        if ((lane & 15) == 0 && act) p.scores[row + pend_col] = a;
       } else {
         // M=64: only lanes 0-15 of a lane group hold accumulator rows (16 query tokens)
-        const float sc = warp_sum((ZP == 2 && lane >= 16) ? 0.f : m[0]);
+        const float sc = warp_sum((ZP == 2 && lane >= 16) ? 0.f : pend_m[0]);
         if (lane == 0 && active[0]) {
-          if constexpr (ZP == 2) atomicAdd(&p.scores[out_row[0] + col], sc);   // the other token half adds its part
-          else p.scores[out_row[0] + col] = sc;
+          if constexpr (ZP == 2) atomicAdd(&p.scores[out_row[0] + pend_col], sc);   // the other token half adds its part
+          else p.scores[out_row[0] + pend_col] = sc;
         }
-        m[0] = -INFINITY;
       }
+      pending = false;
+    };
+
+    auto finish_doc = [&]() {   // park the score(s) of document `my`, move to this warp's next document
+      if (pending) emit_pending();
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) { pend_m[mt] = m[mt]; m[mt] = -INFINITY; }
+      pend_col = (p.cand_ids == nullptr) ? (doc_begin + my) : item;
+      pending = true;
       my += rep;
       have_doc = my < n_docs_seg;
       s_tok = ns_tok;
@@ -544,9 +559,11 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
         if constexpr (CG == 2) mbar_arrive_cluster(&tempty[ts], 0);   // the leader's MMA issuer owns both accumulators
         else mbar_arrive(&tempty[ts]);
       }
+      if (pending) emit_pending();          // after the release: off the MMA <-> epilogue critical path
       if (++ts == kTileStages) { ts = 0; tphase ^= 1; }
     }
     while (have_doc) finish_doc();          // trailing empty documents (no tokens, no tile): -inf
+    if (pending) emit_pending();
   }
 
   tc_fence_before_sync();
