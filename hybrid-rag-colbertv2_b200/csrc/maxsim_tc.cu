@@ -164,7 +164,7 @@ __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-template <int MT, int TN, bool TS, int ZP = 0, int CG = 1>
+template <int MT, int TN, bool TS, int ZP = 0, int CG = 1, int MTW = MT>
 __global__ void __launch_bounds__(cta_threads(MT, ZP), 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_q,
                  const TcParams p) {
@@ -184,6 +184,14 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   static_assert(kTileBytes % 2048 == 0, "tile slabs must stay 1024-byte aligned for the 128B swizzle");
   static_assert(ZP == 0 || (MT == 1 && !TS), "ZP is a few-query variant");
   static_assert(CG == 1 || (CG == 2 && MT == 2 && !TS && ZP == 0), "CTA pairs: batched SS kernel only");
+  // MTW = M-tiles per epilogue warp.  MTW == MT: the warps of a lane group alternate DOCUMENTS and each reads all
+  // M-tiles; the accumulators of a tile are one unit (one tfull / tempty pair per stage).  MTW == 1 (< MT): the
+  // warps of a lane group take one M-TILE each and walk every document; every (stage, M-tile) is its own unit
+  // with its own barriers, so 2 x MT hand-shakes are in flight and their latency leaves the critical path.
+  static_assert(MTW == MT || (MTW == 1 && MT == 2 && ZP == 0), "bad MTW");
+  constexpr int kUnitsPerStage = MT / MTW;
+  constexpr int kUnits = kTileStages * kUnitsPerStage;
+  static_assert(kUnits <= 4, "tfull / tempty hold 4 barriers each");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -237,8 +245,8 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     tma_prefetch_desc(&tmap_d);
     if (!TS) tma_prefetch_desc(&tmap_q);
     for (int i = 0; i < p.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < kTileStages; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps * CG); }
-    mbar_init(qfull, TS ? 4 : 1);
+    for (int i = 0; i < kUnits; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], (kEpiWarps / kUnitsPerStage) * CG); }
+    mbar_init(qfull, TS ? (MTW == MT ? 4 : kEpiWarps) : 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -316,13 +324,16 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
       int stage = 0; uint32_t phase = 0;
       int ts = 0; uint32_t tphase = 0;
       for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait_wd(&tempty[ts], tphase ^ 1);
         mbar_wait_wd(&full[stage], phase);
-        tc_fence_after_sync();
-        if (elect_one()) {
-          const uint32_t b_addr = sD_addr + stage * kTileBytes;
+        const uint32_t b_addr = sD_addr + stage * kTileBytes;
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
+          const int unit = ts * kUnitsPerStage + mt / MTW;
+          if (mt % MTW == 0) {               // first M-tile of an accumulator unit: wait until its readers are done
+            mbar_wait_wd(&tempty[unit], tphase ^ 1);
+            tc_fence_after_sync();
+          }
+          if (elect_one()) {
             const uint32_t d_tmem = acc_base + uint32_t((ts * MT + mt) * TN);
 #pragma unroll
             for (int k = 0; k < HRC_DIM / 16; ++k) {
@@ -338,16 +349,16 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
                 else umma_bf16_ss(d_tmem, make_kmajor_sw128_desc(a_addr), b_desc, kIdesc, k > 0 ? 1u : 0u);
               }
             }
+            // commits (CG == 2: multicast, the peer's producer and epilogue wait on their own copies)
+            if (mt % MTW == MTW - 1) {         // last M-tile of the unit: accumulators ready for the epilogue
+              if constexpr (CG == 2) umma_commit_cg2(&tfull[unit]); else umma_commit(&tfull[unit]);
+            }
+            if (mt == MT - 1) {                // smem slot reusable once these MMAs have read it
+              if constexpr (CG == 2) umma_commit_cg2(&empty[stage]); else umma_commit(&empty[stage]);
+            }
           }
-          if constexpr (CG == 2) {      // multicast: the peer's producer and epilogue wait on their own copies
-            umma_commit_cg2(&empty[stage]);
-            umma_commit_cg2(&tfull[ts]);
-          } else {
-            umma_commit(&empty[stage]);   // smem slot reusable once these MMAs have read it
-            umma_commit(&tfull[ts]);      // accumulators ready for the epilogue
-          }
+          __syncwarp();
         }
-        __syncwarp();
         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         if (++ts == kTileStages) { ts = 0; tphase ^= 1; }
       }
@@ -360,24 +371,27 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     const int slot = warp & 3;                           // TMEM lanes 32*slot .. 32*slot+31
     const uint32_t lane_base = uint32_t(slot * 32) << 16;
     const int sub = ZP ? (warp >> 2) - 1 : (warp - kEpiWarp0) >> 2;
-    const int rep = ZP ? 4 / p.slots_used : (4 / p.slots_used) * kSplit;
-    const int residue = ZP ? sub : (slot / p.slots_used) * kSplit + sub;
-    bool active[MT];
-    int64_t out_row[MT];
+    constexpr bool kMtSplit = MTW < MT;                  // the warps of a lane group split M-tiles, not documents
+    const int mt0 = kMtSplit ? sub : 0;                   // this warp reads M-tiles mt0 .. mt0 + MTW - 1
+    const int rep = ZP ? 4 / p.slots_used : (4 / p.slots_used) * (kMtSplit ? 1 : kSplit);
+    const int residue = ZP ? sub : (kMtSplit ? slot / p.slots_used : (slot / p.slots_used) * kSplit + sub);
+    bool active[MTW];
+    int64_t out_row[MTW];
     bool any_active = false;
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      const int q = ZP == 2 ? q_base + (slot >> 1) : q_base + 4 * mt + (slot % p.slots_used);
-      active[mt] = q < p.n_queries;
-      out_row[mt] = int64_t(q) * p.n_items;
-      any_active |= active[mt];
+    for (int j = 0; j < MTW; ++j) {
+      const int q = ZP == 2 ? q_base + (slot >> 1) : q_base + 4 * (mt0 + j) + (slot % p.slots_used);
+      active[j] = q < p.n_queries;
+      out_row[j] = int64_t(q) * p.n_items;
+      any_active |= active[j];
     }
 
     if constexpr (TS) {
       // Stage the query tiles in TMEM (A operand): this thread owns row (slot, lane) = query token `lane`.
-      if (sub == 0 && n_tiles > 0) {
+      if ((kMtSplit || sub == 0) && n_tiles > 0) {
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
+        for (int j = 0; j < MTW; ++j) {
+          const int mt = mt0 + j;
           uint32_t qv[64];
           const int q = q_base + 4 * mt + (slot % p.slots_used);
           if (q < p.n_queries && lane < p.lq) {
@@ -441,21 +455,21 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
         ne_tok = end_of(my + rep);
       }
     }
-    float m[MT];
+    float m[MTW];
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) m[mt] = -INFINITY;
+    for (int j = 0; j < MTW; ++j) m[j] = -INFINITY;
 
     // Emitting a score (a 5-step shuffle butterfly + a store, ~500 cycles of latency) is taken OFF the
     // accumulator hand-shake: finish_doc only parks the finished maxima; they are reduced and stored after this
     // warp has released the tile (or when the next document of the same tile finishes).
-    float pend_m[MT];
+    float pend_m[MTW];
     int64_t pend_col = 0;
     bool pending = false;
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) pend_m[mt] = 0.f;
+    for (int j = 0; j < MTW; ++j) pend_m[j] = 0.f;
 
     auto emit_pending = [&]() {
-      if constexpr (MT == 2) {
+      if constexpr (MTW == 2) {
         // both M-tiles in ONE butterfly: after the first exchange lanes 0-15 carry M-tile 0 and lanes 16-31 M-tile 1
         const bool lo_half = lane < 16;
         float a = lo_half ? pend_m[0] : pend_m[1];
@@ -480,7 +494,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     auto finish_doc = [&]() {   // park the score(s) of document `my`, move to this warp's next document
       if (pending) emit_pending();
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) { pend_m[mt] = m[mt]; m[mt] = -INFINITY; }
+      for (int j = 0; j < MTW; ++j) { pend_m[j] = m[j]; m[j] = -INFINITY; }
       pend_col = (p.cand_ids == nullptr) ? (doc_begin + my) : item;
       pending = true;
       my += rep;
@@ -495,12 +509,13 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
 
     int ts = 0; uint32_t tphase = 0;
     for (int t = 0; t < n_tiles; ++t) {
-      mbar_wait_wd(&tfull[ts], tphase);
+      const int unit = ts * kUnitsPerStage + (kMtSplit ? sub : 0);
+      mbar_wait_wd(&tfull[unit], tphase);
       tc_fence_after_sync();
       const int tile0 = t * TN, tile1 = tile0 + TN;
-      // accumulator columns of this tile for M-tile mt: tacc + mt * TN + (token position - tile0)
-      const uint32_t tacc = acc_base + lane_base + uint32_t(ts * MT * TN);
-      uint32_t v[MT][32];
+      // accumulator columns of this tile for this warp's j-th M-tile: tacc + j * TN + (token position - tile0)
+      const uint32_t tacc = acc_base + lane_base + uint32_t((ts * MT + mt0) * TN);
+      uint32_t v[2][32];
       while (have_doc && s_tok < tile1) {
         const int lo = max(s_tok, tile0), hi = min(e_tok, tile1);
         const int len = hi - lo;              // this document's tokens inside this tile
@@ -511,7 +526,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
             // harmless under max — so no column is ever masked.
             const int last = hi - 32;
             int c = lo;
-            if constexpr (MT == 2) {
+            if constexpr (MTW == 2) {
               // software pipeline over (chunk, M-tile) steps: one TMEM load is in flight while the max tree of the
               // previous step runs (v[0] always holds M-tile 0, v[1] M-tile 1)
               uint32_t col = uint32_t(min(c, last) - tile0);
@@ -530,6 +545,21 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
                 m[1] = max32_acc(v[1], m[1]);
                 if (!more) break;
               }
+            } else if constexpr (kMtSplit) {
+              // one M-tile per warp: software pipeline over chunks, two register buffers
+              tmem_ld_32x32(tacc + uint32_t(min(c, last) - tile0), v[0]);
+              while (true) {
+                tmem_ld_wait();
+                const bool more1 = c < last;
+                if (more1) { c += 32; tmem_ld_32x32(tacc + uint32_t(min(c, last) - tile0), v[1]); }
+                m[0] = max32_acc(v[0], m[0]);
+                if (!more1) break;
+                tmem_ld_wait();
+                const bool more0 = c < last;
+                if (more0) { c += 32; tmem_ld_32x32(tacc + uint32_t(min(c, last) - tile0), v[0]); }
+                m[0] = max32_acc(v[1], m[0]);
+                if (!more0) break;
+              }
             } else {
               while (true) {
                 tmem_ld_32x32(tacc + uint32_t(min(c, last) - tile0), v[0]);
@@ -543,12 +573,12 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
             // fewer than 32 of its tokens here (a short document, or the head / tail a tile boundary cut off)
             const int cc = min(lo, tile1 - 32);
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) tmem_ld_32x32(tacc + uint32_t(mt * TN) + uint32_t(cc - tile0), v[mt]);
+            for (int j = 0; j < MTW; ++j) tmem_ld_32x32(tacc + uint32_t(j * TN) + uint32_t(cc - tile0), v[j]);
             tmem_ld_wait();
             const int a = lo - cc, b = hi - cc;   // 0 <= a < b <= 32, b - a < 32
             const uint32_t bits = ((1u << (b - a)) - 1u) << a;
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) m[mt] = max32_masked_acc(v[mt], bits, m[mt]);
+            for (int j = 0; j < MTW; ++j) m[j] = max32_masked_acc(v[j], bits, m[j]);
           }
         }
         if (e_tok <= tile1) finish_doc(); else break;   // else: the document continues in the next tile
@@ -556,8 +586,8 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_cluster(&tempty[ts], 0);   // the leader's MMA issuer owns both accumulators
-        else mbar_arrive(&tempty[ts]);
+        if constexpr (CG == 2) mbar_arrive_cluster(&tempty[unit], 0);   // the leader's MMA issuer owns both accumulators
+        else mbar_arrive(&tempty[unit]);
       }
       if (pending) emit_pending();          // after the release: off the MMA <-> epilogue critical path
       if (++ts == kTileStages) { ts = 0; tphase ^= 1; }
@@ -608,7 +638,7 @@ int sm_count() {
   return n;
 }
 
-template <int MT, int TN, bool TS, int ZP = 0, int CG = 1>
+template <int MT, int TN, bool TS, int ZP = 0, int CG = 1, int MTW = MT>
 int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries, TcParams p, dim3 grid,
                cudaStream_t stream) {
   constexpr int kTileBytes = (TN / CG) * HRC_DIM * 2;   // what ONE CTA stages per tile
@@ -641,7 +671,7 @@ int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries
   static PerDeviceOnce once;
   int dev;
   if (once.pending(&dev)) {
-    HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT, TN, TS, ZP, CG>,
+    HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT, TN, TS, ZP, CG, MTW>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     once.mark(dev);
   }
@@ -660,9 +690,9 @@ int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    HRC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, maxsim_tc_kernel<MT, TN, TS, ZP, CG>, tmap_d, tmap_q, p));
+    HRC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, maxsim_tc_kernel<MT, TN, TS, ZP, CG, MTW>, tmap_d, tmap_q, p));
   } else {
-    maxsim_tc_kernel<MT, TN, TS, ZP, CG><<<grid, cta_threads(MT, ZP), smem_bytes, stream>>>(tmap_d, tmap_q, p);
+    maxsim_tc_kernel<MT, TN, TS, ZP, CG, MTW><<<grid, cta_threads(MT, ZP), smem_bytes, stream>>>(tmap_d, tmap_q, p);
   }
   count_launch();
   HRC_CHECK_CUDA(cudaGetLastError());
@@ -734,8 +764,11 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
     TcParams pp = p;
     pp.n_qgroups = paired;
     pp.n_queries = n_queries < paired * 8 ? n_queries : paired * 8;
-    int rc = launch_cfg<2, 128, false, 0, 2>(encode, d_tokens, d_queries, pp, dim3((unsigned)(pp.n_segments * paired)),
-                                             stream);
+    const bool mt_split = getenv("HRC_TC_MTSPLIT") != nullptr && atoi(getenv("HRC_TC_MTSPLIT")) != 0;
+    int rc = mt_split ? launch_cfg<2, 128, false, 0, 2, 1>(encode, d_tokens, d_queries, pp,
+                                                           dim3((unsigned)(pp.n_segments * paired)), stream)
+                      : launch_cfg<2, 128, false, 0, 2>(encode, d_tokens, d_queries, pp,
+                                                        dim3((unsigned)(pp.n_segments * paired)), stream);
     if (rc != 0 || paired == p.n_qgroups) return rc;
     const int done = paired * 8;                        // the odd group: queries [done, n_queries)
     TcParams pl = p;

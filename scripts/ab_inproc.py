@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--rounds", type=int, default=12)
     ap.add_argument("--launches", type=int, default=10)
     ap.add_argument("--docs", type=int, default=0)
+    ap.add_argument("--env-ab", default="", help="NAME: run every library with NAME=0 and NAME=1 as separate contestants")
     ap.add_argument("libs", nargs="+")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -43,16 +44,23 @@ def main():
     q = synth_queries(nq, 32, device=dev)
     out = torch.empty((nq, store.n_docs), dtype=torch.float32, device=dev)
     fns = [bind(os.path.abspath(p)) for p in a.libs]
+    envs = [None] * len(fns)
+    if a.env_ab:
+        fns = [f for f in fns for _ in (0, 1)]
+        envs = ["0", "1"] * len(a.libs)
+        a.libs = [f"{os.path.basename(p)}[{a.env_ab}={v}]" for p in a.libs for v in ("0", "1")]
     stream = torch.cuda.current_stream(dev).cuda_stream
 
-    def launch(fn):
+    def launch(fn, env=None):
+        if env is not None:
+            os.environ[a.env_ab] = env
         rc = fn(store.tokens.data_ptr(), store.offsets.data_ptr(), store.n_docs, store.total_tokens, q.data_ptr(), nq, 32,
                 out.data_ptr(), 0, stream)
         assert rc == 0, rc
 
-    for fn in fns:
+    for fn, env in zip(fns, envs):
         for _ in range(3):
-            launch(fn)
+            launch(fn, env)
     torch.cuda.synchronize()
     times = [[] for _ in fns]
     for r in range(a.rounds):
@@ -63,7 +71,7 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(a.launches):
-                launch(fns[i])
+                launch(fns[i], envs[i])
             e1.record()
             torch.cuda.synchronize()
             times[i].append(e0.elapsed_time(e1) / a.launches)
@@ -71,7 +79,7 @@ def main():
         med = statistics.median(t)
         extra = (f"{store.total_tokens * 256 / med / 1e6:8.0f} GB/s" if nq == 1 else
                  f"{2.0 * 32 * 128 * nq * store.total_tokens / med / 1e9:8.0f} TFLOP/s")
-        print(f"{os.path.basename(p):22s} median {med:8.4f} ms  min {min(t):8.4f}  max {max(t):8.4f}  {extra}")
+        print(f"{os.path.basename(p):34s} median {med:8.4f} ms  min {min(t):8.4f}  max {max(t):8.4f}  {extra}")
 
 
 if __name__ == "__main__":
