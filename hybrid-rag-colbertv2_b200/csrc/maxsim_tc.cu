@@ -164,7 +164,7 @@ __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-template <int MT, int TN, bool TS, int ZP = 0, int CG = 1, int MTW = MT>
+template <int MT, int TN, bool TS, int ZP = 0, int CG = 1, int EPI = 0>
 __global__ void __launch_bounds__(cta_threads(MT, ZP), 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_q,
                  const TcParams p) {
@@ -184,13 +184,17 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   static_assert(kTileBytes % 2048 == 0, "tile slabs must stay 1024-byte aligned for the 128B swizzle");
   static_assert(ZP == 0 || (MT == 1 && !TS), "ZP is a few-query variant");
   static_assert(CG == 1 || (CG == 2 && MT == 2 && !TS && ZP == 0), "CTA pairs: batched SS kernel only");
-  // MTW = M-tiles per epilogue warp.  MTW == MT: the warps of a lane group alternate DOCUMENTS and each reads all
-  // M-tiles; the accumulators of a tile are one unit (one tfull / tempty pair per stage).  MTW == 1 (< MT): the
-  // warps of a lane group take one M-TILE each and walk every document; every (stage, M-tile) is its own unit
-  // with its own barriers, so 2 x MT hand-shakes are in flight and their latency leaves the critical path.
-  static_assert(MTW == MT || (MTW == 1 && MT == 2 && ZP == 0), "bad MTW");
-  constexpr int kUnitsPerStage = MT / MTW;
+  // How the epilogue warps of a lane group share the work (EPI):
+  //  0  the warps alternate DOCUMENTS and each reads all M-tiles of a tile in one walk; a tile's accumulators are one
+  //     unit (one tfull / tempty pair per stage).  Default.
+  //  1  the warps take one M-TILE each and both walk every document; every (stage, M-tile) is its own unit.
+  //  2  the warps alternate documents, and each walks a tile once PER M-TILE, releasing M-tile 0 before it reads
+  //     M-tile 1; every (stage, M-tile) is its own unit, so 2 x MT hand-shakes are in flight.
+  static_assert(EPI == 0 || (MT == 2 && ZP == 0), "bad EPI");
+  constexpr int MTW = EPI == 0 ? MT : 1;                 // M-tiles read in one walk
+  constexpr int kUnitsPerStage = EPI == 0 ? 1 : MT;
   constexpr int kUnits = kTileStages * kUnitsPerStage;
+  constexpr int kReadersPerUnit = EPI == 1 ? epi_warps(MT) / MT : (ZP == 2 ? 8 : epi_warps(MT));
   static_assert(kUnits <= 4, "tfull / tempty hold 4 barriers each");
 
   extern __shared__ uint8_t smem_raw[];
@@ -245,8 +249,8 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     tma_prefetch_desc(&tmap_d);
     if (!TS) tma_prefetch_desc(&tmap_q);
     for (int i = 0; i < p.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < kUnits; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], (kEpiWarps / kUnitsPerStage) * CG); }
-    mbar_init(qfull, TS ? (MTW == MT ? 4 : kEpiWarps) : 1);
+    for (int i = 0; i < kUnits; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kReadersPerUnit * CG); }
+    mbar_init(qfull, TS ? (EPI == 1 ? kEpiWarps : 4) : 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -328,8 +332,8 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
         const uint32_t b_addr = sD_addr + stage * kTileBytes;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          const int unit = ts * kUnitsPerStage + mt / MTW;
-          if (mt % MTW == 0) {               // first M-tile of an accumulator unit: wait until its readers are done
+          const int unit = ts * kUnitsPerStage + (EPI == 0 ? 0 : mt);
+          if (EPI != 0 || mt == 0) {         // first M-tile of an accumulator unit: wait until its readers are done
             mbar_wait_wd(&tempty[unit], tphase ^ 1);
             tc_fence_after_sync();
           }
@@ -350,7 +354,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
               }
             }
             // commits (CG == 2: multicast, the peer's producer and epilogue wait on their own copies)
-            if (mt % MTW == MTW - 1) {         // last M-tile of the unit: accumulators ready for the epilogue
+            if (EPI != 0 || mt == MT - 1) {    // last M-tile of the unit: accumulators ready for the epilogue
               if constexpr (CG == 2) umma_commit_cg2(&tfull[unit]); else umma_commit(&tfull[unit]);
             }
             if (mt == MT - 1) {                // smem slot reusable once these MMAs have read it
@@ -371,8 +375,10 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     const int slot = warp & 3;                           // TMEM lanes 32*slot .. 32*slot+31
     const uint32_t lane_base = uint32_t(slot * 32) << 16;
     const int sub = ZP ? (warp >> 2) - 1 : (warp - kEpiWarp0) >> 2;
-    constexpr bool kMtSplit = MTW < MT;                  // the warps of a lane group split M-tiles, not documents
-    const int mt0 = kMtSplit ? sub : 0;                   // this warp reads M-tiles mt0 .. mt0 + MTW - 1
+    constexpr bool kMtSplit = EPI == 1;                  // the warps of a lane group split M-tiles, not documents
+    constexpr bool kMtPass = EPI == 2;                   // one walk per M-tile
+    constexpr int kPasses = kMtPass ? MT : 1;
+    int mt0 = kMtSplit ? sub : 0;                        // this walk reads M-tiles mt0 .. mt0 + MTW - 1
     const int rep = ZP ? 4 / p.slots_used : (4 / p.slots_used) * (kMtSplit ? 1 : kSplit);
     const int residue = ZP ? sub : (kMtSplit ? slot / p.slots_used : (slot / p.slots_used) * kSplit + sub);
     bool active[MTW];
@@ -385,10 +391,24 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
       out_row[j] = int64_t(q) * p.n_items;
       any_active |= active[j];
     }
+    // kMtPass: per-pass copies of what differs between the M-tiles (swapped into the [0] slots around each walk)
+    bool active_p[kPasses];
+    int64_t out_row_p[kPasses];
+    float m_p[kPasses], pend_m_p[kPasses];
+    int64_t pend_col_p[kPasses];
+    bool pending_p[kPasses];
+#pragma unroll
+    for (int ps = 0; ps < kPasses; ++ps) {
+      const int q = q_base + 4 * ps + (slot % p.slots_used);
+      active_p[ps] = q < p.n_queries;
+      out_row_p[ps] = int64_t(q) * p.n_items;
+      m_p[ps] = -INFINITY; pend_m_p[ps] = 0.f; pend_col_p[ps] = 0; pending_p[ps] = false;
+      if (kMtPass) any_active |= active_p[ps];
+    }
 
     if constexpr (TS) {
       // Stage the query tiles in TMEM (A operand): this thread owns row (slot, lane) = query token `lane`.
-      if ((kMtSplit || sub == 0) && n_tiles > 0) {
+      if ((kMtSplit || sub == 0) && n_tiles > 0) {   // (TS is only instantiated with EPI == 0)
 #pragma unroll
         for (int j = 0; j < MTW; ++j) {
           const int mt = mt0 + j;
@@ -509,91 +529,123 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
 
     int ts = 0; uint32_t tphase = 0;
     for (int t = 0; t < n_tiles; ++t) {
-      const int unit = ts * kUnitsPerStage + (kMtSplit ? sub : 0);
-      mbar_wait_wd(&tfull[unit], tphase);
-      tc_fence_after_sync();
-      const int tile0 = t * TN, tile1 = tile0 + TN;
-      // accumulator columns of this tile for this warp's j-th M-tile: tacc + j * TN + (token position - tile0)
-      const uint32_t tacc = acc_base + lane_base + uint32_t((ts * MT + mt0) * TN);
-      uint32_t v[2][32];
-      while (have_doc && s_tok < tile1) {
-        const int lo = max(s_tok, tile0), hi = min(e_tok, tile1);
-        const int len = hi - lo;              // this document's tokens inside this tile
-        if (len > 0 && !(p.debug & 1)) {
-          if (len >= 32) {
-            // Whole 32-column loads that START AT the document's first column (TMEM columns are addressable one by
-            // one); the last load is pulled back so that it ENDS at the document's last column — the overlap is
-            // harmless under max — so no column is ever masked.
-            const int last = hi - 32;
-            int c = lo;
-            if constexpr (MTW == 2) {
-              // software pipeline over (chunk, M-tile) steps: one TMEM load is in flight while the max tree of the
-              // previous step runs (v[0] always holds M-tile 0, v[1] M-tile 1)
-              uint32_t col = uint32_t(min(c, last) - tile0);
-              tmem_ld_32x32(tacc + col, v[0]);
-              while (true) {
-                tmem_ld_wait();
-                tmem_ld_32x32(tacc + uint32_t(TN) + col, v[1]);
-                m[0] = max32_acc(v[0], m[0]);
-                tmem_ld_wait();
-                const bool more = c < last;
-                if (more) {
-                  c += 32;
-                  col = uint32_t(min(c, last) - tile0);
-                  tmem_ld_32x32(tacc + col, v[0]);
+      // kMtPass: the walk state at the start of the tile, replayed for every M-tile
+      const int sv_my = my, sv_s = s_tok, sv_e = e_tok, sv_ns = ns_tok, sv_ne = ne_tok, sv_batch = batch;
+      const bool sv_have = have_doc;
+      const uint32_t sv_ends = ends, sv_ends_next = ends_next;
+#pragma unroll
+      for (int ps = 0; ps < kPasses; ++ps) {
+        if constexpr (kMtPass) {
+          my = sv_my; s_tok = sv_s; e_tok = sv_e; ns_tok = sv_ns; ne_tok = sv_ne; batch = sv_batch; have_doc = sv_have;
+          ends = sv_ends; ends_next = sv_ends_next;
+          mt0 = ps;
+          active[0] = active_p[ps]; out_row[0] = out_row_p[ps];
+          m[0] = m_p[ps]; pend_m[0] = pend_m_p[ps]; pend_col = pend_col_p[ps]; pending = pending_p[ps];
+        }
+        const int unit = ts * kUnitsPerStage + (kMtSplit ? sub : (kMtPass ? ps : 0));
+        mbar_wait_wd(&tfull[unit], tphase);
+        tc_fence_after_sync();
+        const int tile0 = t * TN, tile1 = tile0 + TN;
+        // accumulator columns of this tile for this warp's j-th M-tile: tacc + j * TN + (token position - tile0)
+        const uint32_t tacc = acc_base + lane_base + uint32_t((ts * MT + mt0) * TN);
+        uint32_t v[2][32];
+        while (have_doc && s_tok < tile1) {
+          const int lo = max(s_tok, tile0), hi = min(e_tok, tile1);
+          const int len = hi - lo;              // this document's tokens inside this tile
+          if (len > 0 && !(p.debug & 1)) {
+            if (len >= 32) {
+              // Whole 32-column loads that START AT the document's first column (TMEM columns are addressable one by
+              // one); the last load is pulled back so that it ENDS at the document's last column — the overlap is
+              // harmless under max — so no column is ever masked.
+              const int last = hi - 32;
+              int c = lo;
+              if constexpr (MTW == 2) {
+                // software pipeline over (chunk, M-tile) steps: one TMEM load is in flight while the max tree of the
+                // previous step runs (v[0] always holds M-tile 0, v[1] M-tile 1)
+                uint32_t col = uint32_t(min(c, last) - tile0);
+                tmem_ld_32x32(tacc + col, v[0]);
+                while (true) {
+                  tmem_ld_wait();
+                  tmem_ld_32x32(tacc + uint32_t(TN) + col, v[1]);
+                  m[0] = max32_acc(v[0], m[0]);
+                  tmem_ld_wait();
+                  const bool more = c < last;
+                  if (more) {
+                    c += 32;
+                    col = uint32_t(min(c, last) - tile0);
+                    tmem_ld_32x32(tacc + col, v[0]);
+                  }
+                  m[1] = max32_acc(v[1], m[1]);
+                  if (!more) break;
                 }
-                m[1] = max32_acc(v[1], m[1]);
-                if (!more) break;
-              }
-            } else if constexpr (kMtSplit) {
-              // one M-tile per warp: software pipeline over chunks, two register buffers
-              tmem_ld_32x32(tacc + uint32_t(min(c, last) - tile0), v[0]);
-              while (true) {
-                tmem_ld_wait();
-                const bool more1 = c < last;
-                if (more1) { c += 32; tmem_ld_32x32(tacc + uint32_t(min(c, last) - tile0), v[1]); }
-                m[0] = max32_acc(v[0], m[0]);
-                if (!more1) break;
-                tmem_ld_wait();
-                const bool more0 = c < last;
-                if (more0) { c += 32; tmem_ld_32x32(tacc + uint32_t(min(c, last) - tile0), v[0]); }
-                m[0] = max32_acc(v[1], m[0]);
-                if (!more0) break;
+              } else if constexpr (kMtSplit) {
+                // one M-tile per warp: software pipeline over chunks, two register buffers
+                tmem_ld_32x32(tacc + uint32_t(min(c, last) - tile0), v[0]);
+                while (true) {
+                  tmem_ld_wait();
+                  const bool more1 = c < last;
+                  if (more1) { c += 32; tmem_ld_32x32(tacc + uint32_t(min(c, last) - tile0), v[1]); }
+                  m[0] = max32_acc(v[0], m[0]);
+                  if (!more1) break;
+                  tmem_ld_wait();
+                  const bool more0 = c < last;
+                  if (more0) { c += 32; tmem_ld_32x32(tacc + uint32_t(min(c, last) - tile0), v[0]); }
+                  m[0] = max32_acc(v[1], m[0]);
+                  if (!more0) break;
+                }
+              } else {
+                while (true) {
+                  tmem_ld_32x32(tacc + uint32_t(min(c, last) - tile0), v[0]);
+                  tmem_ld_wait();
+                  m[0] = max32_acc(v[0], m[0]);
+                  if (c >= last) break;
+                  c += 32;
+                }
               }
             } else {
-              while (true) {
-                tmem_ld_32x32(tacc + uint32_t(min(c, last) - tile0), v[0]);
-                tmem_ld_wait();
-                m[0] = max32_acc(v[0], m[0]);
-                if (c >= last) break;
-                c += 32;
-              }
+              // fewer than 32 of its tokens here (a short document, or the head / tail a tile boundary cut off)
+              const int cc = min(lo, tile1 - 32);
+  #pragma unroll
+              for (int j = 0; j < MTW; ++j) tmem_ld_32x32(tacc + uint32_t(j * TN) + uint32_t(cc - tile0), v[j]);
+              tmem_ld_wait();
+              const int a = lo - cc, b = hi - cc;   // 0 <= a < b <= 32, b - a < 32
+              const uint32_t bits = ((1u << (b - a)) - 1u) << a;
+  #pragma unroll
+              for (int j = 0; j < MTW; ++j) m[j] = max32_masked_acc(v[j], bits, m[j]);
             }
-          } else {
-            // fewer than 32 of its tokens here (a short document, or the head / tail a tile boundary cut off)
-            const int cc = min(lo, tile1 - 32);
-#pragma unroll
-            for (int j = 0; j < MTW; ++j) tmem_ld_32x32(tacc + uint32_t(j * TN) + uint32_t(cc - tile0), v[j]);
-            tmem_ld_wait();
-            const int a = lo - cc, b = hi - cc;   // 0 <= a < b <= 32, b - a < 32
-            const uint32_t bits = ((1u << (b - a)) - 1u) << a;
-#pragma unroll
-            for (int j = 0; j < MTW; ++j) m[j] = max32_masked_acc(v[j], bits, m[j]);
           }
+          if (e_tok <= tile1) finish_doc(); else break;   // else: the document continues in the next tile
         }
-        if (e_tok <= tile1) finish_doc(); else break;   // else: the document continues in the next tile
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(&tempty[unit], 0);   // the leader's MMA issuer owns both accumulators
+          else mbar_arrive(&tempty[unit]);
+        }
+        if (pending) emit_pending();          // after the release: off the MMA <-> epilogue critical path
+        if constexpr (kMtPass) {
+          m_p[ps] = m[0]; pend_m_p[ps] = pend_m[0]; pend_col_p[ps] = pend_col; pending_p[ps] = pending;
+        }
       }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_cluster(&tempty[unit], 0);   // the leader's MMA issuer owns both accumulators
-        else mbar_arrive(&tempty[unit]);
-      }
-      if (pending) emit_pending();          // after the release: off the MMA <-> epilogue critical path
       if (++ts == kTileStages) { ts = 0; tphase ^= 1; }
     }
-    while (have_doc) finish_doc();          // trailing empty documents (no tokens, no tile): -inf
-    if (pending) emit_pending();
+    if constexpr (kMtPass) {
+      const int sv_my = my, sv_s = s_tok, sv_e = e_tok, sv_ns = ns_tok, sv_ne = ne_tok, sv_batch = batch;
+      const bool sv_have = have_doc;
+      const uint32_t sv_ends = ends, sv_ends_next = ends_next;
+#pragma unroll
+      for (int ps = 0; ps < kPasses; ++ps) {
+        my = sv_my; s_tok = sv_s; e_tok = sv_e; ns_tok = sv_ns; ne_tok = sv_ne; batch = sv_batch; have_doc = sv_have;
+        ends = sv_ends; ends_next = sv_ends_next;
+        active[0] = active_p[ps]; out_row[0] = out_row_p[ps];
+        m[0] = m_p[ps]; pend_m[0] = pend_m_p[ps]; pend_col = pend_col_p[ps]; pending = pending_p[ps];
+        while (have_doc) finish_doc();
+        if (pending) emit_pending();
+      }
+    } else {
+      while (have_doc) finish_doc();        // trailing empty documents (no tokens, no tile): -inf
+      if (pending) emit_pending();
+    }
   }
 
   tc_fence_before_sync();
@@ -638,7 +690,7 @@ int sm_count() {
   return n;
 }
 
-template <int MT, int TN, bool TS, int ZP = 0, int CG = 1, int MTW = MT>
+template <int MT, int TN, bool TS, int ZP = 0, int CG = 1, int EPI = 0>
 int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries, TcParams p, dim3 grid,
                cudaStream_t stream) {
   constexpr int kTileBytes = (TN / CG) * HRC_DIM * 2;   // what ONE CTA stages per tile
@@ -671,7 +723,7 @@ int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries
   static PerDeviceOnce once;
   int dev;
   if (once.pending(&dev)) {
-    HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT, TN, TS, ZP, CG, MTW>,
+    HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT, TN, TS, ZP, CG, EPI>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     once.mark(dev);
   }
@@ -690,9 +742,9 @@ int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    HRC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, maxsim_tc_kernel<MT, TN, TS, ZP, CG, MTW>, tmap_d, tmap_q, p));
+    HRC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, maxsim_tc_kernel<MT, TN, TS, ZP, CG, EPI>, tmap_d, tmap_q, p));
   } else {
-    maxsim_tc_kernel<MT, TN, TS, ZP, CG, MTW><<<grid, cta_threads(MT, ZP), smem_bytes, stream>>>(tmap_d, tmap_q, p);
+    maxsim_tc_kernel<MT, TN, TS, ZP, CG, EPI><<<grid, cta_threads(MT, ZP), smem_bytes, stream>>>(tmap_d, tmap_q, p);
   }
   count_launch();
   HRC_CHECK_CUDA(cudaGetLastError());
@@ -764,11 +816,11 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
     TcParams pp = p;
     pp.n_qgroups = paired;
     pp.n_queries = n_queries < paired * 8 ? n_queries : paired * 8;
-    const bool mt_split = getenv("HRC_TC_MTSPLIT") != nullptr && atoi(getenv("HRC_TC_MTSPLIT")) != 0;
-    int rc = mt_split ? launch_cfg<2, 128, false, 0, 2, 1>(encode, d_tokens, d_queries, pp,
-                                                           dim3((unsigned)(pp.n_segments * paired)), stream)
-                      : launch_cfg<2, 128, false, 0, 2>(encode, d_tokens, d_queries, pp,
-                                                        dim3((unsigned)(pp.n_segments * paired)), stream);
+    const int epi = getenv("HRC_TC_EPI") != nullptr ? atoi(getenv("HRC_TC_EPI")) : 0;   // see EPI in the kernel
+    const dim3 pgrid((unsigned)(pp.n_segments * paired));
+    int rc = epi == 1   ? launch_cfg<2, 128, false, 0, 2, 1>(encode, d_tokens, d_queries, pp, pgrid, stream)
+             : epi == 2 ? launch_cfg<2, 128, false, 0, 2, 2>(encode, d_tokens, d_queries, pp, pgrid, stream)
+                        : launch_cfg<2, 128, false, 0, 2, 0>(encode, d_tokens, d_queries, pp, pgrid, stream);
     if (rc != 0 || paired == p.n_qgroups) return rc;
     const int done = paired * 8;                        // the odd group: queries [done, n_queries)
     TcParams pl = p;

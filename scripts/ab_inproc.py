@@ -31,7 +31,8 @@ def main():
     ap.add_argument("--rounds", type=int, default=12)
     ap.add_argument("--launches", type=int, default=10)
     ap.add_argument("--docs", type=int, default=0)
-    ap.add_argument("--env-ab", default="", help="NAME: run every library with NAME=0 and NAME=1 as separate contestants")
+    ap.add_argument("--env-ab", default="", help="NAME: run every library with NAME=<each of --env-values> as separate contestants")
+    ap.add_argument("--env-values", default="0,1")
     ap.add_argument("libs", nargs="+")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -46,9 +47,10 @@ def main():
     fns = [bind(os.path.abspath(p)) for p in a.libs]
     envs = [None] * len(fns)
     if a.env_ab:
-        fns = [f for f in fns for _ in (0, 1)]
-        envs = ["0", "1"] * len(a.libs)
-        a.libs = [f"{os.path.basename(p)}[{a.env_ab}={v}]" for p in a.libs for v in ("0", "1")]
+        vals = a.env_values.split(",")
+        fns = [f for f in fns for _ in vals]
+        envs = vals * len(a.libs)
+        a.libs = [f"{os.path.basename(p)}[{a.env_ab}={v}]" for p in a.libs for v in vals]
     stream = torch.cuda.current_stream(dev).cuda_stream
 
     def launch(fn, env=None):

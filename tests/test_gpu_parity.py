@@ -85,15 +85,15 @@ def test_batched_ts_kernel_matches_oracle(cuda_dev, shape, monkeypatch):
 
 @pytest.mark.parametrize("shape", [(64, 32, 512, 9, 32), (33, 127, 129, 5, 32), (120, 1, 200, 21, 32), (300, 1, 40, 16, 20),
                                    (3000, 16, 200, 40, 32), (1, 700, 700, 17, 32)])
-@pytest.mark.parametrize("pair", ["1", "0", "mtsplit"])
+@pytest.mark.parametrize("pair", ["1", "0", "epi1", "epi2"])
 def test_batched_kernel_more_shapes(cuda_dev, shape, pair, monkeypatch):
     """Batched (MT=2) kernels — CTA pairs (cta_group::2, the default from two query groups up, with an odd last
     group on the single-CTA kernel) and single CTAs (HRC_TC_PAIR=0): 40 queries over many segments, 17 queries on
     one 6-tile document, short documents, partial query groups."""
     L = _lib()
     monkeypatch.setenv("HRC_TC_PAIR", "0" if pair == "0" else "1")
-    if pair == "mtsplit":                      # optional variant: one M-tile per epilogue warp, per-unit barriers
-        monkeypatch.setenv("HRC_TC_MTSPLIT", "1")
+    if pair.startswith("epi"):                 # optional epilogue organisations (per-M-tile accumulator units)
+        monkeypatch.setenv("HRC_TC_EPI", pair[3:])
     q, tok, off = _case(78, *shape)
     exp = o.maxsim_scores(q.float(), tok.float(), off)
     got = L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev), path=L.PATH_TC)
