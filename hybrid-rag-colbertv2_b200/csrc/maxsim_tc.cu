@@ -190,11 +190,20 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   //  1  the warps take one M-TILE each and both walk every document; every (stage, M-tile) is its own unit.
   //  2  the warps alternate documents, and each walks a tile once PER M-TILE, releasing M-tile 0 before it reads
   //     M-tile 1; every (stage, M-tile) is its own unit, so 2 x MT hand-shakes are in flight.
+  //  3  as 0, but the MMA issuer publishes every M-TILE of a tile separately (one tfull per (stage, M-tile), still
+  //     one tempty per stage) and a warp reads a document's columns M-tile by M-tile: it works on M-tile 0 while
+  //     the MMAs of M-tile 1 are still executing, which takes half an epilogue off the hand-shake chain.
   static_assert(EPI == 0 || (MT == 2 && ZP == 0), "bad EPI");
-  constexpr int MTW = EPI == 0 ? MT : 1;                 // M-tiles read in one walk
-  constexpr int kUnitsPerStage = EPI == 0 ? 1 : MT;
+  constexpr int MTW = (EPI == 0 || EPI == 3) ? MT : 1;   // M-tiles read in one walk
+  constexpr int kFullPerStage = EPI == 0 ? 1 : MT;       // tfull barriers per accumulator stage
+  constexpr int kUnitsPerStage = (EPI == 0 || EPI == 3) ? 1 : MT;   // tempty barriers per accumulator stage
   constexpr int kUnits = kTileStages * kUnitsPerStage;
   constexpr int kReadersPerUnit = EPI == 1 ? epi_warps(MT) / MT : (ZP == 2 ? 8 : epi_warps(MT));
+  // HBM-bound kernels (MT == 1): ONE tcgen05.commit per tile (tfull); the shared-memory slot is released by the
+  // first epilogue warp when it sees tfull (the same event, ~100 cycles later, irrelevant with a 6-deep TMA ring).
+  // In-process A/B: C2 4.79 -> 4.70 ms, ragged 10.32 -> 10.07 ms.  The batched kernels keep the second commit
+  // (1,349 vs 1,332 TFLOP/s).
+  constexpr bool kForwardEmpty = MT == 1;
   static_assert(kUnits <= 4, "tfull / tempty hold 4 barriers each");
 
   extern __shared__ uint8_t smem_raw[];
@@ -249,7 +258,8 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     tma_prefetch_desc(&tmap_d);
     if (!TS) tma_prefetch_desc(&tmap_q);
     for (int i = 0; i < p.n_stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < kUnits; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kReadersPerUnit * CG); }
+    for (int i = 0; i < kTileStages * kFullPerStage; ++i) mbar_init(&tfull[i], 1);
+    for (int i = 0; i < kUnits; ++i) mbar_init(&tempty[i], kReadersPerUnit * CG);
     mbar_init(qfull, TS ? (EPI == 1 ? kEpiWarps : 4) : 1);
     fence_mbar_init();
   }
@@ -332,8 +342,9 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
         const uint32_t b_addr = sD_addr + stage * kTileBytes;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          const int unit = ts * kUnitsPerStage + (EPI == 0 ? 0 : mt);
-          if (EPI != 0 || mt == 0) {         // first M-tile of an accumulator unit: wait until its readers are done
+          const int unit = ts * kUnitsPerStage + (kUnitsPerStage == 1 ? 0 : mt);
+          const int funit = ts * kFullPerStage + (kFullPerStage == 1 ? 0 : mt);
+          if (kUnitsPerStage == MT || mt == 0) {   // first M-tile of an accumulator unit: wait until its readers are done
             mbar_wait_wd(&tempty[unit], tphase ^ 1);
             tc_fence_after_sync();
           }
@@ -354,10 +365,10 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
               }
             }
             // commits (CG == 2: multicast, the peer's producer and epilogue wait on their own copies)
-            if (EPI != 0 || mt == MT - 1) {    // last M-tile of the unit: accumulators ready for the epilogue
-              if constexpr (CG == 2) umma_commit_cg2(&tfull[unit]); else umma_commit(&tfull[unit]);
+            if (kFullPerStage == MT || mt == MT - 1) {   // accumulators (of this M-tile) ready for the epilogue
+              if constexpr (CG == 2) umma_commit_cg2(&tfull[funit]); else umma_commit(&tfull[funit]);
             }
-            if (mt == MT - 1) {                // smem slot reusable once these MMAs have read it
+            if (!kForwardEmpty && mt == MT - 1) {   // smem slot reusable once these MMAs have read it
               if constexpr (CG == 2) umma_commit_cg2(&empty[stage]); else umma_commit(&empty[stage]);
             }
           }
@@ -528,6 +539,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     };
 
     int ts = 0; uint32_t tphase = 0;
+    int stage_e = 0;                        // shared-memory slot of the tile being read (kForwardEmpty)
     for (int t = 0; t < n_tiles; ++t) {
       // kMtPass: the walk state at the start of the tile, replayed for every M-tile
       const int sv_my = my, sv_s = s_tok, sv_e = e_tok, sv_ns = ns_tok, sv_ne = ne_tok, sv_batch = batch;
@@ -543,8 +555,18 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
           m[0] = m_p[ps]; pend_m[0] = pend_m_p[ps]; pend_col = pend_col_p[ps]; pending = pending_p[ps];
         }
         const int unit = ts * kUnitsPerStage + (kMtSplit ? sub : (kMtPass ? ps : 0));
-        mbar_wait_wd(&tfull[unit], tphase);
+        mbar_wait_wd(&tfull[EPI == 3 ? ts * MT : unit], tphase);
+        if constexpr (kForwardEmpty) {        // the tile's MMAs are done: its shared-memory slot may be refilled
+          if (warp == (ZP ? 4 : kEpiWarp0) && lane == 0) mbar_arrive(&empty[stage_e]);
+          if (++stage_e == p.n_stages) stage_e = 0;
+        }
         tc_fence_after_sync();
+        bool got1 = EPI != 3;                 // EPI == 3: M-tile 1 of this tile has been waited for
+        auto need_mt1 = [&]() {
+          if constexpr (EPI == 3) {
+            if (!got1) { mbar_wait_wd(&tfull[ts * MT + 1], tphase); tc_fence_after_sync(); got1 = true; }
+          }
+        };
         const int tile0 = t * TN, tile1 = tile0 + TN;
         // accumulator columns of this tile for this warp's j-th M-tile: tacc + j * TN + (token position - tile0)
         const uint32_t tacc = acc_base + lane_base + uint32_t((ts * MT + mt0) * TN);
@@ -559,7 +581,29 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
               // harmless under max — so no column is ever masked.
               const int last = hi - 32;
               int c = lo;
-              if constexpr (MTW == 2) {
+              if constexpr (EPI == 3) {
+                // M-tile major: all of this document's columns of M-tile 0 (while M-tile 1's MMAs may still be
+                // executing), then M-tile 1; software pipeline over chunks with two register buffers
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  if (j == 1) need_mt1();
+                  const uint32_t tj = tacc + uint32_t(j * TN);
+                  c = lo;
+                  tmem_ld_32x32(tj + uint32_t(min(c, last) - tile0), v[0]);
+                  while (true) {
+                    tmem_ld_wait();
+                    const bool more1 = c < last;
+                    if (more1) { c += 32; tmem_ld_32x32(tj + uint32_t(min(c, last) - tile0), v[1]); }
+                    m[j] = max32_acc(v[0], m[j]);
+                    if (!more1) break;
+                    tmem_ld_wait();
+                    const bool more0 = c < last;
+                    if (more0) { c += 32; tmem_ld_32x32(tj + uint32_t(min(c, last) - tile0), v[0]); }
+                    m[j] = max32_acc(v[1], m[j]);
+                    if (!more0) break;
+                  }
+                }
+              } else if constexpr (MTW == 2) {
                 // software pipeline over (chunk, M-tile) steps: one TMEM load is in flight while the max tree of the
                 // previous step runs (v[0] always holds M-tile 0, v[1] M-tile 1)
                 uint32_t col = uint32_t(min(c, last) - tile0);
@@ -605,12 +649,13 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
             } else {
               // fewer than 32 of its tokens here (a short document, or the head / tail a tile boundary cut off)
               const int cc = min(lo, tile1 - 32);
-  #pragma unroll
+              need_mt1();
+#pragma unroll
               for (int j = 0; j < MTW; ++j) tmem_ld_32x32(tacc + uint32_t(j * TN) + uint32_t(cc - tile0), v[j]);
               tmem_ld_wait();
               const int a = lo - cc, b = hi - cc;   // 0 <= a < b <= 32, b - a < 32
               const uint32_t bits = ((1u << (b - a)) - 1u) << a;
-  #pragma unroll
+#pragma unroll
               for (int j = 0; j < MTW; ++j) m[j] = max32_masked_acc(v[j], bits, m[j]);
             }
           }
@@ -820,6 +865,7 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
     const dim3 pgrid((unsigned)(pp.n_segments * paired));
     int rc = epi == 1   ? launch_cfg<2, 128, false, 0, 2, 1>(encode, d_tokens, d_queries, pp, pgrid, stream)
              : epi == 2 ? launch_cfg<2, 128, false, 0, 2, 2>(encode, d_tokens, d_queries, pp, pgrid, stream)
+             : epi == 3 ? launch_cfg<2, 128, false, 0, 2, 3>(encode, d_tokens, d_queries, pp, pgrid, stream)
                         : launch_cfg<2, 128, false, 0, 2, 0>(encode, d_tokens, d_queries, pp, pgrid, stream);
     if (rc != 0 || paired == p.n_qgroups) return rc;
     const int done = paired * 8;                        // the odd group: queries [done, n_queries)

@@ -85,7 +85,7 @@ def test_batched_ts_kernel_matches_oracle(cuda_dev, shape, monkeypatch):
 
 @pytest.mark.parametrize("shape", [(64, 32, 512, 9, 32), (33, 127, 129, 5, 32), (120, 1, 200, 21, 32), (300, 1, 40, 16, 20),
                                    (3000, 16, 200, 40, 32), (1, 700, 700, 17, 32)])
-@pytest.mark.parametrize("pair", ["1", "0", "epi1", "epi2"])
+@pytest.mark.parametrize("pair", ["1", "0", "epi1", "epi2", "epi3"])
 def test_batched_kernel_more_shapes(cuda_dev, shape, pair, monkeypatch):
     """Batched (MT=2) kernels — CTA pairs (cta_group::2, the default from two query groups up, with an odd last
     group on the single-CTA kernel) and single CTAs (HRC_TC_PAIR=0): 40 queries over many segments, 17 queries on
