@@ -364,7 +364,7 @@ class HybridRetriever:
         self._log(f"   • ColBERT: {t['colbert']:.3f}s")
 
         start = time.time()
-        fused_results = self._reciprocal_rank_fusion(bm25_results, colbert_results)
+        fused_results = self._reciprocal_rank_fusion(bm25_results, colbert_results, k=self.config.rrf_k)
         candidates = fused_results[:self.config.rerank_candidates]
         t['fusion'] = time.time() - start
         self._log(f"   • Fusion: {t['fusion']:.3f}s")
@@ -400,11 +400,9 @@ class HybridRetriever:
         results = self.indexer.colbert_retriever.search(query=query, k=k)
         return [{'chunk_id': r['document_id'], 'score': r['score'], 'source': 'colbert'} for r in results]
 
-    def _reciprocal_rank_fusion(self, bm25_results: List[Dict], colbert_results: List[Dict], k: int = None
+    def _reciprocal_rank_fusion(self, bm25_results: List[Dict], colbert_results: List[Dict], k: int = 60
                                 ) -> List[Dict]:
         """RRF fusion (:960-978) on the device, bit-compatible with the reference's fp64 Python arithmetic."""
-        if k is None:
-            k = self.config.rrf_k
         dev = self.indexer.colbert_retriever.device
         a = torch.tensor([[r['chunk_id'] for r in bm25_results]], dtype=torch.int32, device=dev).reshape(1, -1)
         b = torch.tensor([[r['chunk_id'] for r in colbert_results]], dtype=torch.int32, device=dev).reshape(1, -1)

@@ -10,6 +10,8 @@ SURVEY.md F4), so those imports are stubbed with MagicMock exactly as in SURVEY.
                       reference's own search() / rerank() results on them: pins the GPU "reference_literal" path
   api_shapes.json     search()/rerank()/index()/load() observable behaviour with a fake encoder
   rrf.json            `_reciprocal_rank_fusion` ids + fp64 scores (repr round-trips) incl. tie order
+  api_signatures.json the reference's method signatures (names, parameter names, defaults) and RAGConfig fields
+                      for the classes on the path: what "drops into local_rag_complete.py unchanged" must match
 """
 import importlib.util
 import json
@@ -155,6 +157,29 @@ def main():
             api["maxsim_1d"] = type(e).__name__
     with open(os.path.join(HERE, "api_shapes.json"), "w") as f:
         json.dump(api, f, indent=1, sort_keys=True)
+
+    # ---- 2b. signatures of the classes on the path ----------------------------------------------
+    import dataclasses
+    import inspect
+
+    def sig(fn):
+        out = []
+        for name, prm in inspect.signature(fn).parameters.items():
+            out.append({"name": name, "kind": prm.kind.name,
+                        "default": None if prm.default is inspect.Parameter.empty else repr(prm.default),
+                        "has_default": prm.default is not inspect.Parameter.empty})
+        return out
+
+    sigs = {"RAGConfig": [{"name": f.name, "default": repr(f.default)} for f in dataclasses.fields(m.RAGConfig)]}
+    for cls, methods in {
+        "JinaColBERTRetriever": ["__init__", "index", "load", "search", "rerank", "_maxsim_score"],
+        "DualIndexer": ["__init__", "build_bm25_index", "build_colbert_index", "load_indexes"],
+        "HybridRetriever": ["__init__", "retrieve", "_bm25_search", "_colbert_search", "_reciprocal_rank_fusion",
+                            "_fetch_chunks_from_db", "_colbert_rerank"],
+    }.items():
+        sigs[cls] = {name: sig(getattr(getattr(m, cls), name)) for name in methods}
+    with open(os.path.join(HERE, "api_signatures.json"), "w") as f:
+        json.dump(sigs, f, indent=1, sort_keys=True)
 
     # ---- 3. RRF ----------------------------------------------------------------------------------
     H = m.HybridRetriever.__new__(m.HybridRetriever)

@@ -132,3 +132,31 @@ def test_config_matches_reference_defaults(golden_dir):
     for k, v in api["config_defaults"].items():
         assert getattr(cfg, k) == v
     assert cfg.device == "cuda" and cfg.rrf_k == 60 and cfg.rerank_candidates == 50
+
+
+def test_class_surface_matches_reference_signatures(golden_dir):
+    """tests/golden/api_signatures.json was extracted from the unmodified reference (make_golden.py): every method on
+    the path exists here with the same leading parameter names and defaults, so the classes drop into
+    local_rag_complete.py unchanged (call sites :844, :871, :879, :954, :999).  Extra parameters must be optional."""
+    import dataclasses
+    import inspect
+    ref = json.load(open(os.path.join(golden_dir, "api_signatures.json")))
+    ours_fields = {f.name: repr(f.default) for f in dataclasses.fields(hrc.RAGConfig)}
+    for f in ref["RAGConfig"]:
+        assert f["name"] in ours_fields, f["name"]
+        if f["name"] != "device":                      # the one deliberate difference: "cuda" instead of "cpu"
+            assert ours_fields[f["name"]] == f["default"], f["name"]
+    assert ours_fields["device"] == "'cuda'"
+    for cls in ("JinaColBERTRetriever", "DualIndexer", "HybridRetriever"):
+        for meth, params in ref[cls].items():
+            fn = getattr(getattr(hrc, cls), meth, None)
+            assert fn is not None, f"{cls}.{meth} missing"
+            mine = list(inspect.signature(fn).parameters.values())
+            assert len(mine) >= len(params), f"{cls}.{meth}: fewer parameters than the reference"
+            for i, rp in enumerate(params):
+                assert mine[i].name == rp["name"], f"{cls}.{meth}: parameter {i} is {mine[i].name}, reference {rp['name']}"
+                if rp["has_default"]:
+                    assert repr(mine[i].default) == rp["default"], f"{cls}.{meth}({rp['name']}) default"
+            for extra in mine[len(params):]:
+                assert extra.default is not inspect.Parameter.empty or extra.kind in (
+                    inspect.Parameter.VAR_POSITIONAL, inspect.Parameter.VAR_KEYWORD), f"{cls}.{meth}: extra required {extra.name}"
