@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("HRC_LIB_PATH") or os.path.join(_HERE, "libhrc.so")   
 PATH_AUTO, PATH_SIMT, PATH_TC = 0, 1, 2
 DIM = 128
 MAX_TOPK = 2048
-TC_MAX_LQ = 32
+TC_MAX_LQ = 32          # query tokens per slot on the tensor-core path; up to 8 slots (lq <= 256)
 
 #: every symbol include/hrc.h declares: name -> (restype, argtypes)
 _c = ctypes

@@ -62,7 +62,7 @@ static int maxsim_dispatch(const void* d_tokens, const int64_t* d_offsets, int64
   HRC_REQUIRE(n_items == 0 || n_queries == 0 ||
                   (d_tokens != nullptr && d_offsets != nullptr && d_queries != nullptr && d_scores != nullptr),
               "maxsim: null pointer argument");
-  if (path == HRC_PATH_AUTO) path = (lq <= HRC_TC_MAX_LQ && total_tokens > 0) ? HRC_PATH_TC : HRC_PATH_SIMT;
+  if (path == HRC_PATH_AUTO) path = (lq <= HRC_TC_MAX_LQ * HRC_TC_MAX_SLOTS && total_tokens > 0) ? HRC_PATH_TC : HRC_PATH_SIMT;
   if (path == HRC_PATH_TC)
     return launch_maxsim_tc(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_items, d_queries, n_queries, lq,
                             d_scores, stream);

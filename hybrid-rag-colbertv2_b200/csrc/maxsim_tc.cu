@@ -69,7 +69,10 @@ struct TcParams {
   int64_t n_docs;
   int64_t total_tokens;
   int64_t n_items;          // row stride of scores (n_docs, or n_cand)
-  int n_queries;
+  int n_queries;            // (virtual) queries: one per 32-token slot of a real query
+  int n_real_queries;       // rows of the query tensor
+  int q_slots;              // 32-token slots per real query: ceil(lq / 32); virtual query v = real v / q_slots, slot v % q_slots
+  int vq_base;              // first virtual query of this launch
   int lq;
   int n_segments;           // corpus mode: CTAs along the corpus
   int n_qgroups;            // corpus mode: query groups (4*MT queries each)
@@ -227,8 +230,8 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   int q_base;   // first query of slot 0, M-tile 0
   int64_t item = 0;
   if (p.cand_ids == nullptr) {
-    q_base = int(blockIdx.x % p.n_qgroups) * 4 * MT;   // query groups vary fastest: CTAs sharing a
-    item = blockIdx.x / p.n_qgroups;                   // corpus segment run together (L2 reuse)
+    q_base = p.vq_base + int(blockIdx.x % p.n_qgroups) * 4 * MT;   // query groups vary fastest: CTAs sharing a
+    item = blockIdx.x / p.n_qgroups;                                // corpus segment run together (L2 reuse)
   } else {
     q_base = blockIdx.y;
     item = blockIdx.x;
@@ -242,7 +245,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
       d1 = (item + 1 == p.n_segments) ? p.n_docs : lower_bound_doc(p.offsets, p.n_docs, b1);
       if (item == 0) d0 = 0;
     } else {
-      const int64_t id = p.cand_ids[int64_t(q_base) * p.n_items + item];
+      const int64_t id = p.cand_ids[int64_t(q_base / p.q_slots) * p.n_items + item];   // the REAL query's list
       if (id < 0 || id >= p.n_docs) {
         p.scores[int64_t(q_base) * p.n_items + item] = -INFINITY;
         d0 = d1 = 0;
@@ -291,14 +294,16 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
           // Rows >= lq and queries >= n_queries are out of bounds of the map and arrive as zeros.
 #pragma unroll
           for (int g = 0; g < kM / 32; ++g) {
-            const int q = (ZP && g >= p.slots_used) ? p.n_queries : q_base + 4 * mt + (g % p.slots_used);   // ZP: out of bounds -> zeros
+            const int vq = (ZP && g >= p.slots_used) ? p.n_queries : q_base + 4 * mt + (g % p.slots_used);   // ZP: out of bounds -> zeros
+            // virtual query -> (real query, first token row); a query longer than 32 tokens is scored slot by slot
+            const int q = vq / p.q_slots, row0 = (vq % p.q_slots) * 32;
             uint8_t* dst = sQ + mt * kQBytes + g * kSlotBytes;
             if constexpr (CG == 2) {
-              tma_load_3d_cg2(dst, &tmap_q, qfull, 0, 0, q, kEvictLast);
-              tma_load_3d_cg2(dst + kQBytes / 2, &tmap_q, qfull, 64, 0, q, kEvictLast);
+              tma_load_3d_cg2(dst, &tmap_q, qfull, 0, row0, q, kEvictLast);
+              tma_load_3d_cg2(dst + kQBytes / 2, &tmap_q, qfull, 64, row0, q, kEvictLast);
             } else {
-              tma_load_3d(dst, &tmap_q, qfull, 0, 0, q, kEvictLast);
-              tma_load_3d(dst + kQBytes / 2, &tmap_q, qfull, 64, 0, q, kEvictLast);
+              tma_load_3d(dst, &tmap_q, qfull, 0, row0, q, kEvictLast);
+              tma_load_3d(dst + kQBytes / 2, &tmap_q, qfull, 64, row0, q, kEvictLast);
             }
           }
         }
@@ -751,7 +756,7 @@ int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries
     HRC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(tokens) failed: %d", int(r));
   }
   {
-    cuuint64_t dims[3] = {HRC_DIM, (cuuint64_t)p.lq, (cuuint64_t)p.n_queries};
+    cuuint64_t dims[3] = {HRC_DIM, (cuuint64_t)p.lq, (cuuint64_t)p.n_real_queries};
     cuuint64_t strides[2] = {HRC_DIM * 2, (cuuint64_t)p.lq * HRC_DIM * 2};
     cuuint32_t box[3] = {64, 32, 1};
     cuuint32_t estr[3] = {1, 1, 1};
@@ -798,11 +803,52 @@ int launch_cfg(EncodeTiledFn encode, const void* d_tokens, const void* d_queries
 
 }  // namespace
 
+// out[q][i] = sum over the slots of query q, in slot order (deterministic)
+__global__ void sum_slots_kernel(const float* __restrict__ part, int q_slots, int64_t n_items, int64_t total,
+                                 float* __restrict__ out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t q = i / n_items, d = i - q * n_items;
+  float acc = 0.f;
+  for (int sl = 0; sl < q_slots; ++sl) acc += part[(q * q_slots + sl) * n_items + d];
+  out[i] = acc;
+}
+
+static int launch_tc_slots(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                           const int32_t* d_cand_ids, int64_t n_items, const void* d_queries, int n_real_queries,
+                           int q_slots, int lq, float* d_scores, cudaStream_t stream);
+
 int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
                      const int32_t* d_cand_ids, int64_t n_items, const void* d_queries, int n_queries,
                      int lq, float* d_scores, cudaStream_t stream) {
   if (n_items == 0 || n_queries == 0) return 0;
-  HRC_REQUIRE(lq >= 1 && lq <= HRC_TC_MAX_LQ, "tc path: lq=%d not in [1,%d]", lq, HRC_TC_MAX_LQ);
+  HRC_REQUIRE(lq >= 1 && lq <= HRC_TC_MAX_LQ * HRC_TC_MAX_SLOTS, "tc path: lq=%d not in [1,%d]", lq,
+              HRC_TC_MAX_LQ * HRC_TC_MAX_SLOTS);
+  const int q_slots = (lq + HRC_TC_MAX_LQ - 1) / HRC_TC_MAX_LQ;
+  if (q_slots == 1)
+    return launch_tc_slots(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_items, d_queries, n_queries, 1, lq,
+                           d_scores, stream);
+  // A query of more than 32 tokens is scored as q_slots virtual queries of <= 32 tokens (rows beyond lq arrive as
+  // zeros from TMA and add max_t <0, d_t> = 0); their partial scores are summed in slot order.
+  HRC_REQUIRE(int64_t(n_queries) * q_slots <= 65535, "tc path: too many query slots (%d x %d)", n_queries, q_slots);
+  float* part = nullptr;
+  const int64_t total = int64_t(n_queries) * n_items;
+  HRC_CHECK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&part), size_t(total) * q_slots * sizeof(float), stream));
+  int rc = launch_tc_slots(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_items, d_queries, n_queries, q_slots,
+                           lq, part, stream);
+  if (rc == 0) {
+    sum_slots_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(part, q_slots, n_items, total, d_scores);
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) rc = 1;
+  }
+  cudaFreeAsync(part, stream);
+  return rc;
+}
+
+static int launch_tc_slots(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                           const int32_t* d_cand_ids, int64_t n_items, const void* d_queries, int n_real_queries,
+                           int q_slots, int lq, float* d_scores, cudaStream_t stream) {
+  const int n_queries = n_real_queries * q_slots;      // virtual queries from here on
   HRC_REQUIRE(total_tokens > 0 && total_tokens < (1ll << 31), "tc path: total_tokens=%lld out of range",
               (long long)total_tokens);
   HRC_REQUIRE((reinterpret_cast<uintptr_t>(d_tokens) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_queries) & 15) == 0,
@@ -819,6 +865,9 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
   p.total_tokens = total_tokens;
   p.n_items = n_items;
   p.n_queries = n_queries;
+  p.n_real_queries = n_real_queries;
+  p.q_slots = q_slots;
+  p.vq_base = 0;
   p.lq = lq;
   p.n_segments = 1;
   p.n_qgroups = 1;
@@ -848,7 +897,7 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
   p.doc_policy = kEvictNormal;  // the other query groups re-read this tile from L2
   // Batched default: SS operands, N=128.  Measured on C3 (256 queries, power-capped at ~990 W): SS 1123 TFLOP/s,
   // TS (A in TMEM, N=96) 1069 TFLOP/s; with TMA and epilogue disabled both reach the cuBLAS burst rate.
-  const bool use_ts = getenv("HRC_TC_TS") != nullptr && atoi(getenv("HRC_TC_TS")) != 0;
+  const bool use_ts = q_slots == 1 && getenv("HRC_TC_TS") != nullptr && atoi(getenv("HRC_TC_TS")) != 0;
   // CTA pairs (cta_group::2, default from 2 query groups up; env HRC_TC_PAIR=0 disables): two query groups of the
   // same corpus segment share every document tile — each CTA stages half of it — so the L2 -> shared-memory
   // traffic and the B-operand reads per SM halve.  C3 (256 queries, 1M ragged documents, power-capped):
@@ -868,13 +917,10 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
              : epi == 3 ? launch_cfg<2, 128, false, 0, 2, 3>(encode, d_tokens, d_queries, pp, pgrid, stream)
                         : launch_cfg<2, 128, false, 0, 2, 0>(encode, d_tokens, d_queries, pp, pgrid, stream);
     if (rc != 0 || paired == p.n_qgroups) return rc;
-    const int done = paired * 8;                        // the odd group: queries [done, n_queries)
-    TcParams pl = p;
+    TcParams pl = p;                                    // the odd group: (virtual) queries [paired * 8, n_queries)
     pl.n_qgroups = 1;
-    pl.n_queries = n_queries - done;
-    pl.queries = p.queries + size_t(done) * lq * HRC_DIM;
-    pl.scores = p.scores + size_t(done) * size_t(n_items);
-    return launch_cfg<2, 128, false>(encode, d_tokens, pl.queries, pl, dim3((unsigned)pl.n_segments), stream);
+    pl.vq_base = paired * 8;
+    return launch_cfg<2, 128, false>(encode, d_tokens, d_queries, pl, dim3((unsigned)pl.n_segments), stream);
   }
   if (!use_ts) {
     const int64_t tiles = (total_tokens + 127) / 128;

@@ -34,6 +34,7 @@ extern "C" {
 #define HRC_DIM 128            /* embedding width (jina-colbert-v2 projects to 128)            */
 #define HRC_MAX_TOPK 2048      /* largest k the selection kernels accept                        */
 #define HRC_TC_MAX_LQ 32       /* query tokens per query slot on the tcgen05 path               */
+#define HRC_TC_MAX_SLOTS 8     /* a longer query is scored as up to 8 slots: lq <= 256 on that path */
 
 /* scoring path selector */
 #define HRC_PATH_AUTO 0
@@ -56,7 +57,8 @@ uint64_t hrc_launch_count(void);
  * Replaces: JinaColBERTRetriever._maxsim_score, local_rag_complete.py:802-831 (as its docstring
  * :807-812 and BASELINE.json's north_star define it), called from search :764.
  *   d_queries : bf16 [n_queries][lq][128]
- *   path      : HRC_PATH_*; AUTO picks TC when lq <= HRC_TC_MAX_LQ and the corpus is large enough.
+ *   path      : HRC_PATH_*; AUTO picks TC when lq <= HRC_TC_MAX_LQ * HRC_TC_MAX_SLOTS (a query longer than 32
+ *               tokens is scored as ceil(lq / 32) slots whose partial scores are summed in slot order).
  * An empty document (length 0) scores -inf.
  */
 int hrc_maxsim_scores(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs,

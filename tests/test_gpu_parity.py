@@ -189,11 +189,31 @@ def test_search_host_equals_device_search(cuda_dev):
     assert small.search_host(qf, 1000)[0].shape == (3, 30)    # k clamps to N (:767)
 
 
-def test_simt_handles_long_queries(cuda_dev):
+@pytest.mark.parametrize("shape", [(25, 1, 70, 2, 77), (300, 20, 300, 1, 64), (40, 1, 200, 5, 33), (64, 32, 512, 9, 96),
+                                   (10, 3, 40, 1, 256)])
+def test_long_queries_on_the_tensor_core_path(cuda_dev, shape):
+    """lq > 32: the query is scored as ceil(lq / 32) slots of <= 32 tokens (zero-filled rows add 0) whose partial
+    scores are summed in slot order — single-query, few-query and CTA-pair kernels, and the candidate entry point."""
     L = _lib()
-    q, tok, off = _case(11, 25, 1, 70, 2, 77)
+    q, tok, off = _case(11, *shape)
     exp = o.maxsim_scores(q.float(), tok.float(), off)
-    _assert_scores(L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev)), exp, "auto lq=77")
+    tok_d, off_d, q_d = tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev)
+    _assert_scores(L.maxsim_scores(tok_d, off_d, q_d, path=L.PATH_TC), exp, f"tc lq={shape[4]}")
+    _assert_scores(L.maxsim_scores(tok_d, off_d, q_d), exp, f"auto lq={shape[4]}")
+    n = shape[0]
+    g = torch.Generator().manual_seed(4)
+    cand = torch.randint(0, n, (shape[3], 7), generator=g, dtype=torch.int32)
+    cand[0, 3] = -1
+    expc = torch.gather(exp, 1, cand.clamp(0, n - 1).to(torch.int64))
+    expc[0, 3] = float("-inf")
+    _assert_scores(L.maxsim_scores_ids(tok_d, off_d, cand.to(cuda_dev), q_d, path=L.PATH_TC), expc, "candidates")
+
+
+def test_very_long_queries_take_the_simt_path(cuda_dev):
+    L = _lib()
+    q, tok, off = _case(11, 25, 1, 70, 2, 300)
+    exp = o.maxsim_scores(q.float(), tok.float(), off)
+    _assert_scores(L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev)), exp, "auto lq=300")
     with pytest.raises(Exception):
         L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev), path=L.PATH_TC)
 
