@@ -9,6 +9,7 @@ B200 raises.
 from __future__ import annotations
 
 import os
+import sys
 import time
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
@@ -48,6 +49,17 @@ class RAGConfig:
     maxsim_path: int = _lib.PATH_AUTO
 
 
+_ENCODER_NOTICE_SHOWN = False
+
+# additive knobs and their defaults: the reference's own RAGConfig (used after `install`) does not have them
+_KNOB_DEFAULTS = {"rrf_k": 60, "rerank_candidates": 50, "score_reduction": "sum", "score_mode": "maxsim",
+                  "maxsim_path": _lib.PATH_AUTO}
+
+
+def _knob(config, name: str):
+    return getattr(config, name, _KNOB_DEFAULTS[name])
+
+
 def _as_query_batch(q: torch.Tensor) -> torch.Tensor:
     """[Lq, D] or [Bq, Lq, D] -> bf16 [Bq, Lq, D] (the unsqueeze at local_rag_complete.py:814-815)."""
     if q.dim() == 2:
@@ -62,13 +74,29 @@ class JinaColBERTRetriever:
 
     def __init__(self, config: RAGConfig, encoder=None):
         self.config = config
-        # the reference loads SentenceTransformer(config.embedding_model) here (:720-724); weights are
-        # unavailable offline and the encoder is out of the hot path, so it is injectable.
-        self.model = encoder if encoder is not None else SyntheticEncoder()
+        # The reference loads SentenceTransformer(config.embedding_model, trust_remote_code=True, device=...) here
+        # (:720-724).  The encoder is not on the hot path, so it is injectable; without one, the reference's own
+        # construction is attempted and the deterministic stand-in is used (loudly) when the package or the weights
+        # are unavailable, as they are offline.
+        self.model = encoder if encoder is not None else self._default_encoder()
         self.store: Optional[PackedStore] = None
         self.corpus: Optional[List[str]] = None
         self._buffers = _lib.SearchBuffers()
         self._host_search = _lib.HostSearch()
+
+    def _default_encoder(self):
+        if os.environ.get("HRC_ENCODER", "").lower() != "synthetic":
+            try:
+                from sentence_transformers import SentenceTransformer   # absent offline
+                return SentenceTransformer(self.config.embedding_model, trust_remote_code=True, device=str(self.device))
+            except Exception as exc:   # noqa: BLE001  (ImportError, missing weights, no network ...)
+                global _ENCODER_NOTICE_SHOWN
+                if not _ENCODER_NOTICE_SHOWN:   # once per process, on stderr (stdout carries bench.py's JSON line)
+                    _ENCODER_NOTICE_SHOWN = True
+                    print(f"[hrc] {getattr(self.config, 'embedding_model', 'encoder')} unavailable "
+                          f"({type(exc).__name__}); using the deterministic SyntheticEncoder — pass encoder=... for "
+                          "real embeddings", file=sys.stderr)
+        return SyntheticEncoder()
 
     # `corpus_embeddings` is the reference's attribute name for the store (:725,:735,:752)
     @property
@@ -77,7 +105,10 @@ class JinaColBERTRetriever:
 
     @property
     def device(self) -> torch.device:
-        return torch.device(self.config.device)
+        """The CUDA device of the store.  The reference's RAGConfig says "cpu" / "mps" (:82); this implementation has
+        no CPU path, so anything that is not a CUDA device name means "the current CUDA device"."""
+        dev = str(getattr(self.config, "device", "cuda"))
+        return torch.device(dev if dev.startswith("cuda") else "cuda")
 
     # ------------------------------------------------------------------------------------------
     # index build / persistence  (:728-753)
@@ -143,10 +174,10 @@ class JinaColBERTRetriever:
         return _as_query_batch(q).to(self.device, torch.bfloat16).contiguous()
 
     def _finish_scores(self, scores: torch.Tensor, lq: int) -> torch.Tensor:
-        return scores / float(lq) if self.config.score_reduction == "mean" else scores
+        return scores / float(lq) if _knob(self.config, "score_reduction") == "mean" else scores
 
     def _literal(self, mode: Optional[str] = None) -> bool:
-        mode = self.config.score_mode if mode is None else mode
+        mode = _knob(self.config, "score_mode") if mode is None else mode
         if mode not in ("maxsim", "reference_literal"):
             raise ValueError(f"score_mode must be 'maxsim' or 'reference_literal', got {mode!r}")
         return mode == "reference_literal"
@@ -154,7 +185,7 @@ class JinaColBERTRetriever:
     def _score_store(self, store: PackedStore, q: torch.Tensor, mode: Optional[str] = None) -> torch.Tensor:
         if self._literal(mode):
             return _lib.meanpool_cosine_scores(store.tokens, store.offsets, q)
-        s = _lib.maxsim_scores(store.tokens, store.offsets, q, path=self.config.maxsim_path)
+        s = _lib.maxsim_scores(store.tokens, store.offsets, q, path=_knob(self.config, "maxsim_path"))
         return self._finish_scores(s, q.shape[1])
 
     def score_embeddings(self, query_embeddings: torch.Tensor) -> torch.Tensor:
@@ -178,7 +209,7 @@ class JinaColBERTRetriever:
             ids, sc = _lib.keys_unpack(keys) if unpack else (None, None)
             return keys, ids, sc
         return _lib.search(self.store.tokens, self.store.offsets, q, k_eff, id_base=self.store.doc_id_base,
-                           path=self.config.maxsim_path, buffers=self._buffers, unpack=unpack)
+                           path=_knob(self.config, "maxsim_path"), buffers=self._buffers, unpack=unpack)
 
     def search_embeddings(self, query_embeddings: torch.Tensor, k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
         """(doc ids int32 [Bq, k'], scores fp32 [Bq, k']) with k' = min(k, N), best first."""
@@ -202,7 +233,7 @@ class JinaColBERTRetriever:
         if k_eff <= 0:
             return torch.zeros((q.shape[0], 0), dtype=torch.int32), torch.zeros((q.shape[0], 0))
         ids, sc = self._host_search(self.store.tokens, self.store.offsets, q, k_eff, id_base=self.store.doc_id_base,
-                                    path=self.config.maxsim_path)
+                                    path=_knob(self.config, "maxsim_path"))
         return ids, self._finish_scores(sc, q.shape[1])
 
     def rerank_ids(self, query_embeddings: torch.Tensor, candidate_ids: torch.Tensor, k: int = 10
@@ -227,7 +258,7 @@ class JinaColBERTRetriever:
             pos, top_scores = _lib.keys_unpack(_lib.topk(cs, k_eff))
             return pos, torch.gather(cand, 1, pos.clamp_min(0).long()), top_scores
         pos, doc_ids, top_scores, _ = _lib.rerank(self.store.tokens, self.store.offsets, cand, q, k_eff,
-                                                  path=self.config.maxsim_path)
+                                                  path=_knob(self.config, "maxsim_path"))
         return pos, doc_ids, self._finish_scores(top_scores, q.shape[1])
 
     def _require_store(self) -> None:
@@ -286,6 +317,27 @@ class JinaColBERTRetriever:
         q = self._prep_queries(query_embedding)
         tmp = PackedStore.from_dense(doc_embeddings, None, device=self.device)
         return self._score_store(tmp, q, mode).squeeze()
+
+
+def install(module, classes: Sequence[str] = ("JinaColBERTRetriever",)) -> None:
+    """Drop this implementation into a loaded `local_rag_complete` module WITHOUT editing it.
+
+    The reference's `DualIndexer.__init__` constructs `JinaColBERTRetriever(config)` through the module's global
+    name (:844), and `HybridRetriever` only calls `search(query=, k=)` / `rerank(query=, documents=, k=)` on it
+    (:954, :999), so rebinding that one name is enough: the reference's own DualIndexer, HybridRetriever and
+    RAGApplication then run on the B200 kernels.  `classes` may also name "DualIndexer" and "HybridRetriever"
+    to take the device-resident RRF and the rerank-by-id path as well.
+
+        import local_rag_complete as lrc, hybrid_rag_colbertv2_b200 as hrc
+        hrc.install(lrc)                       # or hrc.install(lrc, ("JinaColBERTRetriever", "DualIndexer", "HybridRetriever"))
+    """
+    mine = {"JinaColBERTRetriever": JinaColBERTRetriever, "DualIndexer": DualIndexer, "HybridRetriever": HybridRetriever}
+    for name in classes:
+        if name not in mine:
+            raise ValueError(f"install: unknown class {name!r}")
+        if not hasattr(module, name):
+            raise AttributeError(f"install: {module.__name__} has no {name}")
+        setattr(module, name, mine[name])
 
 
 class DualIndexer:
@@ -364,8 +416,8 @@ class HybridRetriever:
         self._log(f"   • ColBERT: {t['colbert']:.3f}s")
 
         start = time.time()
-        fused_results = self._reciprocal_rank_fusion(bm25_results, colbert_results, k=self.config.rrf_k)
-        candidates = fused_results[:self.config.rerank_candidates]
+        fused_results = self._reciprocal_rank_fusion(bm25_results, colbert_results, k=_knob(self.config, "rrf_k"))
+        candidates = fused_results[:_knob(self.config, "rerank_candidates")]
         t['fusion'] = time.time() - start
         self._log(f"   • Fusion: {t['fusion']:.3f}s")
 
@@ -469,7 +521,7 @@ class HybridRetriever:
         k_final = cfg.final_top_k if top_k_final is None else top_k_final
         col_ids, _ = retr.search_embeddings(query_embeddings, cfg.colbert_top_k)
         a = bm25_ids.to(retr.device, torch.int32).contiguous()
-        fused_ids, _, _ = _lib.rrf_fuse(a, col_ids.contiguous(), cfg.rrf_k, cfg.rerank_candidates)
+        fused_ids, _, _ = _lib.rrf_fuse(a, col_ids.contiguous(), _knob(cfg, "rrf_k"), _knob(cfg, "rerank_candidates"))
         base = retr.store.doc_id_base
         local = torch.where(fused_ids >= 0, fused_ids - base, fused_ids)
         _, doc_ids, scores = retr.rerank_ids(query_embeddings, local, k=k_final)

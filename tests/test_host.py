@@ -160,3 +160,43 @@ def test_class_surface_matches_reference_signatures(golden_dir):
             for extra in mine[len(params):]:
                 assert extra.default is not inspect.Parameter.empty or extra.kind in (
                     inspect.Parameter.VAR_POSITIONAL, inspect.Parameter.VAR_KEYWORD), f"{cls}.{meth}: extra required {extra.name}"
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/local_rag_complete.py"), reason="reference not mounted")
+def test_install_into_the_unmodified_reference_module():
+    """hrc.install(module) rebinds JinaColBERTRetriever inside the loaded reference module: the reference's OWN
+    DualIndexer (:841-844) then constructs this implementation, with the reference's own RAGConfig (device "cpu")."""
+    import importlib.util
+    import sys
+    from unittest.mock import MagicMock
+    saved = {}
+    for name in ["pymupdf4llm", "fitz", "bm25s", "sentence_transformers", "sqlalchemy", "sqlalchemy.ext",
+                 "sqlalchemy.ext.declarative", "sqlalchemy.orm"]:
+        saved[name] = sys.modules.get(name)
+        sys.modules[name] = MagicMock()
+    try:
+        spec = importlib.util.spec_from_file_location("local_rag_complete_under_test", "/root/reference/local_rag_complete.py")
+        lrc = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(lrc)
+        ref_retriever = lrc.JinaColBERTRetriever
+        hrc.install(lrc)
+        assert lrc.JinaColBERTRetriever is hrc.JinaColBERTRetriever and ref_retriever is not hrc.JinaColBERTRetriever
+        cfg = lrc.RAGConfig()                                # the reference's own dataclass
+        idx = lrc.DualIndexer(cfg)                           # the reference's own class, :841-844
+        assert isinstance(idx.colbert_retriever, hrc.JinaColBERTRetriever)
+        assert idx.colbert_retriever.config is cfg and idx.colbert_retriever.device.type == "cuda"
+        assert not hasattr(cfg, "score_mode")               # the reference's config lacks the additive knobs ...
+        assert idx.colbert_retriever._literal() is False    # ... which then take their defaults
+        assert idx.colbert_retriever._finish_scores(torch.ones(2), 32).tolist() == [1.0, 1.0]
+        h = lrc.HybridRetriever(cfg, idx, None)              # the reference's own class, :889-892
+        assert h.indexer.colbert_retriever is idx.colbert_retriever
+        with pytest.raises(ValueError):
+            hrc.install(lrc, ("NoSuchClass",))
+        hrc.install(lrc, ("JinaColBERTRetriever", "DualIndexer", "HybridRetriever"))
+        assert lrc.HybridRetriever is hrc.HybridRetriever
+    finally:
+        for name, mod in saved.items():
+            if mod is None:
+                sys.modules.pop(name, None)
+            else:
+                sys.modules[name] = mod
