@@ -88,10 +88,22 @@ def time_cpu(n_docs, min_seconds=10.0, max_seconds=30.0):
         el = time.perf_counter() - t0
         if el >= min_seconds or (passes >= 2 and el >= max_seconds):
             break
+    # the reference's function EXACTLY as coded (:821-829, mean-pool cosine — not MaxSim) on the same sample, for the record
+    from oracle import maxsim_oracle as o
+    dense = tok.view(-1, DOC_LEN, 128)
+    o.literal_reference(q[0], dense)
+    t1 = time.perf_counter()
+    lit_passes = 0
+    while time.perf_counter() - t1 < 2.0:
+        torch.topk(o.literal_reference(q[0], dense), k=min(K, n_docs))
+        lit_passes += 1
+    lit_el = time.perf_counter() - t1
     return {"value": n_docs * passes / el, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{passes} passes over {n_docs} docs x {DOC_LEN} tokens (fp32, torch CPU oracle: "
                       f"einsum -> max -> sum -> torch.topk), {el:.1f} s",
-            "tokens_per_s": n_docs * passes * DOC_LEN / el}
+            "tokens_per_s": n_docs * passes * DOC_LEN / el,
+            "reference_literal_docs_per_s": n_docs * lit_passes / lit_el,
+            "reference_literal_note": "local_rag_complete.py:821-829 as coded (mean-pool cosine, not MaxSim) + torch.topk, same sample"}
 
 
 def run_reference(args):
