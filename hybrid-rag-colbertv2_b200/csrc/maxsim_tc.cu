@@ -4,28 +4,33 @@
 // Data layout in HBM
 //   tokens  : bf16 [total_tokens][128], packed, padding-free           (TMA map: 2-D, 128B swizzle)
 //   offsets : int64 [n_docs + 1] CSR document boundaries
-//   queries : bf16 [n_queries][lq][128], lq <= 32
+//   queries : bf16 [n_queries][lq][128]; 32 query tokens per A-tile slot, a longer query (lq <= 256) is scored as
+//             ceil(lq / 32) "virtual queries" whose partial scores are summed in slot order (sum_slots_kernel)
 //
-// One CTA = one contiguous run of whole documents ("segment") x one group of 4*MT queries.
+// One CTA = one contiguous run of whole documents ("segment") x one group of 4*MT (virtual) queries.
 //   warp 0      : TMA producer  — streams TN-token x 128-dim tiles through a shared-memory ring
-//   warp 1      : MMA issuer    — per tile and M-tile: 8 x tcgen05.mma (M=128, N=TN, K=16), accumulator =
-//                                 TN TMEM columns; owns TMEM alloc/dealloc
+//   warp 1      : MMA issuer    — per tile and M-tile: 8 x tcgen05.mma (M=128 [256 over a CTA pair], N=TN, K=16),
+//                                 accumulator = TN TMEM columns; owns TMEM alloc/dealloc
 //   warps 2..   : epilogue      — a warp owns TMEM lanes 32*(w%4).. = one query slot: thread i holds query
-//                                 token i, so the max over a document's tokens is a per-thread reduction
-//                                 over TMEM columns, document boundaries are warp-uniform, and a document's
-//                                 score is one warp_sum.  Every warp owns WHOLE documents (no combine).
+//                                 token i, so the max over a document's tokens is a per-thread FMNMX3 tree over
+//                                 32 TMEM columns (loads aligned to the DOCUMENT, not the tile: no masking for
+//                                 >= 32-token pieces), document boundaries are warp-uniform, and a document's
+//                                 score is one shuffle butterfly, emitted after the tile has been released.
+//                                 Every warp owns WHOLE documents (no cross-warp combine).
 // MMA orientation: A = queries (M = 4 slots x 32 tokens), B = document tokens (N):
 // D[row = query token][col = doc token].
 //
-// Two instantiations:
-//   <MT=1, TN=128, TS=false>  HBM-bound (<= 4 queries): A and B from shared memory (SS), 6-stage ring,
-//        4 accumulator stages; with fewer than 4 queries the query is REPLICATED over the free slots so
-//        all four epilogue warps work (each takes every rep-th document).
-//   <MT=2, TN=128, TS=false>  tensor-bound (batched, 8 queries per CTA pass): 8 epilogue warps (two per lane
-//        group, splitting documents), 2 x 2 accumulators.  This is the default batched kernel.
-//   <MT=2, TN=96,  TS=true>   alternative (env HRC_TC_TS=1): the query tiles live in TMEM (A operand from
-//        TMEM, written with tcgen05.st), TMEM = 128 (Q) + 2 x 2 x 96 (acc).  Halves the operand traffic from
-//        shared memory, but measured slower on C3 (1069 vs 1123 TFLOP/s), so it is not the default.
+// Instantiations <MT, TN, TS, ZP, CG, EPI> (DESIGN.md §4.1 has the measurements behind each choice):
+//   <1,128,SS,ZP=1>       HBM-bound (<= 4 queries) and candidate (rerank) mode: the unused rows of the A tile are
+//                         zero, the 4 epilogue warps are stacked on the used lane groups, 6-stage smem ring,
+//                         4 accumulator stages, one tcgen05.commit per tile.            [default]
+//   <1,128,SS,ZP=2>       M=64 MMA for <= 2 queries (env HRC_TC_M64=1); <1,128,SS,ZP=0> replicated query (HRC_TC_ZP=0)
+//   <2,128,SS,CG=2>       tensor-bound, batched: CTA PAIR (cta_group::2, cluster of 2), one M=256 MMA per K slice,
+//                         each CTA stages half of every document tile; 8 epilogue warps per CTA (two per lane
+//                         group, alternating documents), 2 x 2 accumulators.            [default from 9 queries]
+//   <2,128,SS>            single-CTA batched kernel (5..8 queries, an odd last query group, or HRC_TC_PAIR=0)
+//   <2,128,SS,CG=2,EPI=1..3>  other organisations of the batched epilogue (env HRC_TC_EPI), parity-tested, slower
+//   <2,96,TS>             query tiles in TMEM as the A operand (env HRC_TC_TS=1), parity-tested, slower
 //
 // Reference semantics: local_rag_complete.py:807-812 (docstring), :813-817 (shapes), summed over
 // query tokens per BASELINE.json north_star.  Algorithmic traffic: 256 B per document token.

@@ -8,6 +8,10 @@
  *                          tokens"), summed over query tokens (BASELINE.json north_star); fp32, index order.
  *                          PARITY UNPINNED BY THE REFERENCE (its body :819-829 is a mean-pool cosine; it
  *                          ships no tests) — cross-checked against the Python oracle and the golden fixtures.
+ *   oracle_literal_scores  the BODY of _maxsim_score as coded, :821-829: cosine of the mean-pooled token vectors
+ *                          (fp32 accumulation in index order; torch reduces in a different order, so this agrees
+ *                          with the reference's vectors to ~1e-6, not bit for bit).  PINNED on
+ *                          tests/golden/literal_maxsim.npz and literal_bf16.npz.
  *   oracle_rrf             _reciprocal_rank_fusion :960-978: dict in insertion order, fp64 `0 + 1/(k+rank)`
  *                          accumulated list a then list b, stable descending sort.  PINNED on tests/golden/rrf.json.
  *   oracle_topk_keys       torch.topk :767 / argsort :789 expressed on the 64-bit (score, id) keys of
@@ -39,6 +43,33 @@ void oracle_maxsim_scores(const float* q, int n_queries, int lq, const float* to
       }
       out[(int64_t)b * n_docs + d] = empty ? -INFINITY : total;
     }
+  }
+}
+
+/* the reference's function as coded (:821-829); dense documents [n_docs][ld][128], one query [lq][128] */
+void oracle_literal_scores(const float* q, int lq, const float* docs, int64_t n_docs, int ld, float* out) {
+  float qv[DIM];
+  float qn = 0.0f;
+  for (int c = 0; c < DIM; ++c) {
+    float a = 0.0f;
+    for (int i = 0; i < lq; ++i) a += q[(int64_t)i * DIM + c];
+    qv[c] = a / (float)lq;                                      /* :821 */
+    qn += qv[c] * qv[c];
+  }
+  qn = sqrtf(qn);
+  if (qn < 1e-8f) qn = 1e-8f;                                   /* cosine_similarity eps */
+  for (int64_t d = 0; d < n_docs; ++d) {
+    float dot = 0.0f, dn = 0.0f;
+    for (int c = 0; c < DIM; ++c) {
+      float a = 0.0f;
+      for (int t = 0; t < ld; ++t) a += docs[((int64_t)d * ld + t) * DIM + c];
+      a /= (float)ld;                                           /* :822 */
+      dot += a * qv[c];
+      dn += a * a;
+    }
+    dn = sqrtf(dn);
+    if (dn < 1e-8f) dn = 1e-8f;
+    out[d] = dot / (dn * qn);                                   /* :825-829 */
   }
 }
 

@@ -41,6 +41,17 @@ def test_c_maxsim_matches_python_oracle(clib):
     np.testing.assert_allclose(out[fin], exp[fin], rtol=1e-5, atol=1e-6)
 
 
+def test_c_literal_matches_reference_outputs(clib, golden_dir):
+    """The C restatement of what the reference's `_maxsim_score` literally computes, against the vectors the
+    unmodified reference produced (both fixtures)."""
+    for name in ("literal_maxsim.npz", "literal_bf16.npz"):
+        z = np.load(os.path.join(golden_dir, name))
+        q, D = np.ascontiguousarray(z["q"]), np.ascontiguousarray(z["D"])
+        out = np.empty(D.shape[0], dtype=np.float32)
+        clib.oracle_literal_scores(_p(q), q.shape[0], _p(D), ctypes.c_int64(D.shape[0]), D.shape[1], _p(out))
+        np.testing.assert_allclose(out, z["out_q_D"], rtol=0, atol=2e-6)
+
+
 def test_c_rrf_bit_equal_to_reference_fixtures(clib, golden_dir):
     for c in json.load(open(os.path.join(golden_dir, "rrf.json"))):
         a = np.asarray(c["a"], dtype=np.int32)
