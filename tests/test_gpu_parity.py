@@ -543,3 +543,35 @@ def test_full_size_properties_c3(cuda_dev):
     # (5) shard invariance: a 3-way document split gives bit-identical scores
     parts = [L.maxsim_scores(s.tokens, s.offsets, q) for s in (store.shard(rk, 3) for rk in range(3))]
     assert torch.equal(torch.cat(parts, 1), scores)
+
+
+def test_randomised_shapes_against_oracle(cuda_dev):
+    """Seeded fuzz through the C ABI: document-length mixes (empty, 1-3 tokens, around the 32-column chunk and the
+    128-token tile, several tiles long), query counts that hit every kernel (1-4: HBM-bound variants, 5-8: single-CTA
+    batched, 9+: CTA pairs with and without an odd group) and query lengths on both sides of the 32-token slot."""
+    L = _lib()
+    rng = np.random.default_rng(20260118)
+    modes = {
+        "tiny": lambda n: rng.integers(0, 4, n),
+        "chunk": lambda n: rng.integers(28, 37, n),
+        "tile": lambda n: rng.integers(120, 137, n),
+        "mixed": lambda n: np.where(rng.random(n) < 0.3, rng.integers(0, 6, n), rng.integers(1, 300, n)),
+        "long": lambda n: rng.integers(200, 900, n),
+    }
+    nqs = [1, 2, 3, 4, 5, 8, 9, 16, 17, 24, 33]
+    lqs = [1, 7, 16, 31, 32, 33, 64, 100]
+    for case in range(44):
+        mode = list(modes)[case % len(modes)]
+        n_docs = int(rng.integers(1, 260 if mode != "long" else 40))
+        lens = modes[mode](n_docs).astype(np.int64)
+        if lens.sum() == 0:
+            lens[0] = 5
+        nq, lq = nqs[case % len(nqs)], lqs[(case * 3) % len(lqs)]
+        q, tok, off = _case(1000 + case, 0, 0, 0, nq, lq, lens=lens)
+        exp = o.maxsim_scores(q.float(), tok.float(), off)
+        got = L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev), path=L.PATH_TC)
+        torch.cuda.synchronize()
+        _assert_scores(got, exp, f"case {case}: {mode} docs={n_docs} nq={nq} lq={lq}")
+        if case % 4 == 0:
+            simt = L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev), path=L.PATH_SIMT)
+            _assert_scores(simt, exp, f"case {case} simt")
