@@ -38,6 +38,10 @@ SYMBOLS = {
     "hrc_search_host": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int,
                                    _c.c_int, _c.c_int32, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_int,
                                    _c.c_void_p]),
+    "hrc_hybrid_retrieve_workspace_bytes": (_c.c_size_t, [_c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    "hrc_hybrid_retrieve": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int,
+                                       _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int32,
+                                       _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "hrc_rerank": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_void_p,
                               _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                               _c.c_void_p, _c.c_int, _c.c_void_p]),
@@ -252,6 +256,42 @@ class HostSearch:
             _check(rc, "hrc_search_host")
             stream.synchronize()
         return self.ids, self.scores
+
+
+class HybridBuffers:
+    """Reusable device scratch for `hybrid_retrieve`."""
+
+    def __init__(self):
+        self.key = None
+
+    def ensure(self, dev, n_docs: int, nq: int, colbert_k: int, n_cand: int, final_k: int):
+        key = (str(dev), n_docs, nq, colbert_k, n_cand, final_k)
+        if self.key != key:
+            self.ws_bytes = int(load().hrc_hybrid_retrieve_workspace_bytes(n_docs, nq, colbert_k, n_cand, final_k))
+            self.ws = torch.empty(max(self.ws_bytes, 256), dtype=torch.uint8, device=dev)
+            self.key = key
+        return self
+
+
+def hybrid_retrieve(tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.Tensor, bm25_ids: torch.Tensor, *,
+                    colbert_k: int, rrf_k: int, n_candidates: int, final_k: int, id_base: int = 0,
+                    path: int = PATH_AUTO, buffers: Optional[HybridBuffers] = None):
+    """ColBERT top-k -> RRF with the BM25 lists -> rerank of the stored candidates, one C call (hrc_hybrid_retrieve).
+    Returns (global doc ids int32 [nq, final_k], MaxSim scores fp32 [nq, final_k])."""
+    dev = _require_cuda(tokens, offsets, queries, bm25_ids)
+    assert tokens.dtype == torch.bfloat16 and queries.dtype == torch.bfloat16 and offsets.dtype == torch.int64
+    assert bm25_ids.dtype == torch.int32 and bm25_ids.dim() == 2 and bm25_ids.shape[0] == queries.shape[0]
+    n_docs = offsets.numel() - 1
+    nq, lq = int(queries.shape[0]), int(queries.shape[1])
+    buf = (buffers or HybridBuffers()).ensure(dev, n_docs, nq, colbert_k, n_candidates, final_k)
+    ids = torch.empty((nq, final_k), dtype=torch.int32, device=dev)
+    scores = torch.empty((nq, final_k), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = load().hrc_hybrid_retrieve(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), _ptr(queries), nq, lq,
+                                        _ptr(bm25_ids), int(bm25_ids.shape[1]), colbert_k, rrf_k, n_candidates, final_k,
+                                        id_base, _ptr(buf.ws), buf.ws_bytes, _ptr(ids), _ptr(scores), path, _stream(dev))
+    _check(rc, "hrc_hybrid_retrieve")
+    return ids, scores
 
 
 def rerank(tokens: torch.Tensor, offsets: torch.Tensor, cand_ids: torch.Tensor, queries: torch.Tensor, k: int, *,

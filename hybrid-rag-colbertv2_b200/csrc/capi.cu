@@ -79,6 +79,33 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* 
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
+// ids[i] += delta where ids[i] >= 0 (global <-> shard-local document ids; negative = absent stays absent)
+__global__ void shift_ids_kernel(int32_t* ids, int64_t n, int32_t delta) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n && ids[i] >= 0) ids[i] += delta;
+}
+
+struct HybridLayout {
+  size_t scores, topk, keys, col_ids, fused_ids, fused_scores, counts, cand_scores, rr_keys, pos, total, topk_bytes;
+};
+static HybridLayout hybrid_layout(int64_t n_docs, int nq, int colbert_k, int n_cand, int final_k) {
+  HybridLayout L;
+  size_t o = 0;
+  L.scores = o; o += align256(size_t(nq) * size_t(n_docs) * sizeof(float));
+  L.topk_bytes = topk_workspace_bytes(n_docs, nq, colbert_k);
+  L.topk = o; o += align256(L.topk_bytes);
+  L.keys = o; o += align256(size_t(nq) * colbert_k * sizeof(uint64_t));
+  L.col_ids = o; o += align256(size_t(nq) * colbert_k * sizeof(int32_t));
+  L.fused_ids = o; o += align256(size_t(nq) * n_cand * sizeof(int32_t));
+  L.fused_scores = o; o += align256(size_t(nq) * n_cand * sizeof(double));
+  L.counts = o; o += align256(size_t(nq) * sizeof(int32_t));
+  L.cand_scores = o; o += align256(size_t(nq) * n_cand * sizeof(float));
+  L.rr_keys = o; o += align256(size_t(nq) * final_k * sizeof(uint64_t));
+  L.pos = o; o += align256(size_t(nq) * final_k * sizeof(int32_t));
+  L.total = o;
+  return L;
+}
+
 struct HostSearchLayout {
   size_t q32, q16, scores, topk, keys, ids, out_scores, total, topk_bytes;
 };
@@ -185,6 +212,57 @@ int hrc_search_host(const void* d_tokens, const int64_t* d_offsets, int64_t n_do
     return rc;
   HRC_CHECK_CUDA(cudaMemcpyAsync(h_ids_out, d_ids, size_t(n_queries) * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   HRC_CHECK_CUDA(cudaMemcpyAsync(h_scores_out, d_sc, size_t(n_queries) * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+size_t hrc_hybrid_retrieve_workspace_bytes(int64_t n_docs, int n_queries, int colbert_k, int n_candidates, int final_k) {
+  if (n_docs < 0 || n_queries < 0 || colbert_k < 0 || n_candidates < 0 || final_k < 0) return 0;
+  return hybrid_layout(n_docs, n_queries, colbert_k, n_candidates, final_k).total;
+}
+
+int hrc_hybrid_retrieve(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                        const void* d_queries, int n_queries, int lq, const int32_t* d_bm25_ids, int n_bm25, int colbert_k,
+                        int rrf_k, int n_candidates, int final_k, int32_t id_base, void* d_workspace,
+                        size_t workspace_bytes, int32_t* d_ids_out, float* d_scores_out, int path, void* stream) {
+  if (int rc = check_device()) return rc;
+  HRC_REQUIRE(n_queries >= 0 && n_bm25 >= 0 && colbert_k >= 1 && colbert_k <= n_docs && n_candidates >= 1 &&
+                  final_k >= 1 && final_k <= n_candidates,
+              "hybrid_retrieve: need 1 <= colbert_k <= n_docs and 1 <= final_k <= n_candidates");
+  if (n_queries == 0) return 0;
+  HRC_REQUIRE(d_workspace != nullptr && d_ids_out != nullptr && d_scores_out != nullptr && (n_bm25 == 0 || d_bm25_ids != nullptr),
+              "hybrid_retrieve: null buffer");
+  const HybridLayout L = hybrid_layout(n_docs, n_queries, colbert_k, n_candidates, final_k);
+  HRC_REQUIRE(workspace_bytes >= L.total, "hybrid_retrieve: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+  HRC_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, "hybrid_retrieve: workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+  int32_t* col_ids = reinterpret_cast<int32_t*>(ws + L.col_ids);
+  int32_t* fused = reinterpret_cast<int32_t*>(ws + L.fused_ids);
+  // stage 2 of retrieve (:908-911): ColBERT first stage over the whole store, GLOBAL ids
+  if (int rc = hrc_search(d_tokens, d_offsets, n_docs, total_tokens, d_queries, n_queries, lq, colbert_k, id_base,
+                          reinterpret_cast<float*>(ws + L.scores), ws + L.topk, L.topk_bytes,
+                          reinterpret_cast<uint64_t*>(ws + L.keys), col_ids, nullptr, path, stream))
+    return rc;
+  // stage 3 (:914-916): RRF of the BM25 list with the ColBERT list, top n_candidates
+  if (int rc = launch_rrf(d_bm25_ids, n_bm25, col_ids, colbert_k, n_queries, rrf_k, n_candidates, fused,
+                          reinterpret_cast<double*>(ws + L.fused_scores), reinterpret_cast<int32_t*>(ws + L.counts), st))
+    return rc;
+  const int64_t n_fused = int64_t(n_queries) * n_candidates;
+  if (id_base != 0) {   // candidates are looked up by shard-local id
+    shift_ids_kernel<<<unsigned((n_fused + 255) / 256), 256, 0, st>>>(fused, n_fused, -id_base);
+    count_launch();
+  }
+  // stage 5 (:926-929): rerank the candidates' STORED token embeddings, sorted top final_k
+  if (int rc = hrc_rerank(d_tokens, d_offsets, n_docs, total_tokens, fused, n_candidates, d_queries, n_queries, lq, final_k,
+                          reinterpret_cast<float*>(ws + L.cand_scores), reinterpret_cast<uint64_t*>(ws + L.rr_keys),
+                          reinterpret_cast<int32_t*>(ws + L.pos), d_ids_out, d_scores_out, path, stream))
+    return rc;
+  if (id_base != 0) {
+    const int64_t n_out = int64_t(n_queries) * final_k;
+    shift_ids_kernel<<<unsigned((n_out + 255) / 256), 256, 0, st>>>(d_ids_out, n_out, id_base);
+    count_launch();
+  }
+  HRC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -394,6 +394,7 @@ class HybridRetriever:
         self._chunk_fetcher = chunk_fetcher
         self.verbose = verbose
         self.last_timings: Dict[str, float] = {}
+        self._hybrid_buffers = _lib.HybridBuffers()
 
     def _log(self, msg: str) -> None:
         if self.verbose:
@@ -518,10 +519,27 @@ class HybridRetriever:
         """
         cfg = self.config
         retr = self.indexer.colbert_retriever
+        retr._require_store()
         k_final = cfg.final_top_k if top_k_final is None else top_k_final
-        col_ids, _ = retr.search_embeddings(query_embeddings, cfg.colbert_top_k)
+        n_cand = _knob(cfg, "rerank_candidates")
         a = bm25_ids.to(retr.device, torch.int32).contiguous()
-        fused_ids, _, _ = _lib.rrf_fuse(a, col_ids.contiguous(), _knob(cfg, "rrf_k"), _knob(cfg, "rerank_candidates"))
+        colbert_k = min(int(cfg.colbert_top_k), retr.store.n_docs)
+        if retr._literal() or k_final > n_cand or colbert_k < 1:
+            return self._retrieve_batch_staged(query_embeddings, a, k_final)
+        q = retr._prep_queries(query_embeddings)
+        ids, scores = _lib.hybrid_retrieve(retr.store.tokens, retr.store.offsets, q, a, colbert_k=colbert_k,
+                                           rrf_k=_knob(cfg, "rrf_k"), n_candidates=n_cand, final_k=int(k_final),
+                                           id_base=retr.store.doc_id_base, path=_knob(cfg, "maxsim_path"),
+                                           buffers=self._hybrid_buffers)
+        return ids, retr._finish_scores(scores, q.shape[1])
+
+    def _retrieve_batch_staged(self, query_embeddings: torch.Tensor, bm25_ids: torch.Tensor, k_final: int
+                               ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The same pipeline as separate calls (used for score_mode="reference_literal" and as the cross-check)."""
+        cfg = self.config
+        retr = self.indexer.colbert_retriever
+        col_ids, _ = retr.search_embeddings(query_embeddings, cfg.colbert_top_k)
+        fused_ids, _, _ = _lib.rrf_fuse(bm25_ids, col_ids.contiguous(), _knob(cfg, "rrf_k"), _knob(cfg, "rerank_candidates"))
         base = retr.store.doc_id_base
         local = torch.where(fused_ids >= 0, fused_ids - base, fused_ids)
         _, doc_ids, scores = retr.rerank_ids(query_embeddings, local, k=k_final)

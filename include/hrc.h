@@ -129,6 +129,24 @@ int hrc_rerank(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, i
                float* d_scores_ws, uint64_t* d_keys_ws, int32_t* d_pos_out, int32_t* d_ids_out,
                float* d_scores_out, int path, void* stream);
 
+/*
+ * The device part of HybridRetriever.retrieve (local_rag_complete.py:894-935) in one call, for a batch of queries:
+ * ColBERT first stage over the whole store (top colbert_k, :908-911) -> reciprocal-rank fusion with the given BM25
+ * lists (:914-916, bit-compatible fp64, top n_candidates) -> rerank of the candidates' STORED token embeddings
+ * (:926-929, sorted top final_k).  Nothing returns to the host in between.
+ *   d_bm25_ids   : int32 [n_queries][n_bm25] ranked GLOBAL document ids as bm25s.retrieve returns them (:945-949), < 0 = absent
+ *   id_base      : global id of this store's first document (document-sharded stores)
+ *   d_workspace  : hrc_hybrid_retrieve_workspace_bytes(...) bytes of device scratch, 256-B aligned
+ *   d_ids_out    : int32 [n_queries][final_k] GLOBAL ids, best first (-1 = fewer candidates than final_k)
+ *   d_scores_out : fp32  [n_queries][final_k] MaxSim scores
+ * Requires 1 <= colbert_k <= n_docs, 1 <= final_k <= n_candidates <= 8192, n_bm25 + colbert_k <= 4096.
+ */
+size_t hrc_hybrid_retrieve_workspace_bytes(int64_t n_docs, int n_queries, int colbert_k, int n_candidates, int final_k);
+int hrc_hybrid_retrieve(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                        const void* d_queries, int n_queries, int lq, const int32_t* d_bm25_ids, int n_bm25,
+                        int colbert_k, int rrf_k, int n_candidates, int final_k, int32_t id_base, void* d_workspace,
+                        size_t workspace_bytes, int32_t* d_ids_out, float* d_scores_out, int path, void* stream);
+
 /* Bytes of scratch hrc_topk needs for these sizes. */
 size_t hrc_topk_workspace_bytes(int64_t n, int n_rows, int k);
 

@@ -451,6 +451,32 @@ def test_hybrid_retrieve_matches_stagewise_oracle(cuda_dev, tmp_path):
     assert ids[0].tolist() == [x["chunk_id"] for x in out]
 
 
+def test_fused_hybrid_retrieve_equals_staged_pipeline(cuda_dev):
+    """hrc_hybrid_retrieve (search -> RRF -> rerank in one C call) == the staged calls, bit for bit, also on a
+    document shard with a non-zero id base."""
+    import hybrid_rag_colbertv2_b200 as hrc
+    from hybrid_rag_colbertv2_b200.synth import plant, synth_queries, synth_store
+    full = synth_store(30_000, 16, 200, seed=31, device=cuda_dev)
+    q = synth_queries(5, 32, device=cuda_dev)
+    plant(full, q, n_planted=40)
+    g = torch.Generator().manual_seed(6)
+    for store in (full, full.shard(1, 3)):
+        cfg = hrc.RAGConfig(colbert_top_k=100, rerank_candidates=50, final_top_k=10)
+        idx = hrc.DualIndexer(cfg)
+        idx.colbert_retriever.store = store
+        h = hrc.HybridRetriever(cfg, idx, None, verbose=False)
+        lo, n = store.doc_id_base, store.n_docs
+        bm25 = (torch.randint(0, n, (5, 100), generator=g, dtype=torch.int32) + lo).to(cuda_dev)
+        col_ids, _ = idx.colbert_retriever.search_embeddings(q, 100)
+        bm25[:, :20] = col_ids[:, torch.randperm(100, generator=g)[:20].to(cuda_dev)]   # overlap with the ColBERT list
+        bm25[2, 90:] = -1
+        ids_f, sc_f = h.retrieve_batch(q, bm25)
+        ids_s, sc_s = h._retrieve_batch_staged(q, bm25, 10)
+        assert torch.equal(ids_f, ids_s) and torch.equal(sc_f, sc_s)
+        assert bool(((ids_f >= lo) & (ids_f < lo + n)).all())
+        assert bool((sc_f[:, :-1] >= sc_f[:, 1:]).all())
+
+
 def test_full_size_properties_c2(cuda_dev):
     """BASELINE config C2 at full size (1M docs x 128 tokens, 32.8 GB): size-independent checks."""
     import hybrid_rag_colbertv2_b200 as hrc
