@@ -200,3 +200,24 @@ def test_install_into_the_unmodified_reference_module():
                 sys.modules.pop(name, None)
             else:
                 sys.modules[name] = mod
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints ONE JSON line with the contract's
+    keys; under torchrun only rank 0 prints."""
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--cpu-sample-docs", "300"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, check=True).stdout.strip().splitlines()
+    lines = [l for l in out if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "maxsim_docs_scored_per_sec" and d["unit"] == "docs/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "docs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    quiet = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
