@@ -14,6 +14,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA sm_100 (B200) device; run with -m gpu on the GPU box")
 
 
+def pytest_sessionstart(session):
+    """The in-tree libraries are build artefacts (git-ignored): compile them if a fresh checkout has none yet
+    (nvcc cross-compiles sm_100a without a GPU; same commands as __graft_entry__.build())."""
+    import subprocess
+    lib = os.path.join(ROOT, "hybrid-rag-colbertv2_b200", "libhrc.so")
+    if not os.path.exists(lib):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "hybrid-rag-colbertv2_b200", "csrc"), "-j", "8"], check=True,
+                       stdout=subprocess.DEVNULL)
+    if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
