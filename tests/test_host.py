@@ -221,3 +221,50 @@ def test_bench_reference_arm_prints_the_contract_line():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     quiet = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert quiet.returncode == 0 and quiet.stdout.strip() == ""
+
+
+class _WordTokenizer:
+    """Minimal tokenizer with the transformers call signature (no vocabulary files exist offline)."""
+    pad_token_id, cls_token_id, sep_token_id, mask_token_id = 0, 1, 2, 3
+
+    def _ids(self, text, add_special_tokens=True):
+        words = []
+        for w in text.lower().replace(",", " , ").replace(".", " . ").split():
+            words.append(4 + (int.from_bytes(w.encode(), "little") % 900))
+        return ([self.cls_token_id] + words + [self.sep_token_id]) if add_special_tokens else words
+
+    def __call__(self, text, add_special_tokens=True, truncation=False, max_length=None, padding=False, return_tensors=None):
+        single = isinstance(text, str)
+        rows = [self._ids(t, add_special_tokens) for t in ([text] if single else text)]
+        if truncation and max_length:
+            rows = [r[:max_length] for r in rows]
+        if return_tensors is None:
+            return {"input_ids": rows[0] if single else rows}
+        width = max(len(r) for r in rows)
+        ids = torch.tensor([r + [self.pad_token_id] * (width - len(r)) for r in rows])
+        mask = torch.tensor([[1] * len(r) + [0] * (width - len(r)) for r in rows])
+        return {"input_ids": ids, "attention_mask": mask}
+
+
+def test_colbert_encoder_shapes_masking_and_query_augmentation():
+    """The ColBERT-style encoder hook with a small randomly initialised backbone on the CPU:
+    ragged, padding-free, punctuation-free document embeddings; [MASK]-augmented 32-token queries; unit-norm rows;
+    and the output feeds the packed store directly."""
+    from transformers import BertConfig, BertModel
+    from hybrid_rag_colbertv2_b200.encoder import ColBERTEncoder
+    torch.manual_seed(0)
+    backbone = BertModel(BertConfig(vocab_size=1000, hidden_size=64, num_hidden_layers=2, num_attention_heads=4,
+                                    intermediate_size=128, max_position_embeddings=600), add_pooling_layer=False)
+    enc = ColBERTEncoder(backbone, _WordTokenizer(), projection=torch.nn.Linear(64, 128, bias=False), device="cpu",
+                         batch_size=2, doc_maxlen=16)
+    q = enc.encode("what is late interaction", convert_to_tensor=True)
+    assert q.shape == (32, 128) and torch.allclose(q.norm(dim=-1), torch.ones(32), atol=1e-5)
+    docs = enc.encode(["late interaction, scored per token.", "x", "a b c d e f g h i j k l m n o p q r s t"],
+                      show_progress_bar=True, convert_to_tensor=True)
+    assert [d.shape[0] for d in docs] == [7, 3, 16]           # CLS + words + SEP, punctuation dropped, truncation at 16
+    assert all(d.shape[1] == 128 and torch.allclose(d.norm(dim=-1), torch.ones(d.shape[0]), atol=1e-5) for d in docs)
+    again = enc.encode(["x"], convert_to_tensor=True)[0]      # batch composition (padding) must not change a document
+    assert torch.allclose(again, docs[1], atol=1e-5)
+    store = PackedStore.from_ragged(docs, device="cpu")
+    assert store.n_docs == 3 and store.total_tokens == 26 and store.lengths().tolist() == [7, 3, 16]
+    assert enc.encode("x", is_query=False).shape == (3, 128)
