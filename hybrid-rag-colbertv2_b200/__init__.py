@@ -5,13 +5,14 @@ Import as `hybrid_rag_colbertv2_b200` (the repo-root shim makes the hyphenated d
 """
 from . import _lib
 from ._lib import HrcError, PATH_AUTO, PATH_SIMT, PATH_TC
+from .chunks import ChunkIdMap, SqliteChunkFetcher
 from .encoder import ColBERTEncoder, SyntheticEncoder
 from .retriever import DualIndexer, HybridRetriever, JinaColBERTRetriever, RAGConfig, install
 from .sharded import ShardedSearcher, all_gather_keys
 from .store import PackedStore, lengths_to_offsets, shard_doc_ranges
 
 __all__ = [
-    "DualIndexer", "HybridRetriever", "JinaColBERTRetriever", "RAGConfig", "PackedStore", "SyntheticEncoder", "ColBERTEncoder",
+    "DualIndexer", "HybridRetriever", "JinaColBERTRetriever", "RAGConfig", "PackedStore", "SyntheticEncoder", "ColBERTEncoder", "ChunkIdMap", "SqliteChunkFetcher",
     "ShardedSearcher", "all_gather_keys", "lengths_to_offsets", "shard_doc_ranges", "HrcError",
     "PATH_AUTO", "PATH_SIMT", "PATH_TC", "install",
 ]

@@ -268,3 +268,33 @@ def test_colbert_encoder_shapes_masking_and_query_augmentation():
     store = PackedStore.from_ragged(docs, device="cpu")
     assert store.n_docs == 3 and store.total_tokens == 26 and store.lengths().tolist() == [7, 3, 16]
     assert enc.encode("x", is_query=False).shape == (3, 128)
+
+
+def test_chunk_id_map_and_sqlite_fetcher(tmp_path):
+    """§8(f) rank 4: corpus index <-> SQLite primary key, one IN (...) query, the reference's dict shape (:986-993),
+    requested order kept, unknown ids dropped (:985)."""
+    import sqlite3
+    db = str(tmp_path / "rag_local.db")
+    con = sqlite3.connect(db)
+    con.execute("CREATE TABLE chunks (id INTEGER PRIMARY KEY, document_id INTEGER NOT NULL, chunk_index INTEGER NOT NULL, "
+                "text TEXT NOT NULL, heading_path VARCHAR(500), token_count INTEGER, has_images BOOLEAN, metadata TEXT)")
+    for i in range(10):                                    # autoincrement keys 1..10 for corpus indices 0..9
+        con.execute("INSERT INTO chunks (document_id, chunk_index, text, heading_path, token_count, has_images, metadata) "
+                    "VALUES (?, ?, ?, ?, ?, ?, ?)", (7, i, f"chunk text {i}", f"h{i}", 5, i % 2, json.dumps({"page": i}) if i % 3 else None))
+    con.commit()
+    con.close()
+    idmap = hrc.ChunkIdMap.autoincrement(10)
+    assert idmap.to_external([0, 9, 10, -1]) == [1, 10, None, None] and idmap.to_index([1, 10, 11]) == [0, 9, None]
+    fetch = hrc.SqliteChunkFetcher(db, idmap)
+    got = fetch([4, 0, 99, 7])
+    assert [c["chunk_id"] for c in got] == [4, 0, 7]                      # corpus indices, requested order, 99 dropped
+    assert got[0] == {"chunk_id": 4, "text": "chunk text 4", "document_id": 7, "heading_path": "h4", "has_images": False,
+                      "metadata": {"page": 4}}
+    assert got[1]["metadata"] == {} and got[2]["has_images"] is True
+    assert fetch([]) == []
+    with pytest.raises(ValueError):
+        hrc.ChunkIdMap([3, 3])
+    # plugs into HybridRetriever as its chunk_fetcher
+    h = hrc.HybridRetriever(hrc.RAGConfig(), hrc.DualIndexer(hrc.RAGConfig(), encoder=hrc.SyntheticEncoder()), None,
+                            chunk_fetcher=fetch, verbose=False)
+    assert [c["chunk_id"] for c in h._fetch_chunks_from_db([2, 3])] == [2, 3]
