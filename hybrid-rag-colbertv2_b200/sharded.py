@@ -7,7 +7,7 @@ hrc_topk_merge.  Keys are totally ordered, so the merged list equals the single-
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Tuple
 
 import torch
 import torch.distributed as dist

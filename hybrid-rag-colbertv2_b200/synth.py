@@ -5,7 +5,7 @@ reproduces the same global corpus.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Optional
 
 import numpy as np
 import torch
