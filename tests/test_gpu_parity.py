@@ -601,3 +601,23 @@ def test_randomised_shapes_against_oracle(cuda_dev):
         if case % 4 == 0:
             simt = L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev), path=L.PATH_SIMT)
             _assert_scores(simt, exp, f"case {case} simt")
+
+
+def test_plain_c_client_of_the_abi(cuda_dev, tmp_path):
+    """tests/c_abi/client.c: a C99 program (no Python, no torch, no C++) drives libhrc.so through include/hrc.h and
+    cross-checks the tensor-core path against the CUDA-core path and a host loop."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    libdir = os.path.join(root, "hybrid-rag-colbertv2_b200")
+    exe = str(tmp_path / "client")
+    cc = shutil.which("gcc") or shutil.which("cc")
+    assert cc is not None
+    subprocess.run([cc, "-O2", "-std=c99", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+                    os.path.join(root, "tests", "c_abi", "client.c"), "-o", exe, "-L", libdir, "-l:libhrc.so",
+                    "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm", f"-Wl,-rpath,{libdir}",
+                    f"-Wl,-rpath,{os.path.join(cuda, 'lib64')}"], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "c_abi_client ok" in out.stdout
