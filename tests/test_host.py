@@ -44,6 +44,12 @@ def test_no_cpu_fallback():
         _lib.maxsim_scores(tok, off, q)
     with pytest.raises(hrc.HrcError):
         _lib.topk(torch.zeros((1, 4)), 2)
+    with pytest.raises(hrc.HrcError):
+        _lib.meanpool_cosine_scores(tok, off, q)
+    with pytest.raises(hrc.HrcError):
+        _lib.HostSearch()(tok, off, torch.zeros((1, 32, 128)), 1)
+    with pytest.raises(hrc.HrcError):
+        _lib.hybrid_retrieve(tok, off, q, torch.zeros((1, 4), dtype=torch.int32), colbert_k=1, rrf_k=60, n_candidates=1, final_k=1)
     src = open(os.path.join(ROOT, "hybrid-rag-colbertv2_b200", "retriever.py")).read()
     for mod in ("_lib.py", "retriever.py", "store.py", "sharded.py", "synth.py", "encoder.py", "__init__.py"):
         text = open(os.path.join(ROOT, "hybrid-rag-colbertv2_b200", mod)).read()
