@@ -82,6 +82,27 @@ def main():
                               "candidate_tokens": toks, "score_kernel_us": ms_score * 1e3,
                               "rerank_ids_us": ms_full * 1e3, "docs_per_s": 50 / (ms_full * 1e-3)}), flush=True)
         r.config.maxsim_path = _lib.PATH_AUTO
+        # the reference's own CPU path for this config: dense fp32 [50, 512, 128] (padded, as its encoder returns it)
+        # scored with torch on the host — true MaxSim (oracle port, padding masked) and the function as coded
+        from oracle import maxsim_oracle as o
+        torch.set_num_threads(os.cpu_count() or 1)
+        lens = store.lengths()[cand[0].long()].cpu()
+        off = store.offsets.cpu()
+        dense = torch.zeros((50, 512, 128))
+        for j, d in enumerate(cand[0].tolist()):
+            dense[j, : int(lens[j])] = store.tokens[int(off[d]): int(off[d + 1])].float().cpu()
+        qf = q[0].float().cpu()
+
+        def cpu_time(fn, n=30):
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            return (time.perf_counter() - t0) / n * 1e6
+        us_true = cpu_time(lambda: torch.argsort(o.maxsim_dense(qf, dense, lens.tolist()), descending=True)[:10])
+        us_lit = cpu_time(lambda: torch.argsort(o.literal_reference(qf, dense), descending=True)[:10])
+        print(json.dumps({"config": "C1 on the host cores (torch CPU, dense fp32 [50,512,128])", "cores": torch.get_num_threads(),
+                          "true_maxsim_rerank_us": us_true, "reference_literal_rerank_us": us_lit}), flush=True)
         del store, r
 
     if "ragged" in which or "c3" in which:
