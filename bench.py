@@ -4,10 +4,20 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step = one full-corpus MaxSim top-100 search of one 32-token query (config C2: 1M passages x 128
-tokens per GPU, 32.8 GB bf16, far larger than the 126 MB L2, so every step streams from HBM).  With N>1
-each rank holds its own 1M-document shard of an N-million-document corpus (weak scaling, SURVEY.md
-§8(e)); a step adds the all-gather of k keys per rank and the on-device merge.
+Headline: a step = one full-corpus MaxSim top-100 search of one 32-token query (config C2: 1M passages x 128
+tokens per GPU, 32.8 GB bf16, far larger than the 126 MB L2, so every step streams from HBM).  With N>1 each
+rank holds its own 1M-document shard of an N-million-document corpus (weak scaling); a step
+adds the all-gather of k keys per rank and the on-device merge.  The dominant kernel is timed INSIDE the timed
+steps (hrc_trace_*: CUDA events around its launches on its own stream), so kernel_ms <= ms_per_step by
+construction.
+
+After the headline the same process measures, outside the headline's timed region, a `secondary` object with the
+other BASELINE.json configs: `sustained` (C2 back to back for >= 2 s, clocks recorded), `read_peak` (pure-read
+bandwidth probe over the same corpus), `c4` (hybrid pipeline, 1k queries, sequential and in batches of 64), `c3`
+(256 queries x 1M ragged passages: tensor roofline), `c1` (rerank of 50 candidates: latency), `ragged` (single
+query over the C3 corpus) and, with N>1, `c5` (10M passages x 128 tokens split over the ranks), a `parity_check`
+of the merged top-k over real NCCL and the `breakdown` of a sharded step.
+
 Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the same path.
 """
 import argparse
@@ -28,6 +38,7 @@ K = 100
 LQ = 32
 DOC_LEN = 128
 SEED = 20260102
+SEED_C3 = 20260103
 
 
 def parse():
@@ -39,6 +50,10 @@ def parse():
     ap.add_argument("--docs-per-gpu", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample-docs", type=int, default=20_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="headline only (profiling runs)")
+    ap.add_argument("--secondary", default="sustained,read_peak,c4,c3,c1,ragged,c5",
+                    help="comma-separated subset of the secondary measurements")
+    ap.add_argument("--c5-global-docs", type=int, default=10_000_000)
     return ap.parse_args()
 
 
@@ -177,7 +192,7 @@ class ClockSampler:
             self._thread = threading.Thread(target=loop, daemon=True)
             self._thread.start()
             self.source = "nvml, 4 ms period"
-            return
+            return self
         except Exception:  # noqa: BLE001
             self._thread = None
         try:
@@ -188,6 +203,7 @@ class ClockSampler:
             self.source = "nvidia-smi -lms 20"
         except OSError:
             self.proc = None
+        return self
 
     def _physical_index(self):
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
@@ -223,24 +239,42 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# GPU arm
+# helpers
 # --------------------------------------------------------------------------------------------------
 def load_peaks():
+    """(hbm GB/s, bf16 TFLOP/s sustained, bf16 TFLOP/s burst, source)"""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+            d = json.load(f)
+        return (float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", 1390.6)), float(d.get("bf16_tflops", 1665.1)),
+                "measured (MEASURED_PEAKS.json: hbm_gbs = burst read+write copy; bf16_tflops_sustained = 4 s of cuBLAS)")
+    return 6650.0, 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic():
-    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+def load_profile_json(name):
+    path = os.path.join(ROOT, "profiles", name)
     if os.path.exists(path):
         with open(path) as f:
             return json.load(f)
     return None
 
 
+def pct(xs, p):
+    xs = sorted(xs)
+    if not xs:
+        return None
+    return xs[min(len(xs) - 1, max(0, int(round(p / 100.0 * (len(xs) - 1)))))]
+
+
+def summary(xs):
+    return {"median": statistics.median(xs), "p10": pct(xs, 10), "p90": pct(xs, 90), "min": min(xs), "max": max(xs),
+            "n": len(xs)} if xs else None
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -258,6 +292,8 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    hbm_peak, tf_sus, tf_burst, peak_src = load_peaks()
+    want = set() if args.no_secondary else set(args.secondary.split(","))
 
     n_global = args.docs_per_gpu * world
     store = synth_store(n_global, DOC_LEN, DOC_LEN, seed=SEED, device=dev, rank=rank, world_size=world)
@@ -290,62 +326,131 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
 
-    # ---- device-resident timing -------------------------------------------------------------------
-    for i in range(args.warmup):
-        step(i)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    launches0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    barrier()
-    t_wall1 = time.perf_counter()
-    gpu_launches = _lib.launch_count() - launches0
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    def timed_loop(fn, steps, warmup, sample_clocks=False):
+        """W untimed warm-ups, then `steps` calls bracketed by barrier + synchronize; CUDA events on the launching
+        stream, one per step boundary; the scoring kernels inside are traced.  -> dict (ms are max over ranks)."""
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        sampler = ClockSampler(local_rank).start() if (sample_clocks and rank == 0) else None
+        _lib.trace_enable(8 * steps + 8)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        launches0 = _lib.launch_count()
+        t0 = time.perf_counter()
+        ev[0].record()
+        for i in range(steps):
+            fn(i)
+            ev[i + 1].record()
+        barrier()
+        t1 = time.perf_counter()
+        launches = _lib.launch_count() - launches0
+        kern = _lib.trace_collect()
+        _lib.trace_enable(0)
+        per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+        total = max_over_ranks(ev[0].elapsed_time(ev[steps]))
+        per_launch = max(1, len(kern) // max(steps, 1))
+        kern_step = [sum(kern[i * per_launch:(i + 1) * per_launch]) for i in range(len(kern) // per_launch)]
+        out = {"ms_total": total, "ms_per_step": total / steps, "step_ms": summary(per_step),
+               "kernel_ms": summary(kern_step), "kernel_launches_per_step": per_launch,
+               "kernel_ms_mean": max_over_ranks(sum(kern) / max(steps, 1)), "launches": int(launches)}
+        if sampler is not None:
+            out["clocks"] = sampler.stop(t0, t1)
+        return out
 
-    # ---- dominant kernel alone (same stream, CUDA events) for the roofline --------------------------
-    scores_buf = torch.empty((1, store.n_docs), dtype=torch.float32, device=dev)
-    for i in range(2):
-        _lib.maxsim_scores(store.tokens, store.offsets, queries[0:1], out=scores_buf)
-    barrier()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for i in range(args.steps):
-        _lib.maxsim_scores(store.tokens, store.offsets, queries[i % n_q:i % n_q + 1], out=scores_buf)
-    k1.record()
-    barrier()
-    kernel_ms = max_over_ranks(k0.elapsed_time(k1)) / args.steps
-    # the rest of a step (radix top-k of the score row) alone, for the kernel's share of the step
-    ws = torch.empty(max(_lib.topk_workspace_bytes(store.n_docs, 1, K), 1), dtype=torch.uint8, device=dev)
-    for i in range(2):
-        _lib.topk(scores_buf, K, workspace=ws)
-    barrier()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for i in range(args.steps):
-        _lib.topk(scores_buf, K, workspace=ws)
-    s1.record()
-    barrier()
-    topk_ms = max_over_ranks(s0.elapsed_time(s1)) / args.steps
+    # ---- headline: device-resident timing, kernel traced inside the same steps ----------------------------------
+    head = timed_loop(step, args.steps, args.warmup, sample_clocks=True)
+    ms_per_step = head["ms_per_step"]
+    kernel_ms = head["kernel_ms_mean"]              # mean over the SAME timed steps (max over ranks)
 
-    # ---- end to end through the public API with host buffers ---------------------------------------
-    for i in range(args.warmup):
-        step_e2e(i)
-    barrier()
-    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    x0.record()
-    for i in range(args.steps):
-        ids_h, scores_h = step_e2e(i)
-    x1.record()
-    barrier()
-    e2e_ms_total = max_over_ranks(x0.elapsed_time(x1))
+    # ---- end to end through the public API with host buffers ----------------------------------------------------
+    e2e = timed_loop(step_e2e, args.steps, args.warmup)
+
+    secondary = {}
+    traffic = load_profile_json("ncu_traffic.json")
+
+    # ---- multi-GPU: parity of the merged top-k over real NCCL, and where a sharded step's time goes ------------
+    parity_check, breakdown = None, None
+    if world > 1:
+        parity_check = sharded_parity_check(torch, dist, _lib, retr, searcher, queries, rank, world, dev, args)
+        breakdown = sharded_breakdown(torch, dist, _lib, retr, searcher, queries, dev, max_over_ranks, barrier)
+
+    # ---- secondary: sustained C2, read peak, C4 on the C2 corpus -------------------------------------------------
+    if "sustained" in want:
+        n_sus = max(50, int(2200.0 / max(ms_per_step, 0.1)))          # >= 2 s back to back
+        sus = timed_loop(step, n_sus, 3, sample_clocks=True)
+        gbs = 256.0 * store.total_tokens / (sus["kernel_ms_mean"] * 1e-3) / 1e9
+        secondary["sustained"] = {
+            "what": f"C2 step back to back for {sus['ms_total'] / 1e3:.2f} s ({n_sus} steps), same code as the headline",
+            "ms_per_step": sus["ms_per_step"], "docs_per_s": n_global / (sus["ms_per_step"] * 1e-3),
+            "kernel_ms": sus["kernel_ms"], "kernel_ms_mean": sus["kernel_ms_mean"], "achieved_GBps": gbs,
+            "frac_hbm_copy_peak": gbs / hbm_peak, "frac_of_nominal_7.7TBps": gbs / 7700.0, "clocks": sus.get("clocks")}
+    read_peak = None
+    if "read_peak" in want:
+        out = torch.zeros(1, dtype=torch.int32, device=dev)
+        for _ in range(2):
+            _lib.read_probe(store.tokens, out)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(10):
+            _lib.read_probe(store.tokens, out)
+        r1.record()
+        barrier()
+        read_ms = max_over_ranks(r0.elapsed_time(r1)) / 10
+        read_peak = store.total_tokens * 256.0 / (read_ms * 1e-3) / 1e9
+        secondary["read_peak"] = {"what": "hrc_read_probe: 16-byte vector loads over the same 32.8 GB corpus, 10 passes",
+                                  "ms": read_ms, "GBps": read_peak,
+                                  "tma_ring_read": load_profile_json("r02_tma_ring_read.json")}
+    if "c4" in want and world == 1:
+        secondary["c4"] = bench_c4(torch, hrc, _lib, retr, dev, synth_queries)
+
+    # ---- secondary on the ragged C3 corpus (the C2 corpus is released first) -------------------------------------
+    n_docs_c2_local, tokens_c2_local = store.n_docs, store.total_tokens
+    if world == 1 and want & {"c3", "c1", "ragged"}:
+        _lib.store_release(store.tokens)
+        retr.store = None
+        del store
+        torch.cuda.empty_cache()
+        rag = synth_store(args.docs_per_gpu, 32, 512, seed=SEED_C3, device=dev)
+        retr.store = rag
+        if "c3" in want:
+            secondary["c3"] = bench_c3(torch, _lib, retr, rag, dev, synth_queries, tf_sus, tf_burst, timed_loop)
+        if "ragged" in want:
+            rg = timed_loop(lambda i: retr.search_keys(queries[i % n_q:i % n_q + 1], K), 10, 3)
+            gbs = 256.0 * rag.total_tokens / (rg["kernel_ms_mean"] * 1e-3) / 1e9
+            secondary["ragged"] = {"what": f"single query over {rag.n_docs} passages x U(32..512) tokens ({rag.total_tokens} tokens)",
+                                   "ms_per_step": rg["ms_per_step"], "kernel_ms": rg["kernel_ms"], "achieved_GBps": gbs,
+                                   "frac_hbm_copy_peak": gbs / hbm_peak, "docs_per_s": rag.n_docs / (rg["ms_per_step"] * 1e-3)}
+        if "c1" in want:
+            secondary["c1"] = bench_c1(torch, _lib, retr, rag, dev, queries)
+        _lib.store_release(rag.tokens)
+        retr.store = None
+        del rag
+        torch.cuda.empty_cache()
+
+    # ---- C5: 10M passages x 128 tokens over the ranks (needs N > 1: 41 GB per GPU at N = 8) ---------------------
+    if world > 1 and "c5" in want:
+        per_rank_gb = args.c5_global_docs / world * DOC_LEN * 256 / 1e9
+        free_b, _ = torch.cuda.mem_get_info()
+        if per_rank_gb * 1e9 < free_b + n_docs_c2_local * DOC_LEN * 256 - 8e9:
+            _lib.store_release(retr.store.tokens)
+            retr.store = None
+            store = None
+            torch.cuda.empty_cache()
+            c5 = synth_store(args.c5_global_docs, DOC_LEN, DOC_LEN, seed=SEED + 3, device=dev, rank=rank, world_size=world)
+            retr.store = c5
+            r5 = timed_loop(lambda i: searcher.search_keys(queries[i % n_q:i % n_q + 1], K), 20, 3, sample_clocks=True)
+            gbs = 256.0 * c5.total_tokens / (r5["kernel_ms_mean"] * 1e-3) / 1e9
+            pc5 = sharded_parity_check(torch, dist, _lib, retr, searcher, queries, rank, world, dev, args,
+                                       n_global=args.c5_global_docs, seed=SEED + 3)
+            secondary["c5"] = {"what": f"C5: {args.c5_global_docs} passages x {DOC_LEN} tokens "
+                                       f"({args.c5_global_docs * DOC_LEN * 256 / 1e9:.1f} GB bf16) over {world} GPUs, "
+                                       f"{c5.n_docs} per GPU; local top-{K} + NCCL all-gather + merge",
+                               "ms_per_step": r5["ms_per_step"], "docs_per_s": args.c5_global_docs / (r5["ms_per_step"] * 1e-3),
+                               "kernel_ms": r5["kernel_ms"], "per_gpu_GBps": gbs, "frac_hbm_copy_peak": gbs / hbm_peak,
+                               "frac_of_nominal_7.7TBps": gbs / 7700.0, "clocks": r5.get("clocks"), "parity_check": pc5}
+        else:
+            secondary["c5"] = {"skipped": f"{per_rank_gb:.0f} GB per GPU does not fit at N={world}"}
 
     if rank != 0:
         if world > 1:
@@ -353,37 +458,208 @@ def run_ours(args):
         return
 
     docs_per_step = n_global
-    ms_per_step = ms_total / args.steps
     value = docs_per_step / (ms_per_step * 1e-3)
-    peak, peak_src = load_peaks()
-    algo_bytes = 256.0 * store.total_tokens                        # 256 B per document token
+    algo_bytes = 256.0 * tokens_c2_local                            # 256 B per document token
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = load_traffic()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic", "config": workload_config(args, world),
         "tokens_per_s": value * DOC_LEN,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "step_ms": head["step_ms"],
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic["bytes_per_launch"] if traffic else None,
-                     "kernel": "maxsim_tc_kernel<1>", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
-                     "peak_source": peak_src, "frac_of_nominal": {"7.7TB/s_hgx": achieved / 7700.0, "8.0TB/s_dgx": achieved / 8000.0},
-                     "topk_ms": topk_ms, "kernel_share_of_step": kernel_ms / (kernel_ms + topk_ms)},
-        "e2e": {"value": docs_per_step / (e2e_ms_total / args.steps * 1e-3), "unit": UNIT,
+                     "kernel": "maxsim_tc_kernel<MT=1,ZP=1,CG=1>", "kernel_ms": kernel_ms,
+                     "kernel_ms_per_step": head["kernel_ms"], "kernel_launches_per_step": head["kernel_launches_per_step"],
+                     "kernel_timing": "CUDA events around the kernel's launches INSIDE the timed steps (hrc_trace_*), "
+                                      "mean over the same steps as ms_per_step",
+                     "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
+                     "read_peak_gbs": read_peak, "frac_vs_read_peak": (achieved / read_peak) if read_peak else None,
+                     "frac_of_nominal": {"7.7TB/s_hgx": achieved / 7700.0, "8.0TB/s_dgx": achieved / 8000.0},
+                     "kernel_share_of_step": kernel_ms / ms_per_step},
+        "e2e": {"value": docs_per_step / (e2e["ms_per_step"] * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": int(q_host[0].numel() * 4), "d2h_bytes_per_step": K * 8,
-                "ms_per_step": e2e_ms_total / args.steps,
+                "ms_per_step": e2e["ms_per_step"], "step_ms": e2e["step_ms"],
                 "api": ("JinaColBERTRetriever.search_host: pinned fp32 query -> hrc_search_host (H2D, bf16, MaxSim, top-k, "
                         "unpack, D2H) -> ids/scores on the host" if world == 1 else
                         "ShardedSearcher.search_host: pinned fp32 query -> H2D -> local search -> NCCL all-gather -> merge -> "
                         "unpack -> D2H (pinned) -> ids/scores on the host")},
-        "gpu_launches": int(gpu_launches),
-        "clocks": clocks,
+        "gpu_launches": head["launches"],
+        "clocks": head.get("clocks"),
     }
+    if parity_check is not None:
+        line["parity_check"] = parity_check
+    if breakdown is not None:
+        line["breakdown"] = breakdown
+    if secondary:
+        line["secondary"] = secondary
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = time_cpu(args.cpu_sample_docs)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# secondary configs
+# --------------------------------------------------------------------------------------------------
+def cuda_time(torch, fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def bench_c4(torch, hrc, _lib, retr, dev, synth_queries):
+    """C4: BM25 top-100 (synthesised: bm25s is unavailable offline) + ColBERT top-100 -> RRF(60) top-50 -> rerank
+    top-10, 1,000 queries over the C2 corpus — one query at a time (HBM-bound) and in batches of 64 (tensor-bound)."""
+    store = retr.store
+    cfg = hrc.RAGConfig(device=str(dev))
+    idx = hrc.DualIndexer(cfg)
+    idx.colbert_retriever = retr
+    h = hrc.HybridRetriever(cfg, idx, None, verbose=False)
+    n_queries = 1000
+    queries = synth_queries(n_queries, LQ, seed=SEED + 11, device=dev)
+    g = torch.Generator().manual_seed(4)
+    bm25 = torch.randint(0, store.n_docs, (n_queries, 100), generator=g, dtype=torch.int32).to(dev)
+    out = {"what": f"C4 hybrid pipeline x {n_queries} queries over {store.n_docs} passages x {DOC_LEN} tokens: ColBERT "
+                   "top-100 + given BM25 top-100 -> RRF(60) top-50 -> rerank top-10 (hrc_hybrid_retrieve, one C call per batch)"}
+    for batch in (1, 64):
+        def run():
+            for b in range(0, n_queries, batch):
+                h.retrieve_batch(queries[b:b + batch], bm25[b:b + batch], top_k_final=10)
+        for b in range(0, 3 * batch, batch):                    # warm-up: 3 batches
+            h.retrieve_batch(queries[b:b + batch], bm25[b:b + batch], top_k_final=10)
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        ms = cuda_time(torch, run, 1, warmup=0)
+        key = "sequential" if batch == 1 else f"batch{batch}"
+        out[key] = {"ms_per_query": ms / n_queries, "queries_per_s": n_queries / (ms * 1e-3), "queries_timed": n_queries,
+                    "launches_per_call": (_lib.launch_count() - l0) / (n_queries / batch)}
+    return out
+
+
+def bench_c3(torch, _lib, retr, rag, dev, synth_queries, tf_sus, tf_burst, timed_loop):
+    """C3: 256 queries x 32 tokens over 1M passages of 32..512 tokens — the tensor-bound config."""
+    nq = 256
+    q = synth_queries(nq, LQ, seed=SEED_C3 + 1, device=dev)
+    r = timed_loop(lambda i: retr.search_keys(q, K), 5, 3, sample_clocks=True)
+    flops = 2.0 * LQ * 128 * nq * rag.total_tokens                  # useful flops only (no M padding)
+    k_ms = r["kernel_ms_mean"]
+    tfs = flops / (k_ms * 1e-3) / 1e12
+    return {"what": f"C3: {nq} queries x {LQ} tokens over {rag.n_docs} passages x U(32..512) tokens ({rag.total_tokens} tokens, "
+                    f"{rag.total_tokens * 256 / 1e9:.1f} GB); step = MaxSim + top-{K} per query",
+            "ms_per_step": r["ms_per_step"], "kernel_ms": r["kernel_ms"], "kernel_ms_mean": k_ms,
+            "step_minus_kernel_ms": r["ms_per_step"] - k_ms, "useful_tflops": tfs,
+            "pairs_per_s": nq * rag.n_docs / (r["ms_per_step"] * 1e-3),
+            "roofline": {"bound": "tensor", "achieved": tfs, "peak": tf_sus, "unit": "TFLOP/s", "frac": tfs / tf_sus,
+                         "frac_of_burst": tfs / tf_burst, "kernel": "maxsim_tc_kernel<MT=2,ZP=0,CG=2>",
+                         "useful_flops_per_launch": flops,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (the kernel runs 0.4 s per launch, at the power cap)"},
+            "clocks": r.get("clocks"), "launches_per_step": r["launches"] / 5}
+
+
+def bench_c1(torch, _lib, retr, rag, dev, queries):
+    """C1: ColBERT rerank of 50 candidates (docs 32..512 tokens), 1 query x 32 tokens: latency of one call."""
+    g = torch.Generator().manual_seed(0)
+    cand = torch.randint(0, rag.n_docs, (1, 50), generator=g, dtype=torch.int32).to(dev)
+    q = queries[0:1]
+    toks = int(rag.lengths()[cand[0].long()].sum())
+    ws = _lib.Workspace()
+    out = {"what": f"C1: rerank of 50 candidates ({toks} tokens), 1 query x {LQ} tokens, top-10; 200 calls back to back",
+           "candidate_tokens": toks}
+    for name, path in (("tc", _lib.PATH_TC), ("simt", _lib.PATH_SIMT)):
+        us_score = cuda_time(torch, lambda: _lib.maxsim_scores_ids(rag.tokens, rag.offsets, cand, q, path=path, workspace=ws), 200) * 1e3
+        us_call = cuda_time(torch, lambda: _lib.rerank(rag.tokens, rag.offsets, cand, q, 10, path=path, workspace=ws), 200) * 1e3
+        out[name] = {"score_kernel_call_us": us_score, "rerank_call_us": us_call}
+    us_api = cuda_time(torch, lambda: retr.rerank_ids(q, cand, k=10), 200) * 1e3
+    out["rerank_ids_us"] = us_api
+    out["docs_per_s"] = 50 / (us_api * 1e-6)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# multi-GPU checks (outside every timed region)
+# --------------------------------------------------------------------------------------------------
+def sharded_parity_check(torch, dist, _lib, retr, searcher, queries, rank, world, dev, args, n_global=None, seed=SEED):
+    """Over real NCCL: (1) the merged key list equals the CPU merge (oracle.merge_keys) of every rank's local top-k,
+    bit for bit, on every rank; (2) the documents it names, regenerated from the counter-based corpus generator and
+    re-scored by the CPU oracle, carry the returned scores and are in the oracle's order.  -> "ok" or the reason."""
+    import numpy as np
+    n_global = n_global or args.docs_per_gpu * world
+    try:
+        problems = []
+        for qi in (0, 5):
+            q = queries[qi:qi + 1]
+            merged = searcher.search_keys(q, K)                               # [1, K]
+            local = retr.search_keys(q, K)
+            if local.shape[1] < K:
+                local = torch.cat([local, torch.zeros((1, K - local.shape[1]), dtype=local.dtype, device=dev)], 1)
+            allk = [torch.empty_like(local) for _ in range(world)]
+            dist.all_gather(allk, local.contiguous())
+            allm = [torch.empty_like(merged) for _ in range(world)]
+            dist.all_gather(allm, merged.contiguous())
+            if rank != 0:
+                continue
+            from oracle import maxsim_oracle as o                             # the checker, never the thing measured
+            cat = torch.cat(allk, 1).cpu().numpy().view(np.uint64)
+            want = o.merge_keys(cat, K)
+            got = merged.cpu().numpy().view(np.uint64)
+            if not (got == want).all():
+                problems.append(f"query {qi}: merged keys differ from the CPU merge of the local lists")
+            if not all(torch.equal(m, merged) for m in allm):
+                problems.append(f"query {qi}: ranks hold different merged lists")
+            ids, scores = o.unpack_keys(got[0])
+            if len(set(ids.tolist())) != K or ids.min() < 0 or ids.max() >= n_global:
+                problems.append(f"query {qi}: ids not unique / out of range")
+                continue
+            # regenerate the named documents (uniform 128-token passages: tokens [id * 128, id * 128 + 128))
+            rows = torch.empty((K * DOC_LEN, 128), dtype=torch.bfloat16, device=dev)
+            for j, d in enumerate(ids.tolist()):
+                _lib.synth_tokens(rows[j * DOC_LEN:(j + 1) * DOC_LEN], int(d) * DOC_LEN, seed)
+            exp = o.maxsim_scores(q.float().cpu(), rows.float().cpu(), torch.arange(0, K * DOC_LEN + 1, DOC_LEN))[0]
+            err = o.check_ranking(list(range(K)), scores.tolist(), exp, K, 1e-3)
+            if err is not None:
+                problems.append(f"query {qi}: oracle re-score: {err}")
+        flag = torch.tensor([len(problems)], device=dev)
+        dist.broadcast(flag, 0)
+        if rank != 0:
+            return None
+        return "ok" if not problems else "; ".join(problems)
+    except Exception as exc:  # noqa: BLE001
+        return f"parity check raised {type(exc).__name__}: {exc}"
+
+
+def sharded_breakdown(torch, dist, _lib, retr, searcher, queries, dev, max_over_ranks, barrier):
+    """Device time of the three parts of a sharded step, each timed alone (20 reps, CUDA events, max over ranks)."""
+    from hybrid_rag_colbertv2_b200.sharded import all_gather_keys
+    q = queries[0:1]
+    local = retr.search_keys(q, K)
+    gathered = all_gather_keys(local, K)
+    parts = {"local_search_us": lambda: retr.search_keys(q, K),
+             "allgather_us": lambda: all_gather_keys(local, K),
+             "merge_us": lambda: _lib.topk_merge(gathered, K)}
+    out = {}
+    for name, fn in parts.items():
+        for _ in range(3):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        barrier()
+        out[name] = max_over_ranks(e0.elapsed_time(e1)) / 20 * 1e3
+    out["overhead_us"] = out["allgather_us"] + out["merge_us"]
+    out["note"] = "each part timed alone back to back; allgather = NCCL all_gather_into_tensor of k x 8 bytes per rank"
+    return out
 
 
 def main():

@@ -14,45 +14,43 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HRC_LIB_PATH") or os.path.join(_HERE, "libhrc.so")   # override: A/B of library builds
 
-PATH_AUTO, PATH_SIMT, PATH_TC = 0, 1, 2
+PATH_AUTO, PATH_SIMT, PATH_TC, PATH_TC_M64 = 0, 1, 2, 3
 DIM = 128
 MAX_TOPK = 2048
 TC_MAX_LQ = 32          # query tokens per slot on the tensor-core path; up to 8 slots (lq <= 256)
+ABI_VERSION = 200
 
 #: every symbol include/hrc.h declares: name -> (restype, argtypes)
 _c = ctypes
+_P, _I, _I32, _I64, _SZ, _U64 = _c.c_void_p, _c.c_int, _c.c_int32, _c.c_int64, _c.c_size_t, _c.c_uint64
 SYMBOLS = {
-    "hrc_version": (_c.c_int, []),
+    "hrc_version": (_I, []),
     "hrc_last_error": (_c.c_char_p, []),
-    "hrc_launch_count": (_c.c_uint64, []),
-    "hrc_maxsim_scores": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int,
-                                     _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p]),
-    "hrc_maxsim_scores_ids": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int,
-                                         _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p]),
-    "hrc_meanpool_cosine_scores": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int,
-                                              _c.c_int, _c.c_void_p, _c.c_void_p]),
-    "hrc_search": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
-                              _c.c_int32, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_void_p,
-                              _c.c_int, _c.c_void_p]),
-    "hrc_search_host_workspace_bytes": (_c.c_size_t, [_c.c_int64, _c.c_int, _c.c_int, _c.c_int]),
-    "hrc_search_host": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int,
-                                   _c.c_int, _c.c_int32, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_int,
-                                   _c.c_void_p]),
-    "hrc_hybrid_retrieve_workspace_bytes": (_c.c_size_t, [_c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
-    "hrc_hybrid_retrieve": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_int,
-                                       _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int32,
-                                       _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p]),
-    "hrc_rerank": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_void_p,
-                              _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
-                              _c.c_void_p, _c.c_int, _c.c_void_p]),
-    "hrc_topk_workspace_bytes": (_c.c_size_t, [_c.c_int64, _c.c_int, _c.c_int]),
-    "hrc_topk": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int32, _c.c_void_p,
-                            _c.c_void_p, _c.c_size_t, _c.c_void_p]),
-    "hrc_topk_merge": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
-    "hrc_keys_unpack": (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
-    "hrc_rrf_fuse": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
-                                _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
-    "hrc_synth_tokens": (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_int64, _c.c_uint64, _c.c_void_p]),
+    "hrc_launch_count": (_U64, []),
+    "hrc_set_watchdog_ms": (None, [_U64]),
+    "hrc_trace_enable": (_I, [_I]),
+    "hrc_trace_collect": (_I, [_P, _I]),
+    "hrc_store_register": (_I, [_P, _I64]),
+    "hrc_store_release": (None, [_P]),
+    "hrc_maxsim_workspace_bytes": (_SZ, [_I64, _I, _I]),
+    "hrc_maxsim_scores": (_I, [_P, _P, _I64, _I64, _P, _I, _I, _P, _I, _P, _SZ, _P]),
+    "hrc_maxsim_scores_ids": (_I, [_P, _P, _I64, _I64, _P, _I, _P, _I, _I, _P, _I, _P, _SZ, _P]),
+    "hrc_meanpool_cosine_scores": (_I, [_P, _P, _I64, _I64, _P, _I, _I, _P, _P]),
+    "hrc_search_workspace_bytes": (_SZ, [_I64, _I, _I, _I]),
+    "hrc_search": (_I, [_P, _P, _I64, _I64, _P, _I, _I, _I, _I32, _P, _SZ, _P, _P, _P, _I, _P]),
+    "hrc_search_host_workspace_bytes": (_SZ, [_I64, _I, _I, _I]),
+    "hrc_search_host": (_I, [_P, _P, _I64, _I64, _P, _I, _I, _I, _I32, _P, _SZ, _P, _P, _I, _P]),
+    "hrc_rerank_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "hrc_rerank": (_I, [_P, _P, _I64, _I64, _P, _I, _P, _I, _I, _I, _P, _SZ, _P, _P, _P, _P, _I, _P]),
+    "hrc_hybrid_retrieve_workspace_bytes": (_SZ, [_I64, _I, _I, _I, _I, _I]),
+    "hrc_hybrid_retrieve": (_I, [_P, _P, _I64, _I64, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I32, _P, _SZ, _P, _P, _I, _P]),
+    "hrc_topk_workspace_bytes": (_SZ, [_I64, _I, _I]),
+    "hrc_topk": (_I, [_P, _P, _I64, _I, _I, _I32, _P, _P, _SZ, _P]),
+    "hrc_topk_merge": (_I, [_P, _I, _I, _I, _P, _P]),
+    "hrc_keys_unpack": (_I, [_P, _I64, _P, _P, _P]),
+    "hrc_rrf_fuse": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "hrc_synth_tokens": (_I, [_P, _I64, _I64, _U64, _P]),
+    "hrc_read_probe": (_I, [_P, _SZ, _P, _P]),
 }
 
 _lib: Optional[ctypes.CDLL] = None
@@ -119,22 +117,90 @@ def launch_count() -> int:
     return int(load().hrc_launch_count())
 
 
-def maxsim_scores(tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.Tensor, *,
-                  path: int = PATH_AUTO, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """scores[q, d] = sum_i max_{t in doc d} <queries[q, i], tokens[t]>  ->  fp32 [n_queries, n_docs]."""
-    dev = _require_cuda(tokens, offsets, queries)
+def set_watchdog_ms(ms: int) -> None:
+    """mbarrier waits inside the tensor-core kernels trap after `ms` without progress (0 = never)."""
+    load().hrc_set_watchdog_ms(int(ms))
+
+
+def trace_enable(capacity: int) -> None:
+    """Bracket the next `capacity` scoring-kernel launches with CUDA events (0 switches tracing off)."""
+    _check(load().hrc_trace_enable(int(capacity)), "hrc_trace_enable")
+
+
+def trace_collect(max_n: int = 1 << 16):
+    """Device times (ms, launch order) of the scoring kernels traced since the last collect; resets the trace."""
+    buf = (ctypes.c_float * max_n)()
+    n = load().hrc_trace_collect(buf, max_n)
+    if n < 0:
+        _check(1, "hrc_trace_collect")
+    return [float(buf[i]) for i in range(n)]
+
+
+def store_register(tokens: torch.Tensor) -> None:
+    """Pre-encode the TMA descriptors of a token store (optional; the first scoring call does it otherwise)."""
+    _require_cuda(tokens)
+    if tokens.shape[0] == 0:
+        return
+    with torch.cuda.device(tokens.device):
+        _check(load().hrc_store_register(_ptr(tokens), int(tokens.shape[0])), "hrc_store_register")
+
+
+def store_release(tokens: torch.Tensor) -> None:
+    """Drop the cached TMA descriptors of a token store (call before freeing it)."""
+    if _lib is not None and tokens is not None and tokens.is_cuda:
+        _lib.hrc_store_release(_ptr(tokens))
+
+
+class Workspace:
+    """A reusable 256-byte-aligned device scratch buffer that only ever grows: no per-call allocation once warm."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, dev, nbytes: int) -> torch.Tensor:
+        if self.buf is None or self.buf.device != dev or self.buf.numel() < nbytes:
+            self.buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)   # caching allocator: 512-B aligned
+        return self.buf
+
+
+def _ws(workspace: Optional[Workspace], dev, nbytes: int):
+    """(pointer, bytes) of a scratch buffer of at least nbytes; (None, 0) when none is needed."""
+    if nbytes == 0:
+        return None, 0, None
+    buf = (workspace or Workspace()).get(dev, nbytes)
+    return buf.data_ptr(), buf.numel(), buf
+
+
+def maxsim_workspace_bytes(n_items: int, n_queries: int, lq: int) -> int:
+    return int(load().hrc_maxsim_workspace_bytes(n_items, n_queries, lq))
+
+
+def _check_store(tokens, offsets):
     assert tokens.dtype == torch.bfloat16 and tokens.dim() == 2 and tokens.shape[1] == DIM
     assert offsets.dtype == torch.int64 and offsets.dim() == 1 and offsets.numel() >= 1
+
+
+def _check_queries(queries):
     assert queries.dtype == torch.bfloat16 and queries.dim() == 3 and queries.shape[2] == DIM
+
+
+def maxsim_scores(tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.Tensor, *,
+                  path: int = PATH_AUTO, out: Optional[torch.Tensor] = None,
+                  workspace: Optional[Workspace] = None) -> torch.Tensor:
+    """scores[q, d] = sum_i max_{t in doc d} <queries[q, i], tokens[t]>  ->  fp32 [n_queries, n_docs]."""
+    dev = _require_cuda(tokens, offsets, queries)
+    _check_store(tokens, offsets)
+    _check_queries(queries)
     n_docs = offsets.numel() - 1
     nq, lq = int(queries.shape[0]), int(queries.shape[1])
     if out is None:
         out = torch.empty((nq, n_docs), dtype=torch.float32, device=dev)
     else:
         assert out.shape == (nq, n_docs) and out.dtype == torch.float32 and out.is_contiguous()
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, 0 if path == PATH_SIMT else maxsim_workspace_bytes(n_docs, nq, lq))
     with torch.cuda.device(dev):
         rc = load().hrc_maxsim_scores(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), _ptr(queries),
-                                      nq, lq, _ptr(out), path, _stream(dev))
+                                      nq, lq, _ptr(out), path, ws_ptr, ws_bytes, _stream(dev))
     _check(rc, "hrc_maxsim_scores")
     return out
 
@@ -144,9 +210,8 @@ def meanpool_cosine_scores(tokens: torch.Tensor, offsets: torch.Tensor, queries:
     """The reference's `_maxsim_score` exactly as coded (local_rag_complete.py:821-829): cosine of the
     mean-pooled query and document token vectors -> fp32 [n_queries, n_docs]."""
     dev = _require_cuda(tokens, offsets, queries)
-    assert tokens.dtype == torch.bfloat16 and tokens.dim() == 2 and tokens.shape[1] == DIM
-    assert offsets.dtype == torch.int64 and offsets.dim() == 1 and offsets.numel() >= 1
-    assert queries.dtype == torch.bfloat16 and queries.dim() == 3 and queries.shape[2] == DIM
+    _check_store(tokens, offsets)
+    _check_queries(queries)
     n_docs = offsets.numel() - 1
     nq, lq = int(queries.shape[0]), int(queries.shape[1])
     if out is None:
@@ -161,62 +226,47 @@ def meanpool_cosine_scores(tokens: torch.Tensor, offsets: torch.Tensor, queries:
 
 
 def maxsim_scores_ids(tokens: torch.Tensor, offsets: torch.Tensor, cand_ids: torch.Tensor,
-                      queries: torch.Tensor, *, path: int = PATH_AUTO) -> torch.Tensor:
+                      queries: torch.Tensor, *, path: int = PATH_AUTO,
+                      workspace: Optional[Workspace] = None) -> torch.Tensor:
     """scores[q, j] = maxsim(queries[q], doc cand_ids[q, j])  ->  fp32 [n_queries, n_cand]."""
     dev = _require_cuda(tokens, offsets, cand_ids, queries)
     assert cand_ids.dtype == torch.int32 and cand_ids.dim() == 2 and cand_ids.shape[0] == queries.shape[0]
-    assert tokens.dtype == torch.bfloat16 and queries.dtype == torch.bfloat16 and offsets.dtype == torch.int64
+    _check_store(tokens, offsets)
+    _check_queries(queries)
     n_docs = offsets.numel() - 1
     nq, lq = int(queries.shape[0]), int(queries.shape[1])
     n_cand = int(cand_ids.shape[1])
     out = torch.empty((nq, n_cand), dtype=torch.float32, device=dev)
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, 0 if path == PATH_SIMT else maxsim_workspace_bytes(n_cand, nq, lq))
     with torch.cuda.device(dev):
         rc = load().hrc_maxsim_scores_ids(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), _ptr(cand_ids),
-                                          n_cand, _ptr(queries), nq, lq, _ptr(out), path, _stream(dev))
+                                          n_cand, _ptr(queries), nq, lq, _ptr(out), path, ws_ptr, ws_bytes, _stream(dev))
     _check(rc, "hrc_maxsim_scores_ids")
     return out
 
 
-class SearchBuffers:
-    """Reusable device scratch for `search` (scores matrix, top-k workspace, outputs): no per-call allocation."""
-
-    def __init__(self):
-        self.key = None
-
-    def ensure(self, dev, nq: int, n_docs: int, k: int):
-        key = (str(dev), nq, n_docs, k)
-        if self.key != key:
-            self.scores = torch.empty((nq, n_docs), dtype=torch.float32, device=dev)
-            need = topk_workspace_bytes(n_docs, nq, k)
-            self.ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
-            self.ws_bytes = need
-            self.key = key
-        return self
-
-
 def search(tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.Tensor, k: int, *, id_base: int = 0,
-           path: int = PATH_AUTO, buffers: Optional[SearchBuffers] = None, unpack: bool = True):
-    """Fused MaxSim + top-k (+ unpack) in one C call.  Returns (keys int64 [nq,k], ids int32 | None, scores fp32 | None).
-    `buffers.scores` holds the full score matrix afterwards."""
+           path: int = PATH_AUTO, workspace: Optional[Workspace] = None, unpack: bool = True):
+    """Fused MaxSim + top-k (+ unpack) in one C call.  Returns (keys int64 [nq,k], ids int32 | None, scores fp32 | None)."""
     dev = _require_cuda(tokens, offsets, queries)
-    assert tokens.dtype == torch.bfloat16 and queries.dtype == torch.bfloat16 and offsets.dtype == torch.int64
+    _check_store(tokens, offsets)
+    _check_queries(queries)
     n_docs = offsets.numel() - 1
     nq, lq = int(queries.shape[0]), int(queries.shape[1])
-    buf = (buffers or SearchBuffers()).ensure(dev, nq, n_docs, k)
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, int(load().hrc_search_workspace_bytes(n_docs, nq, lq, k)))
     keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
     ids = torch.empty((nq, k), dtype=torch.int32, device=dev) if unpack else None
     scores = torch.empty((nq, k), dtype=torch.float32, device=dev) if unpack else None
     with torch.cuda.device(dev):
         rc = load().hrc_search(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), _ptr(queries), nq, lq, k,
-                               id_base, _ptr(buf.scores), _ptr(buf.ws), buf.ws_bytes, _ptr(keys), _ptr(ids),
-                               _ptr(scores), path, _stream(dev))
+                               id_base, ws_ptr, ws_bytes, _ptr(keys), _ptr(ids), _ptr(scores), path, _stream(dev))
     _check(rc, "hrc_search")
     return keys, ids, scores
 
 
 class HostSearch:
     """End-to-end search with host buffers (hrc_search_host): pinned fp32 queries in, pinned ids / scores out,
-    one C call and one stream synchronisation per search.  Buffers are kept between calls."""
+    one C call and one stream synchronisation per search.  Device scratch and pinned staging are kept between calls."""
 
     def __init__(self):
         self.key = None
@@ -233,12 +283,13 @@ class HostSearch:
             self.key = key
 
     def __call__(self, tokens: torch.Tensor, offsets: torch.Tensor, queries_host: torch.Tensor, k: int, *,
-                 id_base: int = 0, path: int = PATH_AUTO):
+                 id_base: int = 0, path: int = PATH_AUTO, copy: bool = True):
         """queries_host: fp32 CPU tensor [nq, lq, 128] (pinned: used in place; pageable: staged through a pinned
-        buffer).  Returns (ids int32 [nq, k], scores fp32 [nq, k]) as PINNED CPU tensors owned by this object
-        (valid until the next call)."""
+        buffer).  Returns (ids int32 [nq, k], scores fp32 [nq, k]) CPU tensors.  With copy=True (default) they are
+        fresh tensors the caller owns; copy=False returns this object's PINNED staging buffers, which the next call
+        overwrites."""
         dev = _require_cuda(tokens, offsets)
-        assert tokens.dtype == torch.bfloat16 and offsets.dtype == torch.int64
+        _check_store(tokens, offsets)
         assert not queries_host.is_cuda and queries_host.dtype == torch.float32 and queries_host.dim() == 3
         assert queries_host.shape[2] == DIM and queries_host.is_contiguous()
         n_docs = offsets.numel() - 1
@@ -255,64 +306,53 @@ class HostSearch:
                                         self.scores.data_ptr(), path, stream.cuda_stream)
             _check(rc, "hrc_search_host")
             stream.synchronize()
+        if copy:
+            return self.ids.clone(), self.scores.clone()
         return self.ids, self.scores
-
-
-class HybridBuffers:
-    """Reusable device scratch for `hybrid_retrieve`."""
-
-    def __init__(self):
-        self.key = None
-
-    def ensure(self, dev, n_docs: int, nq: int, colbert_k: int, n_cand: int, final_k: int):
-        key = (str(dev), n_docs, nq, colbert_k, n_cand, final_k)
-        if self.key != key:
-            self.ws_bytes = int(load().hrc_hybrid_retrieve_workspace_bytes(n_docs, nq, colbert_k, n_cand, final_k))
-            self.ws = torch.empty(max(self.ws_bytes, 256), dtype=torch.uint8, device=dev)
-            self.key = key
-        return self
 
 
 def hybrid_retrieve(tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.Tensor, bm25_ids: torch.Tensor, *,
                     colbert_k: int, rrf_k: int, n_candidates: int, final_k: int, id_base: int = 0,
-                    path: int = PATH_AUTO, buffers: Optional[HybridBuffers] = None):
+                    path: int = PATH_AUTO, workspace: Optional[Workspace] = None):
     """ColBERT top-k -> RRF with the BM25 lists -> rerank of the stored candidates, one C call (hrc_hybrid_retrieve).
     Returns (global doc ids int32 [nq, final_k], MaxSim scores fp32 [nq, final_k])."""
     dev = _require_cuda(tokens, offsets, queries, bm25_ids)
-    assert tokens.dtype == torch.bfloat16 and queries.dtype == torch.bfloat16 and offsets.dtype == torch.int64
+    _check_store(tokens, offsets)
+    _check_queries(queries)
     assert bm25_ids.dtype == torch.int32 and bm25_ids.dim() == 2 and bm25_ids.shape[0] == queries.shape[0]
     n_docs = offsets.numel() - 1
     nq, lq = int(queries.shape[0]), int(queries.shape[1])
-    buf = (buffers or HybridBuffers()).ensure(dev, n_docs, nq, colbert_k, n_candidates, final_k)
+    need = int(load().hrc_hybrid_retrieve_workspace_bytes(n_docs, nq, lq, colbert_k, n_candidates, final_k))
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, need)
     ids = torch.empty((nq, final_k), dtype=torch.int32, device=dev)
     scores = torch.empty((nq, final_k), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         rc = load().hrc_hybrid_retrieve(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), _ptr(queries), nq, lq,
                                         _ptr(bm25_ids), int(bm25_ids.shape[1]), colbert_k, rrf_k, n_candidates, final_k,
-                                        id_base, _ptr(buf.ws), buf.ws_bytes, _ptr(ids), _ptr(scores), path, _stream(dev))
+                                        id_base, ws_ptr, ws_bytes, _ptr(ids), _ptr(scores), path, _stream(dev))
     _check(rc, "hrc_hybrid_retrieve")
     return ids, scores
 
 
 def rerank(tokens: torch.Tensor, offsets: torch.Tensor, cand_ids: torch.Tensor, queries: torch.Tensor, k: int, *,
-           path: int = PATH_AUTO):
+           path: int = PATH_AUTO, workspace: Optional[Workspace] = None, want_cand_scores: bool = False):
     """Fused candidate MaxSim + sorted top-k in one C call.
-    Returns (pos int32 [nq,k], doc ids int32 [nq,k], scores fp32 [nq,k], candidate scores fp32 [nq,n_cand])."""
+    Returns (pos int32 [nq,k], doc ids int32 [nq,k], scores fp32 [nq,k], candidate scores fp32 [nq,n_cand] | None)."""
     dev = _require_cuda(tokens, offsets, cand_ids, queries)
     assert cand_ids.dtype == torch.int32 and cand_ids.dim() == 2 and cand_ids.shape[0] == queries.shape[0]
-    assert tokens.dtype == torch.bfloat16 and queries.dtype == torch.bfloat16 and offsets.dtype == torch.int64
+    _check_store(tokens, offsets)
+    _check_queries(queries)
     n_docs = offsets.numel() - 1
     nq, lq = int(queries.shape[0]), int(queries.shape[1])
     n_cand = int(cand_ids.shape[1])
-    cand_scores = torch.empty((nq, n_cand), dtype=torch.float32, device=dev)
-    keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
-    pos = torch.empty((nq, k), dtype=torch.int32, device=dev)
-    ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
-    scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, int(load().hrc_rerank_workspace_bytes(n_cand, nq, lq, k)))
+    cand_scores = torch.empty((nq, n_cand), dtype=torch.float32, device=dev) if want_cand_scores else None
+    out = torch.empty((3, nq, k), dtype=torch.int32, device=dev)      # one allocation: pos | ids | scores (fp32 view)
+    pos, ids, scores = out[0], out[1], out[2].view(torch.float32)
     with torch.cuda.device(dev):
         rc = load().hrc_rerank(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), _ptr(cand_ids), n_cand,
-                               _ptr(queries), nq, lq, k, _ptr(cand_scores), _ptr(keys), _ptr(pos), _ptr(ids),
-                               _ptr(scores), path, _stream(dev))
+                               _ptr(queries), nq, lq, k, ws_ptr, ws_bytes, pos.data_ptr(), ids.data_ptr(),
+                               scores.data_ptr(), _ptr(cand_scores), path, _stream(dev))
     _check(rc, "hrc_rerank")
     return pos, ids, scores, cand_scores
 
@@ -388,4 +428,15 @@ def synth_tokens(out: torch.Tensor, token_begin: int, seed: int) -> torch.Tensor
     with torch.cuda.device(dev):
         rc = load().hrc_synth_tokens(_ptr(out), token_begin, int(out.shape[0]), seed & (2**64 - 1), _stream(dev))
     _check(rc, "hrc_synth_tokens")
+    return out
+
+
+def read_probe(buf: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Stream `buf` once with 16-byte loads (bench utility: the pure-read bandwidth probe)."""
+    dev = _require_cuda(buf)
+    if out is None:
+        out = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = load().hrc_read_probe(_ptr(buf), buf.numel() * buf.element_size(), _ptr(out), _stream(dev))
+    _check(rc, "hrc_read_probe")
     return out

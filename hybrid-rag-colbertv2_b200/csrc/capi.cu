@@ -4,6 +4,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
+#include <vector>
 
 #include "hrc_common.cuh"
 
@@ -20,10 +22,42 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(uint64_t(n), std::memory_order_relaxed); }
 
+// ---- kernel trace (hrc_trace_enable / hrc_trace_collect): CUDA events around every scoring-kernel launch ----------
+struct Trace {
+  std::vector<cudaEvent_t> ev;   // 2 * capacity: begin, end, begin, end ...
+  int n = 0;                     // launches recorded
+  bool open = false;             // a begin without its end
+};
+static Trace g_trace;
+static std::mutex g_trace_mu;
+
+void trace_begin(cudaStream_t stream) {
+  if (g_trace.ev.empty()) return;
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  if (2 * g_trace.n + 1 >= int(g_trace.ev.size())) return;     // full: later launches are not recorded
+  cudaEventRecord(g_trace.ev[2 * g_trace.n], stream);
+  g_trace.open = true;
+}
+void trace_end(cudaStream_t stream) {
+  if (g_trace.ev.empty()) return;
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  if (!g_trace.open) return;
+  cudaEventRecord(g_trace.ev[2 * g_trace.n + 1], stream);
+  g_trace.open = false;
+  ++g_trace.n;
+}
+
 int launch_maxsim_simt(const void*, const int64_t*, int64_t, const int32_t*, int64_t, const void*, int, int, float*,
                        cudaStream_t);
 int launch_maxsim_tc(const void*, const int64_t*, int64_t, int64_t, const int32_t*, int64_t, const void*, int, int,
-                     float*, cudaStream_t);
+                     float*, bool, void*, size_t, cudaStream_t);
+size_t maxsim_tc_workspace_bytes(int64_t, int, int);
+void set_watchdog_ns(uint64_t);
+int store_register(const void*, int64_t);
+void store_release(const void*);
+#ifdef HRC_EXPERIMENTS
+void set_debug(int);
+#endif
 size_t topk_workspace_bytes(int64_t, int, int);
 int launch_topk(const float*, const int32_t*, int64_t, int, int, int32_t, uint64_t*, void*, size_t, cudaStream_t);
 int launch_topk_merge(const uint64_t*, int, int, int, uint64_t*, cudaStream_t);
@@ -31,6 +65,7 @@ int launch_keys_unpack(const uint64_t*, int64_t, int32_t*, float*, cudaStream_t)
 int launch_rerank_unpack(const uint64_t*, int, int, const int32_t*, int, int32_t*, int32_t*, float*, cudaStream_t);
 int launch_rrf(const int32_t*, int, const int32_t*, int, int, int, int, int32_t*, double*, int32_t*, cudaStream_t);
 int launch_synth(void*, int64_t, int64_t, uint64_t, cudaStream_t);
+int launch_read_probe(const void*, size_t, uint32_t*, cudaStream_t);
 int launch_meanpool_cosine(const void*, const int64_t*, int64_t, const void*, int, int, float*, cudaStream_t);
 
 static int check_device() {
@@ -54,18 +89,27 @@ static int check_device() {
   return 0;
 }
 
+// bytes of caller workspace one scoring call needs (only queries longer than 32 tokens on the tensor-core path)
+static size_t maxsim_ws_bytes(int64_t n_items, int n_queries, int lq, int path) {
+  if (path == HRC_PATH_SIMT) return 0;
+  return maxsim_tc_workspace_bytes(n_items, n_queries, lq);
+}
+
 static int maxsim_dispatch(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
                            const int32_t* d_cand_ids, int64_t n_items, const void* d_queries, int n_queries, int lq,
-                           float* d_scores, int path, cudaStream_t stream) {
+                           float* d_scores, int path, void* d_workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (int rc = check_device()) return rc;
   HRC_REQUIRE(n_docs >= 0 && total_tokens >= 0 && n_queries >= 0 && lq >= 1, "maxsim: negative size or lq < 1");
   HRC_REQUIRE(n_items == 0 || n_queries == 0 ||
                   (d_tokens != nullptr && d_offsets != nullptr && d_queries != nullptr && d_scores != nullptr),
               "maxsim: null pointer argument");
+  // AUTO: the tensor-core path whenever it applies (lq <= 256).  Measured on B200 (profiles/r02_summary.md, "TC / SIMT
+  // crossover"): the tcgen05 kernel is faster than the CUDA-core kernel down to a single query token and a 50-document
+  // rerank, because the SIMT kernel is FMA-bound and both pay the same launch latency.
   if (path == HRC_PATH_AUTO) path = (lq <= HRC_TC_MAX_LQ * HRC_TC_MAX_SLOTS && total_tokens > 0) ? HRC_PATH_TC : HRC_PATH_SIMT;
-  if (path == HRC_PATH_TC)
+  if (path == HRC_PATH_TC || path == HRC_PATH_TC_M64)
     return launch_maxsim_tc(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_items, d_queries, n_queries, lq,
-                            d_scores, stream);
+                            d_scores, path == HRC_PATH_TC_M64, d_workspace, workspace_bytes, stream);
   HRC_REQUIRE(path == HRC_PATH_SIMT, "maxsim: unknown path %d", path);
   return launch_maxsim_simt(d_tokens, d_offsets, n_docs, d_cand_ids, n_items, d_queries, n_queries, lq, d_scores,
                             stream);
@@ -85,38 +129,68 @@ __global__ void shift_ids_kernel(int32_t* ids, int64_t n, int32_t delta) {
   if (i < n && ids[i] >= 0) ids[i] += delta;
 }
 
-struct HybridLayout {
-  size_t scores, topk, keys, col_ids, fused_ids, fused_scores, counts, cand_scores, rr_keys, pos, total, topk_bytes;
+// ---- workspace layouts (every sub-buffer 256-byte aligned) -------------------------------------------------
+struct SearchLayout {      // hrc_search: score matrix, slot partials (lq > 32), top-k scratch
+  size_t scores, part, topk, total, part_bytes, topk_bytes;
 };
-static HybridLayout hybrid_layout(int64_t n_docs, int nq, int colbert_k, int n_cand, int final_k) {
-  HybridLayout L;
+static SearchLayout search_layout(int64_t n_docs, int nq, int lq, int k) {
+  SearchLayout L;
   size_t o = 0;
   L.scores = o; o += align256(size_t(nq) * size_t(n_docs) * sizeof(float));
-  L.topk_bytes = topk_workspace_bytes(n_docs, nq, colbert_k);
+  L.part_bytes = maxsim_tc_workspace_bytes(n_docs, nq, lq);
+  L.part = o; o += align256(L.part_bytes);
+  L.topk_bytes = topk_workspace_bytes(n_docs, nq, k);
   L.topk = o; o += align256(L.topk_bytes);
+  L.total = o;
+  return L;
+}
+
+struct RerankLayout {      // hrc_rerank: candidate scores, slot partials, top-k scratch, keys
+  size_t scores, part, topk, keys, total, part_bytes, topk_bytes;
+};
+static RerankLayout rerank_layout(int n_cand, int nq, int lq, int k) {
+  RerankLayout L;
+  size_t o = 0;
+  L.scores = o; o += align256(size_t(nq) * size_t(n_cand) * sizeof(float));
+  L.part_bytes = maxsim_tc_workspace_bytes(n_cand, nq, lq);
+  L.part = o; o += align256(L.part_bytes);
+  L.topk_bytes = topk_workspace_bytes(n_cand, nq, k);
+  L.topk = o; o += align256(L.topk_bytes);
+  L.keys = o; o += align256(size_t(nq) * size_t(k) * sizeof(uint64_t));
+  L.total = o;
+  return L;
+}
+
+struct HybridLayout {
+  size_t search, keys, col_ids, fused_ids, fused_scores, counts, rerank, pos, total, search_bytes, rerank_bytes;
+};
+static HybridLayout hybrid_layout(int64_t n_docs, int nq, int lq, int colbert_k, int n_cand, int final_k) {
+  HybridLayout L;
+  size_t o = 0;
+  L.search_bytes = search_layout(n_docs, nq, lq, colbert_k).total;
+  L.search = o; o += align256(L.search_bytes);
   L.keys = o; o += align256(size_t(nq) * colbert_k * sizeof(uint64_t));
   L.col_ids = o; o += align256(size_t(nq) * colbert_k * sizeof(int32_t));
   L.fused_ids = o; o += align256(size_t(nq) * n_cand * sizeof(int32_t));
   L.fused_scores = o; o += align256(size_t(nq) * n_cand * sizeof(double));
   L.counts = o; o += align256(size_t(nq) * sizeof(int32_t));
-  L.cand_scores = o; o += align256(size_t(nq) * n_cand * sizeof(float));
-  L.rr_keys = o; o += align256(size_t(nq) * final_k * sizeof(uint64_t));
+  L.rerank_bytes = rerank_layout(n_cand, nq, lq, final_k).total;
+  L.rerank = o; o += align256(L.rerank_bytes);
   L.pos = o; o += align256(size_t(nq) * final_k * sizeof(int32_t));
   L.total = o;
   return L;
 }
 
 struct HostSearchLayout {
-  size_t q32, q16, scores, topk, keys, ids, out_scores, total, topk_bytes;
+  size_t q32, q16, search, keys, ids, out_scores, total, search_bytes;
 };
 static HostSearchLayout host_search_layout(int64_t n_docs, int n_queries, int lq, int k) {
   HostSearchLayout L;
   size_t o = 0;
   L.q32 = o; o += align256(size_t(n_queries) * lq * HRC_DIM * sizeof(float));
   L.q16 = o; o += align256(size_t(n_queries) * lq * HRC_DIM * 2);
-  L.scores = o; o += align256(size_t(n_queries) * size_t(n_docs) * sizeof(float));
-  L.topk_bytes = topk_workspace_bytes(n_docs, n_queries, k);
-  L.topk = o; o += align256(L.topk_bytes);
+  L.search_bytes = search_layout(n_docs, n_queries, lq, k).total;
+  L.search = o; o += align256(L.search_bytes);
   L.keys = o; o += align256(size_t(n_queries) * k * sizeof(uint64_t));
   L.ids = o; o += align256(size_t(n_queries) * k * sizeof(int32_t));
   L.out_scores = o; o += align256(size_t(n_queries) * k * sizeof(float));
@@ -124,31 +198,79 @@ static HostSearchLayout host_search_layout(int64_t n_docs, int n_queries, int lq
   return L;
 }
 
+static bool aligned256(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 255) == 0; }
+
 }  // namespace hrc
 
 using namespace hrc;
 
 extern "C" {
 
-int hrc_version(void) { return 100; }
+int hrc_version(void) { return 200; }
 
 const char* hrc_last_error(void) { return g_error; }
 
 uint64_t hrc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+void hrc_set_watchdog_ms(uint64_t ms) { set_watchdog_ns(ms * 1000000ull); }
+
+int hrc_trace_enable(int capacity) {
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  for (cudaEvent_t e : g_trace.ev) cudaEventDestroy(e);
+  g_trace.ev.clear();
+  g_trace.n = 0;
+  g_trace.open = false;
+  HRC_REQUIRE(capacity >= 0 && capacity <= (1 << 20), "trace_enable: capacity %d out of range", capacity);
+  g_trace.ev.resize(size_t(2) * capacity);
+  for (auto& e : g_trace.ev) HRC_CHECK_CUDA(cudaEventCreate(&e));
+  return 0;
+}
+
+int hrc_trace_collect(float* ms_out, int max_n) {
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  const int n = g_trace.n < max_n ? g_trace.n : max_n;
+  for (int i = 0; i < n; ++i) {
+    if (cudaEventSynchronize(g_trace.ev[2 * i + 1]) != cudaSuccess ||
+        cudaEventElapsedTime(&ms_out[i], g_trace.ev[2 * i], g_trace.ev[2 * i + 1]) != cudaSuccess) {
+      set_error("trace_collect: event %d not readable", i);
+      return -1;
+    }
+  }
+  g_trace.n = 0;
+  g_trace.open = false;
+  return n;
+}
+
+#ifdef HRC_EXPERIMENTS
+void hrc_exp_set_debug(int bits) { set_debug(bits); }
+#endif
+
+int hrc_store_register(const void* d_tokens, int64_t total_tokens) {
+  if (int rc = check_device()) return rc;
+  return store_register(d_tokens, total_tokens);
+}
+
+void hrc_store_release(const void* d_tokens) { store_release(d_tokens); }
+
+size_t hrc_maxsim_workspace_bytes(int64_t n_items, int n_queries, int lq) {
+  if (n_items < 0 || n_queries < 0 || lq < 1) return 0;
+  return maxsim_tc_workspace_bytes(n_items, n_queries, lq);
+}
+
 int hrc_maxsim_scores(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
-                      const void* d_queries, int n_queries, int lq, float* d_scores, int path, void* stream) {
+                      const void* d_queries, int n_queries, int lq, float* d_scores, int path, void* d_workspace,
+                      size_t workspace_bytes, void* stream) {
   return maxsim_dispatch(d_tokens, d_offsets, n_docs, total_tokens, nullptr, n_docs, d_queries, n_queries, lq,
-                         d_scores, path, static_cast<cudaStream_t>(stream));
+                         d_scores, path, d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int hrc_maxsim_scores_ids(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
                           const int32_t* d_cand_ids, int n_cand, const void* d_queries, int n_queries, int lq,
-                          float* d_scores, int path, void* stream) {
+                          float* d_scores, int path, void* d_workspace, size_t workspace_bytes, void* stream) {
   HRC_REQUIRE(n_cand >= 0, "maxsim_ids: n_cand < 0");
   HRC_REQUIRE(n_cand == 0 || d_cand_ids != nullptr, "maxsim_ids: null candidate list");
   return maxsim_dispatch(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_cand, d_queries, n_queries, lq,
-                         d_scores, path, static_cast<cudaStream_t>(stream));
+                         d_scores, path, d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int hrc_meanpool_cosine_scores(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
@@ -163,16 +285,27 @@ int hrc_meanpool_cosine_scores(const void* d_tokens, const int64_t* d_offsets, i
                                 static_cast<cudaStream_t>(stream));
 }
 
+size_t hrc_search_workspace_bytes(int64_t n_docs, int n_queries, int lq, int k) {
+  if (n_docs < 0 || n_queries < 0 || lq < 1 || k < 0) return 0;
+  return search_layout(n_docs, n_queries, lq, k).total;
+}
+
 int hrc_search(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens, const void* d_queries,
-               int n_queries, int lq, int k, int32_t id_base, float* d_scores_ws, void* d_topk_ws, size_t topk_ws_bytes,
+               int n_queries, int lq, int k, int32_t id_base, void* d_workspace, size_t workspace_bytes,
                uint64_t* d_keys_out, int32_t* d_ids_out, float* d_scores_out, int path, void* stream) {
-  HRC_REQUIRE(k >= 0 && k <= n_docs, "search: k=%d must be in [0, n_docs]", k);
-  HRC_REQUIRE(n_queries == 0 || k == 0 || (d_scores_ws != nullptr && d_keys_out != nullptr), "search: null buffer");
+  HRC_REQUIRE(n_queries >= 0 && lq >= 1 && k >= 0 && k <= n_docs, "search: k=%d must be in [0, n_docs]", k);
+  if (n_queries == 0 || k == 0) return 0;
+  HRC_REQUIRE(d_keys_out != nullptr && d_workspace != nullptr, "search: null buffer");
+  const SearchLayout L = search_layout(n_docs, n_queries, lq, k);
+  HRC_REQUIRE(workspace_bytes >= L.total, "search: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+  HRC_REQUIRE(aligned256(d_workspace), "search: workspace must be 256-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+  float* scores = reinterpret_cast<float*>(ws + L.scores);
   if (int rc = maxsim_dispatch(d_tokens, d_offsets, n_docs, total_tokens, nullptr, n_docs, d_queries, n_queries, lq,
-                               d_scores_ws, path, st))
+                               scores, path, ws + L.part, L.part_bytes, st))
     return rc;
-  if (int rc = launch_topk(d_scores_ws, nullptr, n_docs, n_queries, k, id_base, d_keys_out, d_topk_ws, topk_ws_bytes, st))
+  if (int rc = launch_topk(scores, nullptr, n_docs, n_queries, k, id_base, d_keys_out, ws + L.topk, L.topk_bytes, st))
     return rc;
   if (d_ids_out != nullptr || d_scores_out != nullptr)
     return launch_keys_unpack(d_keys_out, int64_t(n_queries) * k, d_ids_out, d_scores_out, st);
@@ -194,7 +327,7 @@ int hrc_search_host(const void* d_tokens, const int64_t* d_offsets, int64_t n_do
               "search_host: null buffer");
   const HostSearchLayout L = host_search_layout(n_docs, n_queries, lq, k);
   HRC_REQUIRE(workspace_bytes >= L.total, "search_host: workspace too small (%zu < %zu)", workspace_bytes, L.total);
-  HRC_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, "search_host: workspace must be 256-byte aligned");
+  HRC_REQUIRE(aligned256(d_workspace), "search_host: workspace must be 256-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(d_workspace);
   float* q32 = reinterpret_cast<float*>(ws + L.q32);
@@ -206,18 +339,45 @@ int hrc_search_host(const void* d_tokens, const int64_t* d_offsets, int64_t n_do
   HRC_CHECK_CUDA(cudaGetLastError());
   int32_t* d_ids = reinterpret_cast<int32_t*>(ws + L.ids);
   float* d_sc = reinterpret_cast<float*>(ws + L.out_scores);
-  if (int rc = hrc_search(d_tokens, d_offsets, n_docs, total_tokens, q16, n_queries, lq, k, id_base,
-                          reinterpret_cast<float*>(ws + L.scores), ws + L.topk, L.topk_bytes,
-                          reinterpret_cast<uint64_t*>(ws + L.keys), d_ids, d_sc, path, stream))
+  if (int rc = hrc_search(d_tokens, d_offsets, n_docs, total_tokens, q16, n_queries, lq, k, id_base, ws + L.search,
+                          L.search_bytes, reinterpret_cast<uint64_t*>(ws + L.keys), d_ids, d_sc, path, stream))
     return rc;
   HRC_CHECK_CUDA(cudaMemcpyAsync(h_ids_out, d_ids, size_t(n_queries) * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   HRC_CHECK_CUDA(cudaMemcpyAsync(h_scores_out, d_sc, size_t(n_queries) * k * sizeof(float), cudaMemcpyDeviceToHost, st));
   return 0;
 }
 
-size_t hrc_hybrid_retrieve_workspace_bytes(int64_t n_docs, int n_queries, int colbert_k, int n_candidates, int final_k) {
-  if (n_docs < 0 || n_queries < 0 || colbert_k < 0 || n_candidates < 0 || final_k < 0) return 0;
-  return hybrid_layout(n_docs, n_queries, colbert_k, n_candidates, final_k).total;
+size_t hrc_rerank_workspace_bytes(int n_cand, int n_queries, int lq, int k) {
+  if (n_cand < 0 || n_queries < 0 || lq < 1 || k < 0) return 0;
+  return rerank_layout(n_cand, n_queries, lq, k).total;
+}
+
+int hrc_rerank(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+               const int32_t* d_cand_ids, int n_cand, const void* d_queries, int n_queries, int lq, int k,
+               void* d_workspace, size_t workspace_bytes, int32_t* d_pos_out, int32_t* d_ids_out, float* d_scores_out,
+               float* d_cand_scores_out, int path, void* stream) {
+  HRC_REQUIRE(n_cand >= 0 && n_queries >= 0 && lq >= 1, "rerank: negative size or lq < 1");
+  HRC_REQUIRE(k >= 0 && k <= n_cand, "rerank: k=%d must be in [0, n_cand]", k);
+  if (n_queries == 0 || k == 0) return 0;
+  HRC_REQUIRE(d_cand_ids != nullptr && d_workspace != nullptr, "rerank: null buffer");
+  const RerankLayout L = rerank_layout(n_cand, n_queries, lq, k);
+  HRC_REQUIRE(workspace_bytes >= L.total, "rerank: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+  HRC_REQUIRE(aligned256(d_workspace), "rerank: workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+  float* scores = d_cand_scores_out != nullptr ? d_cand_scores_out : reinterpret_cast<float*>(ws + L.scores);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(ws + L.keys);
+  if (int rc = maxsim_dispatch(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_cand, d_queries, n_queries, lq,
+                               scores, path, ws + L.part, L.part_bytes, st))
+    return rc;
+  if (int rc = launch_topk(scores, nullptr, n_cand, n_queries, k, 0, keys, ws + L.topk, L.topk_bytes, st)) return rc;
+  return launch_rerank_unpack(keys, k, n_queries, d_cand_ids, n_cand, d_pos_out, d_ids_out, d_scores_out, st);
+}
+
+size_t hrc_hybrid_retrieve_workspace_bytes(int64_t n_docs, int n_queries, int lq, int colbert_k, int n_candidates,
+                                           int final_k) {
+  if (n_docs < 0 || n_queries < 0 || lq < 1 || colbert_k < 0 || n_candidates < 0 || final_k < 0) return 0;
+  return hybrid_layout(n_docs, n_queries, lq, colbert_k, n_candidates, final_k).total;
 }
 
 int hrc_hybrid_retrieve(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
@@ -225,23 +385,23 @@ int hrc_hybrid_retrieve(const void* d_tokens, const int64_t* d_offsets, int64_t 
                         int rrf_k, int n_candidates, int final_k, int32_t id_base, void* d_workspace,
                         size_t workspace_bytes, int32_t* d_ids_out, float* d_scores_out, int path, void* stream) {
   if (int rc = check_device()) return rc;
-  HRC_REQUIRE(n_queries >= 0 && n_bm25 >= 0 && colbert_k >= 1 && colbert_k <= n_docs && n_candidates >= 1 &&
+  HRC_REQUIRE(n_queries >= 0 && lq >= 1 && n_bm25 >= 0 && colbert_k >= 1 && colbert_k <= n_docs && n_candidates >= 1 &&
                   final_k >= 1 && final_k <= n_candidates,
               "hybrid_retrieve: need 1 <= colbert_k <= n_docs and 1 <= final_k <= n_candidates");
   if (n_queries == 0) return 0;
   HRC_REQUIRE(d_workspace != nullptr && d_ids_out != nullptr && d_scores_out != nullptr && (n_bm25 == 0 || d_bm25_ids != nullptr),
               "hybrid_retrieve: null buffer");
-  const HybridLayout L = hybrid_layout(n_docs, n_queries, colbert_k, n_candidates, final_k);
+  const HybridLayout L = hybrid_layout(n_docs, n_queries, lq, colbert_k, n_candidates, final_k);
   HRC_REQUIRE(workspace_bytes >= L.total, "hybrid_retrieve: workspace too small (%zu < %zu)", workspace_bytes, L.total);
-  HRC_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, "hybrid_retrieve: workspace must be 256-byte aligned");
+  HRC_REQUIRE(aligned256(d_workspace), "hybrid_retrieve: workspace must be 256-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(d_workspace);
   int32_t* col_ids = reinterpret_cast<int32_t*>(ws + L.col_ids);
   int32_t* fused = reinterpret_cast<int32_t*>(ws + L.fused_ids);
   // stage 2 of retrieve (:908-911): ColBERT first stage over the whole store, GLOBAL ids
   if (int rc = hrc_search(d_tokens, d_offsets, n_docs, total_tokens, d_queries, n_queries, lq, colbert_k, id_base,
-                          reinterpret_cast<float*>(ws + L.scores), ws + L.topk, L.topk_bytes,
-                          reinterpret_cast<uint64_t*>(ws + L.keys), col_ids, nullptr, path, stream))
+                          ws + L.search, L.search_bytes, reinterpret_cast<uint64_t*>(ws + L.keys), col_ids, nullptr, path,
+                          stream))
     return rc;
   // stage 3 (:914-916): RRF of the BM25 list with the ColBERT list, top n_candidates
   if (int rc = launch_rrf(d_bm25_ids, n_bm25, col_ids, colbert_k, n_queries, rrf_k, n_candidates, fused,
@@ -254,8 +414,8 @@ int hrc_hybrid_retrieve(const void* d_tokens, const int64_t* d_offsets, int64_t 
   }
   // stage 5 (:926-929): rerank the candidates' STORED token embeddings, sorted top final_k
   if (int rc = hrc_rerank(d_tokens, d_offsets, n_docs, total_tokens, fused, n_candidates, d_queries, n_queries, lq, final_k,
-                          reinterpret_cast<float*>(ws + L.cand_scores), reinterpret_cast<uint64_t*>(ws + L.rr_keys),
-                          reinterpret_cast<int32_t*>(ws + L.pos), d_ids_out, d_scores_out, path, stream))
+                          ws + L.rerank, L.rerank_bytes, reinterpret_cast<int32_t*>(ws + L.pos), d_ids_out, d_scores_out,
+                          nullptr, path, stream))
     return rc;
   if (id_base != 0) {
     const int64_t n_out = int64_t(n_queries) * final_k;
@@ -264,22 +424,6 @@ int hrc_hybrid_retrieve(const void* d_tokens, const int64_t* d_offsets, int64_t 
   }
   HRC_CHECK_CUDA(cudaGetLastError());
   return 0;
-}
-
-int hrc_rerank(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
-               const int32_t* d_cand_ids, int n_cand, const void* d_queries, int n_queries, int lq, int k,
-               float* d_scores_ws, uint64_t* d_keys_ws, int32_t* d_pos_out, int32_t* d_ids_out, float* d_scores_out,
-               int path, void* stream) {
-  HRC_REQUIRE(n_cand >= 0 && n_cand <= 8192, "rerank: n_cand=%d not in [0, 8192]", n_cand);
-  HRC_REQUIRE(k >= 0 && k <= n_cand, "rerank: k=%d must be in [0, n_cand]", k);
-  HRC_REQUIRE(n_queries == 0 || k == 0 || (d_cand_ids != nullptr && d_scores_ws != nullptr && d_keys_ws != nullptr),
-              "rerank: null buffer");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (int rc = maxsim_dispatch(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_cand, d_queries, n_queries, lq,
-                               d_scores_ws, path, st))
-    return rc;
-  if (int rc = launch_topk(d_scores_ws, nullptr, n_cand, n_queries, k, 0, d_keys_ws, nullptr, 0, st)) return rc;
-  return launch_rerank_unpack(d_keys_ws, k, n_queries, d_cand_ids, n_cand, d_pos_out, d_ids_out, d_scores_out, st);
 }
 
 size_t hrc_topk_workspace_bytes(int64_t n, int n_rows, int k) { return topk_workspace_bytes(n, n_rows, k); }
@@ -319,6 +463,11 @@ int hrc_rrf_fuse(const int32_t* d_ids_a, int n_a, const int32_t* d_ids_b, int n_
 int hrc_synth_tokens(void* d_tokens_out, int64_t token_begin, int64_t n_tokens, uint64_t seed, void* stream) {
   if (int rc = check_device()) return rc;
   return launch_synth(d_tokens_out, token_begin, n_tokens, seed, static_cast<cudaStream_t>(stream));
+}
+
+int hrc_read_probe(const void* d_buf, size_t bytes, uint32_t* d_out, void* stream) {
+  if (int rc = check_device()) return rc;
+  return launch_read_probe(d_buf, bytes, d_out, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -16,6 +16,9 @@ namespace hrc {
 // ---------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// hrc_trace_*: when enabled, the scoring kernels' launches are bracketed by CUDA events on their stream
+void trace_begin(cudaStream_t stream);
+void trace_end(cudaStream_t stream);
 
 #define HRC_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \

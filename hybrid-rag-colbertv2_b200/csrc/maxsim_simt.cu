@@ -146,9 +146,11 @@ int launch_maxsim_simt(const void* d_tokens, const int64_t* d_offsets, int64_t n
   HRC_REQUIRE(n_items <= 0x7fffffffLL, "simt path: too many items (%lld)", (long long)n_items);
   HRC_REQUIRE(n_queries <= 65535, "simt path: too many queries per launch (%d)", n_queries);
   dim3 grid((unsigned)n_items, (unsigned)n_queries);
+  trace_begin(stream);
   maxsim_simt_kernel<<<grid, kSimtThreads, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(d_tokens), d_offsets, n_docs, d_cand_ids, int(n_items),
       static_cast<const __nv_bfloat16*>(d_queries), lq, d_scores);
+  trace_end(stream);
   count_launch();
   HRC_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -8,7 +8,7 @@
 // so a fused score is the left-to-right fp64 sum of 1/(k+rank) over the id's occurrences in
 // concat(a, b), and equal scores keep first-occurrence order (an fp32 or re-ordered
 // version flips adjacent results).  One CTA per row; positions are compared all-pairs in shared
-// memory (lists are <= 4096 long, 200 in the reference), which keeps the arithmetic order exact.
+// memory (lists are <= 16384 long, 200 in the reference), which keeps the arithmetic order exact.
 #include "hrc_common.cuh"
 
 namespace hrc {
@@ -16,7 +16,7 @@ namespace hrc {
 namespace {
 
 constexpr int kRrfThreads = 256;
-constexpr int kRrfMax = 4096;
+constexpr int kRrfMax = 16384;   // 13 bytes of shared memory per entry
 
 __global__ void __launch_bounds__(kRrfThreads)
 rrf_fuse_kernel(const int32_t* __restrict__ ids_a, int n_a, const int32_t* __restrict__ ids_b, int n_b,

@@ -51,7 +51,37 @@ synth_tokens_kernel(__nv_bfloat16* __restrict__ out, int64_t token_begin, int64_
   }
 }
 
+// Read-bandwidth probe (bench utility): every thread streams 16-byte loads, four in flight, and folds them into one
+// word so that nothing is optimised away.  Calibrates "what can a pure read reach on this GPU" next to the
+// read+write copy figure in MEASURED_PEAKS.json (BASELINE.md §2 asks for both).
+__global__ void __launch_bounds__(512)
+read_probe_kernel(const uint4* __restrict__ src, int64_t n_vec, uint32_t* __restrict__ out) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  uint32_t acc = 0;
+  for (; i + 3 * stride < n_vec; i += 4 * stride) {
+    const uint4 a = ldg_stream16(src + i), b = ldg_stream16(src + i + stride), c = ldg_stream16(src + i + 2 * stride),
+                d = ldg_stream16(src + i + 3 * stride);
+    acc ^= a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c.x ^ c.y ^ c.z ^ c.w ^ d.x ^ d.y ^ d.z ^ d.w;
+  }
+  for (; i < n_vec; i += stride) {
+    const uint4 a = ldg_stream16(src + i);
+    acc ^= a.x ^ a.y ^ a.z ^ a.w;
+  }
+  acc = __reduce_xor_sync(0xffffffffu, acc);
+  if ((threadIdx.x & 31) == 0 && acc == 0x9e3779b9u) atomicXor(out, acc);   // practically never taken; keeps the loads live
+}
+
 }  // namespace
+
+int launch_read_probe(const void* d_buf, size_t bytes, uint32_t* d_out, cudaStream_t stream) {
+  HRC_REQUIRE((reinterpret_cast<uintptr_t>(d_buf) & 15) == 0 && d_out != nullptr, "read_probe: buffer must be 16-byte aligned");
+  if (bytes < 16) return 0;
+  read_probe_kernel<<<148 * 8, 512, 0, stream>>>(static_cast<const uint4*>(d_buf), int64_t(bytes / 16), d_out);
+  count_launch();
+  HRC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int launch_synth(void* d_out, int64_t token_begin, int64_t n_tokens, uint64_t seed, cudaStream_t stream) {
   if (n_tokens <= 0) return 0;

@@ -1,10 +1,13 @@
 """Host-side mirror of the reference's retrieval classes for the MaxSim hot path.
 
-Same class names, method names, keyword arguments, return shapes and on-disk file as
-local_rag_complete.py (RAGConfig :56-86, JinaColBERTRetriever :715-831, DualIndexer :838-879,
-HybridRetriever :886-1014), so the classes drop into that script unchanged; the arithmetic runs in
-libhrc.so (hand-written sm_100a CUDA) through `_lib`.  There is no CPU fallback: scoring without a
-B200 raises.
+Same class names, method names, keyword arguments and return shapes as local_rag_complete.py
+(RAGConfig :56-86, JinaColBERTRetriever :715-831, DualIndexer :838-879, HybridRetriever :886-1014), so
+the classes drop into that script unchanged; the arithmetic runs in libhrc.so (hand-written sm_100a
+CUDA) through `_lib`.  There is no CPU fallback: scoring without a B200 raises.
+
+On-disk compatibility is ONE-WAY: `load()` reads the reference's dense `index.pt`; what `index()` writes
+is the packed `index.hrc.pt`, which the reference cannot read (and does not mistake for its own file).
+Scores are true MaxSim by default, not the reference's mean-pool cosine: see `install()`.
 """
 from __future__ import annotations
 
@@ -47,6 +50,7 @@ class RAGConfig:
     # compute (cosine of mean-pooled vectors) — for reproducing the reference's own rankings.
     score_mode: str = "maxsim"
     maxsim_path: int = _lib.PATH_AUTO
+    reference_compatible_index: bool = False   # also write a dense fp32 index.pt the reference's load() accepts
 
 
 _ENCODER_NOTICE_SHOWN = False
@@ -81,7 +85,7 @@ class JinaColBERTRetriever:
         self.model = encoder if encoder is not None else self._default_encoder()
         self.store: Optional[PackedStore] = None
         self.corpus: Optional[List[str]] = None
-        self._buffers = _lib.SearchBuffers()
+        self._workspace = _lib.Workspace()          # device scratch, grown on demand and reused: no per-call allocation
         self._host_search = _lib.HostSearch()
 
     def _default_encoder(self):
@@ -148,20 +152,44 @@ class JinaColBERTRetriever:
             self._save_index()
 
     def _save_index(self) -> None:
+        """Persist the packed store as `<colbert_index_path>/index.hrc.pt`.
+
+        NOT the reference's `index.pt`: its `load()` (:748-753) would accept a packed [T, 128] tensor under
+        'embeddings' without complaint and `_maxsim_score` would then treat it as ONE document (:816-817), so the
+        packed layout lives under its own file name and the reference fails loudly (FileNotFoundError) instead.
+        With `config.reference_compatible_index = True` a dense fp32 `index.pt` the reference CAN load is written as
+        well ({'embeddings': [N, Ld_max, 128], 'corpus'} plus 'lengths'; documents shorter than Ld_max are zero-padded,
+        which the reference — it keeps no mask — would pool as real tokens, so this is exact only for equal lengths).
+        """
         os.makedirs(self.config.colbert_index_path, exist_ok=True)
         torch.save({
-            'embeddings': self.store.tokens.cpu(),
-            'corpus': self.corpus,
+            'format': 'hrc-packed-v2',
+            'tokens': self.store.tokens.cpu(),
             'offsets': self.store.offsets.cpu(),
-            'format': 'hrc-packed-v1',
-        }, os.path.join(self.config.colbert_index_path, 'index.pt'))
+            'doc_id_base': int(self.store.doc_id_base),
+            'corpus': self.corpus,
+        }, os.path.join(self.config.colbert_index_path, 'index.hrc.pt'))
+        if getattr(self.config, "reference_compatible_index", False):
+            dense, lengths = self.store.to_dense()
+            torch.save({'embeddings': dense, 'corpus': self.corpus, 'lengths': lengths},
+                       os.path.join(self.config.colbert_index_path, 'index.pt'))
 
     def load(self) -> None:
-        """Load index from disk (:748-753).  Reads both the reference's dense file and the packed one."""
+        """Load index from disk (:748-753): the packed `index.hrc.pt` if present, else the reference's dense
+        `index.pt` ({'embeddings': [N, Ld, D] fp32, 'corpus'}, optional 'lengths')."""
+        packed_file = os.path.join(self.config.colbert_index_path, 'index.hrc.pt')
+        if os.path.exists(packed_file):
+            data = torch.load(packed_file, map_location="cpu")
+            if data.get('format') != 'hrc-packed-v2':
+                raise ValueError(f"{packed_file}: unknown format {data.get('format')!r}")
+            self.store = PackedStore.from_packed(data['tokens'], data['offsets'], device=self.device,
+                                                 doc_id_base=int(data.get('doc_id_base', 0)))
+            self.corpus = data['corpus']
+            return
         index_file = os.path.join(self.config.colbert_index_path, 'index.pt')
         data = torch.load(index_file, map_location="cpu")
         emb = data['embeddings']
-        if data.get('format') == 'hrc-packed-v1':
+        if data.get('format') == 'hrc-packed-v1':     # files written by the first release of this package
             self.store = PackedStore.from_packed(emb, data['offsets'], device=self.device)
         else:  # reference layout: dense fp32 [N, Ld, D], no mask (SURVEY.md F5)
             self.store = PackedStore.from_dense(emb, data.get('lengths'), device=self.device)
@@ -185,7 +213,8 @@ class JinaColBERTRetriever:
     def _score_store(self, store: PackedStore, q: torch.Tensor, mode: Optional[str] = None) -> torch.Tensor:
         if self._literal(mode):
             return _lib.meanpool_cosine_scores(store.tokens, store.offsets, q)
-        s = _lib.maxsim_scores(store.tokens, store.offsets, q, path=_knob(self.config, "maxsim_path"))
+        s = _lib.maxsim_scores(store.tokens, store.offsets, q, path=_knob(self.config, "maxsim_path"),
+                               workspace=self._workspace)
         return self._finish_scores(s, q.shape[1])
 
     def score_embeddings(self, query_embeddings: torch.Tensor) -> torch.Tensor:
@@ -194,8 +223,17 @@ class JinaColBERTRetriever:
         return self._score_store(self.store, self._prep_queries(query_embeddings))
 
     def search_keys(self, query_embeddings: torch.Tensor, k: int) -> torch.Tensor:
-        """Sorted top-k (score, GLOBAL doc id) keys per query: int64 [Bq, min(k, N)] on the device."""
+        """Sorted top-k (score, GLOBAL doc id) keys per query: int64 [Bq, min(k, N)] on the device (k <= 2048)."""
         return self._search(query_embeddings, k, unpack=False)[0]
+
+    @staticmethod
+    def _sort_large(scores: torch.Tensor, k: int, id_base: int = 0):
+        """k beyond the selection kernels' limit (HRC_MAX_TOPK = 2048; the reference's torch.topk / argsort take any
+        k, :767,:789): a full stable device sort of the score rows, which gives the kernels' order exactly (score
+        descending, NaN as -inf, ties to the lower id).  Rare, off the measured path."""
+        clean = torch.where(torch.isnan(scores), torch.full_like(scores, float("-inf")), scores)
+        val, idx = torch.sort(clean, dim=-1, descending=True, stable=True)
+        return (idx[:, :k] + id_base).to(torch.int32).contiguous(), val[:, :k].contiguous()
 
     def _search(self, query_embeddings: torch.Tensor, k: int, unpack: bool):
         self._require_store()
@@ -204,12 +242,20 @@ class JinaColBERTRetriever:
         if k_eff <= 0:
             z = torch.zeros((q.shape[0], 0), dtype=torch.int64, device=self.device)
             return z, z.to(torch.int32), z.to(torch.float32)
+        if k_eff > _lib.MAX_TOPK:
+            if not unpack:
+                raise _lib.HrcError(f"search_keys: k={k_eff} exceeds HRC_MAX_TOPK={_lib.MAX_TOPK}")
+            raw = (_lib.meanpool_cosine_scores(self.store.tokens, self.store.offsets, q) if self._literal() else
+                   _lib.maxsim_scores(self.store.tokens, self.store.offsets, q, path=_knob(self.config, "maxsim_path"),
+                                      workspace=self._workspace))
+            ids, sc = self._sort_large(raw, k_eff, self.store.doc_id_base)
+            return None, ids, sc
         if self._literal():
             keys = _lib.topk(self._score_store(self.store, q), k_eff, id_base=self.store.doc_id_base)
             ids, sc = _lib.keys_unpack(keys) if unpack else (None, None)
             return keys, ids, sc
         return _lib.search(self.store.tokens, self.store.offsets, q, k_eff, id_base=self.store.doc_id_base,
-                           path=_knob(self.config, "maxsim_path"), buffers=self._buffers, unpack=unpack)
+                           path=_knob(self.config, "maxsim_path"), workspace=self._workspace, unpack=unpack)
 
     def search_embeddings(self, query_embeddings: torch.Tensor, k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
         """(doc ids int32 [Bq, k'], scores fp32 [Bq, k']) with k' = min(k, N), best first."""
@@ -220,20 +266,24 @@ class JinaColBERTRetriever:
 
     search_batch = search_embeddings
 
-    def search_host(self, query_embeddings: torch.Tensor, k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
+    def search_host(self, query_embeddings: torch.Tensor, k: int = 10, copy: bool = True
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
         """End-to-end search from a HOST query embedding (what an encoder hands over) to HOST results: fp32 CPU
-        [Lq, 128] or [Bq, Lq, 128] in, (doc ids int32, scores fp32) CPU tensors out, one C call (hrc_search_host)."""
+        [Lq, 128] or [Bq, Lq, 128] in, (doc ids int32, scores fp32) CPU tensors out, one C call (hrc_search_host).
+
+        The returned tensors belong to the caller.  `copy=False` skips the final host copy and returns this
+        retriever's pinned staging buffers instead, which the NEXT search_host call overwrites."""
         self._require_store()
         q = _as_query_batch(query_embeddings)
-        if q.is_cuda or self._literal():
+        k_eff = min(int(k), self.store.n_docs)
+        if q.is_cuda or self._literal() or k_eff > _lib.MAX_TOPK:
             ids, sc = self.search_embeddings(q, k)
             return ids.cpu(), sc.cpu()
         q = q.to(torch.float32).contiguous()
-        k_eff = min(int(k), self.store.n_docs)
         if k_eff <= 0:
             return torch.zeros((q.shape[0], 0), dtype=torch.int32), torch.zeros((q.shape[0], 0))
         ids, sc = self._host_search(self.store.tokens, self.store.offsets, q, k_eff, id_base=self.store.doc_id_base,
-                                    path=_knob(self.config, "maxsim_path"))
+                                    path=_knob(self.config, "maxsim_path"), copy=copy)
         return ids, self._finish_scores(sc, q.shape[1])
 
     def rerank_ids(self, query_embeddings: torch.Tensor, candidate_ids: torch.Tensor, k: int = 10
@@ -257,8 +307,13 @@ class JinaColBERTRetriever:
             cs = torch.where(ok, cs, torch.full_like(cs, float("-inf"))).contiguous()
             pos, top_scores = _lib.keys_unpack(_lib.topk(cs, k_eff))
             return pos, torch.gather(cand, 1, pos.clamp_min(0).long()), top_scores
+        if k_eff > _lib.MAX_TOPK:   # see _sort_large
+            cs = _lib.maxsim_scores_ids(self.store.tokens, self.store.offsets, cand, q,
+                                        path=_knob(self.config, "maxsim_path"), workspace=self._workspace)
+            pos, top_scores = self._sort_large(cs, k_eff)
+            return pos, torch.gather(cand, 1, pos.long()), self._finish_scores(top_scores, q.shape[1])
         pos, doc_ids, top_scores, _ = _lib.rerank(self.store.tokens, self.store.offsets, cand, q, k_eff,
-                                                  path=_knob(self.config, "maxsim_path"))
+                                                  path=_knob(self.config, "maxsim_path"), workspace=self._workspace)
         return pos, doc_ids, self._finish_scores(top_scores, q.shape[1])
 
     def _require_store(self) -> None:
@@ -293,8 +348,9 @@ class JinaColBERTRetriever:
         tmp = self._pack(doc_embeddings)
         q = self._prep_queries(query_embedding)
         scores = self._score_store(tmp, q)
-        keys = _lib.topk(scores, min(int(k), tmp.n_docs))
-        pos, top = _lib.keys_unpack(keys)
+        k_eff = min(int(k), tmp.n_docs)
+        pos, top = (self._sort_large(scores, k_eff) if k_eff > _lib.MAX_TOPK else
+                    _lib.keys_unpack(_lib.topk(scores, k_eff)))
         results = []
         for rank, (idx, score) in enumerate(zip(pos[0].tolist(), top[0].tolist())):
             results.append({
@@ -319,8 +375,14 @@ class JinaColBERTRetriever:
         return self._score_store(tmp, q, mode).squeeze()
 
 
-def install(module, classes: Sequence[str] = ("JinaColBERTRetriever",)) -> None:
+def install(module, classes: Sequence[str] = ("JinaColBERTRetriever",), score_mode: Optional[str] = None) -> None:
     """Drop this implementation into a loaded `local_rag_complete` module WITHOUT editing it.
+
+    BEHAVIOUR NOTE: by default the installed class scores with true MaxSim (what the reference's docstring :807-812
+    and BASELINE.json's north_star define), while the reference's own `_maxsim_score` body computes the cosine of
+    mean-pooled vectors (:821-829, "Simplified: just use mean pooling for now").  Scores and rankings therefore
+    differ from the unmodified reference unless `score_mode="reference_literal"` is passed here (or set on the
+    config), which reproduces the reference's numbers (pinned by tests/golden/literal_*.npz).
 
     The reference's `DualIndexer.__init__` constructs `JinaColBERTRetriever(config)` through the module's global
     name (:844), and `HybridRetriever` only calls `search(query=, k=)` / `rerank(query=, documents=, k=)` on it
@@ -332,6 +394,10 @@ def install(module, classes: Sequence[str] = ("JinaColBERTRetriever",)) -> None:
         hrc.install(lrc)                       # or hrc.install(lrc, ("JinaColBERTRetriever", "DualIndexer", "HybridRetriever"))
     """
     mine = {"JinaColBERTRetriever": JinaColBERTRetriever, "DualIndexer": DualIndexer, "HybridRetriever": HybridRetriever}
+    if score_mode is not None:
+        if score_mode not in ("maxsim", "reference_literal"):
+            raise ValueError(f"install: score_mode must be 'maxsim' or 'reference_literal', got {score_mode!r}")
+        _KNOB_DEFAULTS["score_mode"] = score_mode      # the reference's RAGConfig has no such field: default for it
     for name in classes:
         if name not in mine:
             raise ValueError(f"install: unknown class {name!r}")
@@ -394,7 +460,7 @@ class HybridRetriever:
         self._chunk_fetcher = chunk_fetcher
         self.verbose = verbose
         self.last_timings: Dict[str, float] = {}
-        self._hybrid_buffers = _lib.HybridBuffers()
+        self._hybrid_workspace = _lib.Workspace()
 
     def _log(self, msg: str) -> None:
         if self.verbose:
@@ -491,9 +557,9 @@ class HybridRetriever:
         cand = torch.tensor([[c['chunk_id'] - base for c in chunks]], dtype=torch.int32)
         pos, _, scores = retr.rerank_ids(q, cand, k=top_k)
         final_results = []
-        for rank, (idx, score) in enumerate(zip(pos[0].tolist(), scores[0].tolist())):
-            if idx < 0:
-                continue
+        for idx, score in zip(pos[0].tolist(), scores[0].tolist()):
+            if idx < 0 or score == float("-inf"):
+                continue      # a candidate whose chunk_id this store does not hold scores -inf: not a result
             original_chunk = chunks[idx]
             final_results.append({
                 'chunk_id': original_chunk['chunk_id'],
@@ -503,7 +569,7 @@ class HybridRetriever:
                 'has_images': original_chunk.get('has_images', False),
                 'metadata': original_chunk['metadata'],
                 'score': float(score),
-                'rank': rank + 1,
+                'rank': len(final_results) + 1,
             })
         return final_results
 
@@ -530,7 +596,7 @@ class HybridRetriever:
         ids, scores = _lib.hybrid_retrieve(retr.store.tokens, retr.store.offsets, q, a, colbert_k=colbert_k,
                                            rrf_k=_knob(cfg, "rrf_k"), n_candidates=n_cand, final_k=int(k_final),
                                            id_base=retr.store.doc_id_base, path=_knob(cfg, "maxsim_path"),
-                                           buffers=self._hybrid_buffers)
+                                           workspace=self._hybrid_workspace)
         return ids, retr._finish_scores(scores, q.shape[1])
 
     def _retrieve_batch_staged(self, query_embeddings: torch.Tensor, bm25_ids: torch.Tensor, k_final: int

@@ -46,13 +46,18 @@ class ShardedSearcher:
         gathered = all_gather_keys(local, k, self.group)              # [Bq, world * k]
         return _lib.topk_merge(gathered, k)                           # [Bq, k] sorted, 0 = empty
 
+    def _lq(self, query_embeddings: torch.Tensor) -> int:
+        return int(query_embeddings.shape[-2])
+
     def search_embeddings(self, query_embeddings: torch.Tensor, k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
         ids, scores = _lib.keys_unpack(self.search_keys(query_embeddings, k))
-        return ids, scores
+        return ids, self.retriever._finish_scores(scores, self._lq(query_embeddings))   # honours score_reduction="mean"
 
-    def search_host(self, query_embeddings: torch.Tensor, k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
+    def search_host(self, query_embeddings: torch.Tensor, k: int = 10, copy: bool = True
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Host query embedding (fp32 CPU [Bq, Lq, 128], ideally pinned) -> host (ids, scores): asynchronous H2D,
-        the sharded search, asynchronous D2H into pinned buffers, ONE stream synchronisation."""
+        the sharded search, asynchronous D2H into pinned buffers, ONE stream synchronisation.  The returned tensors
+        belong to the caller; copy=False returns the pinned staging buffers, which the next call overwrites."""
         dev = self.retriever.device
         q = query_embeddings if query_embeddings.dim() == 3 else query_embeddings.unsqueeze(0)
         ids, scores = _lib.keys_unpack(self.search_keys(q.to(dev, non_blocking=True), k))
@@ -62,4 +67,5 @@ class ShardedSearcher:
         self._pinned[0].copy_(ids, non_blocking=True)
         self._pinned[1].copy_(scores, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
-        return self._pinned
+        out_ids, out_sc = (self._pinned[0].clone(), self._pinned[1].clone()) if copy else self._pinned
+        return out_ids, self.retriever._finish_scores(out_sc, self._lq(q))

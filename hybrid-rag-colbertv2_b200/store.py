@@ -136,6 +136,15 @@ class PackedStore:
             tokens = _as_bf16_rows(embeddings.to("cpu")[mask])
         return cls.from_packed(tokens, off, device, allow_empty=allow_empty)
 
+    def to_dense(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(fp32 [N, Ld_max, 128] zero-padded, int64 lengths [N]) on the CPU — the reference's layout (:735-739)."""
+        lens = self.lengths().cpu()
+        n, ld = self.n_docs, int(lens.max()) if self.n_docs else 0
+        dense = torch.zeros((n, ld, DIM), dtype=torch.float32)
+        mask = torch.arange(ld).unsqueeze(0) < lens.unsqueeze(1)
+        dense[mask] = self.tokens.float().cpu()
+        return dense, lens
+
     # ---- sharding ----------------------------------------------------------------------------
     def shard(self, rank: int, world_size: int, device: Optional[Union[str, torch.device]] = None) -> "PackedStore":
         d0, d1 = shard_doc_ranges(self.offsets, world_size)[rank]

@@ -40,6 +40,7 @@ extern "C" {
 #define HRC_PATH_AUTO 0
 #define HRC_PATH_SIMT 1        /* coalesced 16-byte loads + warp-shuffle reduction (CUDA cores) */
 #define HRC_PATH_TC   2        /* TMA + tcgen05.mma + TMEM, fused segmented max/sum epilogue     */
+#define HRC_PATH_TC_M64 3      /* as TC, but 1-2 queries run an M=64 MMA (half the tensor work)  */
 
 /* Library / ABI version (major*10000 + minor*100 + patch). */
 int hrc_version(void);
@@ -52,6 +53,34 @@ const char* hrc_last_error(void);
 uint64_t hrc_launch_count(void);
 
 /*
+ * Every mbarrier wait inside the tensor-core kernels traps after this many milliseconds without progress, so that a
+ * protocol bug faults instead of hanging the GPU (default 20000; 0 disables, e.g. under a debugger, compute-sanitizer
+ * or GPU time-slicing).  Process-wide.  The library reads no environment variables.
+ */
+void hrc_set_watchdog_ms(uint64_t ms);
+
+/*
+ * Kernel trace (the reference's only observability is wall-clock stage timing, local_rag_complete.py:902-933; this
+ * is the device-side counterpart).  After hrc_trace_enable(capacity) every launch of a scoring kernel (tensor-core or
+ * CUDA-core MaxSim) is bracketed by CUDA events on its stream, up to `capacity` launches; hrc_trace_collect waits
+ * for them, writes the launches' device times in milliseconds (launch order) and returns how many it wrote (-1 on
+ * error), resetting the trace.  hrc_trace_enable(0) switches tracing off.  Process-wide; bench.py uses it to time the
+ * dominant kernel INSIDE the timed steps.
+ */
+int hrc_trace_enable(int capacity);
+int hrc_trace_collect(float* ms_out, int max_n);
+
+/*
+ * TMA descriptors (CUtensorMap) depend only on a buffer's address and extents, so the library keeps the ones it has
+ * encoded in a small cache and never encodes on the launch path twice for the same store / query buffer.
+ * hrc_store_register pre-encodes the maps of a token store (optional: the first scoring call does it otherwise);
+ * hrc_store_release drops them (call it before freeing the store).  Replaces: the lifetime of
+ * `self.corpus_embeddings`, local_rag_complete.py:725,735,752.
+ */
+int hrc_store_register(const void* d_tokens, int64_t total_tokens);
+void hrc_store_release(const void* d_tokens);
+
+/*
  * MaxSim scores of every query against every document of the packed store.
  *   d_scores[q * n_docs + d] = sum_{i < lq} max_{t in doc d} <Q[q][i], tokens[t]>      (fp32 accumulate)
  * Replaces: JinaColBERTRetriever._maxsim_score, local_rag_complete.py:802-831 (as its docstring
@@ -59,23 +88,26 @@ uint64_t hrc_launch_count(void);
  *   d_queries : bf16 [n_queries][lq][128]
  *   path      : HRC_PATH_*; AUTO picks TC when lq <= HRC_TC_MAX_LQ * HRC_TC_MAX_SLOTS (a query longer than 32
  *               tokens is scored as ceil(lq / 32) slots whose partial scores are summed in slot order).
+ *   d_workspace : hrc_maxsim_workspace_bytes(n_docs, n_queries, lq) bytes of scratch (0 bytes, and NULL allowed, when
+ *               lq <= 32): the per-slot partial scores of long queries.  No call allocates device memory.
  * An empty document (length 0) scores -inf.
  */
+size_t hrc_maxsim_workspace_bytes(int64_t n_items, int n_queries, int lq);
 int hrc_maxsim_scores(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs,
                       int64_t total_tokens, const void* d_queries, int n_queries, int lq,
-                      float* d_scores, int path, void* stream);
+                      float* d_scores, int path, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /*
  * MaxSim scores of query q against its own candidate list (the rerank shape):
  *   d_scores[q * n_cand + j] = maxsim(Q[q], doc d_cand_ids[q * n_cand + j])
  * Replaces: JinaColBERTRetriever.rerank's scoring step, local_rag_complete.py:782-786 (the
  * reference re-encodes the candidate texts; here the stored token embeddings are gathered by id).
- * Candidate ids < 0 or >= n_docs score -inf.
+ * Candidate ids < 0 or >= n_docs score -inf.  d_workspace: hrc_maxsim_workspace_bytes(n_cand, n_queries, lq).
  */
 int hrc_maxsim_scores_ids(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs,
                           int64_t total_tokens, const int32_t* d_cand_ids, int n_cand,
                           const void* d_queries, int n_queries, int lq, float* d_scores,
-                          int path, void* stream);
+                          int path, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /*
  * The reference's `_maxsim_score` EXACTLY AS CODED, local_rag_complete.py:821-829 — the cosine of the
@@ -91,14 +123,15 @@ int hrc_meanpool_cosine_scores(const void* d_tokens, const int64_t* d_offsets, i
 /*
  * Fused search: MaxSim of every query against the whole store, per-query top-k, optional unpacking —
  * the body of JinaColBERTRetriever.search (local_rag_complete.py:764-775) in one call.
- *   d_scores_ws  : fp32 [n_queries][n_docs] scratch (holds the full score matrix on return)
- *   d_topk_ws    : hrc_topk_workspace_bytes(n_docs, n_queries, k) bytes of scratch
+ *   d_workspace  : hrc_search_workspace_bytes(n_docs, n_queries, lq, k) bytes of scratch, 256-B aligned
  *   d_keys_out   : uint64 [n_queries][k]; d_ids_out / d_scores_out optional int32 / fp32 [n_queries][k]
+ * k <= HRC_MAX_TOPK and k <= n_docs.
  */
+size_t hrc_search_workspace_bytes(int64_t n_docs, int n_queries, int lq, int k);
 int hrc_search(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
-               const void* d_queries, int n_queries, int lq, int k, int32_t id_base, float* d_scores_ws,
-               void* d_topk_ws, size_t topk_ws_bytes, uint64_t* d_keys_out, int32_t* d_ids_out,
-               float* d_scores_out, int path, void* stream);
+               const void* d_queries, int n_queries, int lq, int k, int32_t id_base, void* d_workspace,
+               size_t workspace_bytes, uint64_t* d_keys_out, int32_t* d_ids_out, float* d_scores_out, int path,
+               void* stream);
 
 /*
  * End-to-end search with HOST buffers — what JinaColBERTRetriever.search does between "the encoder returned the
@@ -118,16 +151,18 @@ int hrc_search_host(const void* d_tokens, const int64_t* d_offsets, int64_t n_do
 /*
  * Fused rerank: MaxSim of query q against its candidate list, sorted top-k — the body of
  * JinaColBERTRetriever.rerank (local_rag_complete.py:786-798) on stored embeddings.
- *   d_cand_ids   : int32 [n_queries][n_cand] (n_cand <= 8192)
- *   d_scores_ws  : fp32 [n_queries][n_cand] scratch (candidate scores on return)
- *   d_pos_out    : int32 [n_queries][k] position in the candidate list ("result_index"), -1 = empty
- *   d_ids_out    : int32 [n_queries][k] the candidate's document id, optional
- *   d_scores_out : fp32  [n_queries][k]
+ *   d_cand_ids        : int32 [n_queries][n_cand]
+ *   d_workspace       : hrc_rerank_workspace_bytes(n_cand, n_queries, lq, k) bytes of scratch, 256-B aligned
+ *   d_pos_out         : int32 [n_queries][k] position in the candidate list ("result_index"), -1 = empty
+ *   d_ids_out         : int32 [n_queries][k] the candidate's document id, optional
+ *   d_scores_out      : fp32  [n_queries][k]
+ *   d_cand_scores_out : optional fp32 [n_queries][n_cand], the score of every candidate
  */
+size_t hrc_rerank_workspace_bytes(int n_cand, int n_queries, int lq, int k);
 int hrc_rerank(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
                const int32_t* d_cand_ids, int n_cand, const void* d_queries, int n_queries, int lq, int k,
-               float* d_scores_ws, uint64_t* d_keys_ws, int32_t* d_pos_out, int32_t* d_ids_out,
-               float* d_scores_out, int path, void* stream);
+               void* d_workspace, size_t workspace_bytes, int32_t* d_pos_out, int32_t* d_ids_out,
+               float* d_scores_out, float* d_cand_scores_out, int path, void* stream);
 
 /*
  * The device part of HybridRetriever.retrieve (local_rag_complete.py:894-935) in one call, for a batch of queries:
@@ -139,9 +174,10 @@ int hrc_rerank(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, i
  *   d_workspace  : hrc_hybrid_retrieve_workspace_bytes(...) bytes of device scratch, 256-B aligned
  *   d_ids_out    : int32 [n_queries][final_k] GLOBAL ids, best first (-1 = fewer candidates than final_k)
  *   d_scores_out : fp32  [n_queries][final_k] MaxSim scores
- * Requires 1 <= colbert_k <= n_docs, 1 <= final_k <= n_candidates <= 8192, n_bm25 + colbert_k <= 4096.
+ * Requires 1 <= colbert_k <= n_docs, 1 <= final_k <= n_candidates, n_bm25 + colbert_k <= 16384.
  */
-size_t hrc_hybrid_retrieve_workspace_bytes(int64_t n_docs, int n_queries, int colbert_k, int n_candidates, int final_k);
+size_t hrc_hybrid_retrieve_workspace_bytes(int64_t n_docs, int n_queries, int lq, int colbert_k, int n_candidates,
+                                           int final_k);
 int hrc_hybrid_retrieve(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
                         const void* d_queries, int n_queries, int lq, const int32_t* d_bm25_ids, int n_bm25,
                         int colbert_k, int rrf_k, int n_candidates, int final_k, int32_t id_base, void* d_workspace,
@@ -186,7 +222,7 @@ int hrc_keys_unpack(const uint64_t* d_keys, int64_t n, int32_t* d_ids_out, float
  *   d_ids_out    : int32  [n_rows][top_n]  fused ids, best first (-1 padded)
  *   d_scores_out : double [n_rows][top_n]  fused scores (0 padded)
  *   d_counts_out : int32  [n_rows]         number of distinct ids (may exceed top_n), optional
- * n_a + n_b <= 4096.
+ * n_a + n_b <= 16384.
  */
 int hrc_rrf_fuse(const int32_t* d_ids_a, int n_a, const int32_t* d_ids_b, int n_b, int n_rows,
                  int rrf_k, int top_n, int32_t* d_ids_out, double* d_scores_out,
@@ -199,6 +235,13 @@ int hrc_rrf_fuse(const int32_t* d_ids_a, int n_a, const int32_t* d_ids_b, int n_
  */
 int hrc_synth_tokens(void* d_tokens_out, int64_t token_begin, int64_t n_tokens, uint64_t seed,
                      void* stream);
+
+/*
+ * Read-bandwidth probe (bench utility, not on the query path): streams `bytes` of device memory once with 16-byte
+ * loads and folds them into *d_out (a uint32 the caller zeroes).  bench.py times it over the resident corpus to
+ * state the MaxSim kernel's HBM fraction against a pure-READ peak as well as the read+write copy peak.
+ */
+int hrc_read_probe(const void* d_buf, size_t bytes, uint32_t* d_out, void* stream);
 
 #ifdef __cplusplus
 }

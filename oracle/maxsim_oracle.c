@@ -6,8 +6,10 @@
  * Restated from /root/reference/local_rag_complete.py:
  *   oracle_maxsim_scores   docstring :807-812 ("for each query token, max similarity over the document's
  *                          tokens"), summed over query tokens (BASELINE.json north_star); fp32, index order.
- *                          PARITY UNPINNED BY THE REFERENCE (its body :819-829 is a mean-pool cosine; it
- *                          ships no tests) — cross-checked against the Python oracle and the golden fixtures.
+ *                          PARITY ONLY PARTLY PINNED BY THE REFERENCE (its body :819-829 is a mean-pool cosine; it
+ *                          ships no tests): bit-equal to the unmodified reference where that cosine IS MaxSim
+ *                          (tests/golden/maxsim_pin.npz), within 2e-6 of float64 known answers
+ *                          (maxsim_kat_f64.npz), cross-checked against the Python oracle.
  *   oracle_literal_scores  the BODY of _maxsim_score as coded, :821-829: cosine of the mean-pooled token vectors
  *                          (fp32 accumulation in index order; torch reduces in a different order, so this agrees
  *                          with the reference's vectors to ~1e-6, not bit for bit).  PINNED on

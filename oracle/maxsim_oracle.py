@@ -14,10 +14,15 @@ What is restated, and how it is pinned
   * maxsim_scores / maxsim_dense — TRUE MaxSim as the reference's docstring (:807-812) and
     BASELINE.json's north_star define it: per query token, max over the document's tokens, summed over
     query tokens, fp32 arithmetic on the same bf16-rounded inputs the kernels see.
-    PARITY UNPINNED BY THE REFERENCE: the reference's own function does not compute MaxSim (SURVEY.md
-    F2/F3) and it ships no tests or golden vectors, so no reference output exists for this quantity.
-    It is cross-checked instead against an independent pure-loop implementation (maxsim_naive) and
-    against the dense einsum form on the committed fixtures.
+    PARITY ONLY PARTLY PINNED BY THE REFERENCE: the reference's own function does not compute MaxSim in
+    general and it ships no tests or golden vectors, so no reference output exists for
+    MaxSim on general inputs.  What IS pinned: on the degenerate shapes where its mean-pool cosine equals
+    MaxSim (identical query tokens, identical document tokens, exactly unit-norm dyadic rows) the
+    unmodified reference's outputs (tests/golden/maxsim_pin.npz, made by make_golden.py) are reproduced
+    bit for bit — the dot product, the max over document tokens and the sum over query tokens.  General
+    inputs are anchored on float64 known answers computed with plain numpy loops
+    (tests/golden/maxsim_kat_f64.npz, make_kat.py), an independent pure-loop implementation
+    (maxsim_naive), the plain-C restatement (maxsim_oracle.c) and the dense einsum form.
 All arithmetic the reference delegates to torch (unpinned `torch>=2.0.0`, requirements.txt:8) is done
 here with the installed torch 2.11 CPU kernels, TF32 off.
 """

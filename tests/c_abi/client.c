@@ -38,11 +38,11 @@ int main(void) {
   size_t ws_bytes = hrc_topk_workspace_bytes(N_DOCS, NQ, K);
   CK(cudaMalloc(&d_ws, ws_bytes ? ws_bytes : 256));
   CK(cudaMemcpy(d_off, off, sizeof(int64_t) * (N_DOCS + 1), cudaMemcpyHostToDevice));
-  if (hrc_version() != 100) { printf("unexpected version %d\n", hrc_version()); return 1; }
+  if (hrc_version() != 200) { printf("unexpected version %d\n", hrc_version()); return 1; }
   HK(hrc_synth_tokens(d_tok, 0, T, 7, NULL));                       /* unit-norm bf16 rows */
   HK(hrc_synth_tokens(d_q, 1000000000ll, (int64_t)NQ * LQ, 7, NULL)); /* queries: other rows of the same generator */
-  HK(hrc_maxsim_scores(d_tok, d_off, N_DOCS, T, d_q, NQ, LQ, d_tc, HRC_PATH_TC, NULL));
-  HK(hrc_maxsim_scores(d_tok, d_off, N_DOCS, T, d_q, NQ, LQ, d_simt, HRC_PATH_SIMT, NULL));
+  HK(hrc_maxsim_scores(d_tok, d_off, N_DOCS, T, d_q, NQ, LQ, d_tc, HRC_PATH_TC, NULL, 0, NULL));
+  HK(hrc_maxsim_scores(d_tok, d_off, N_DOCS, T, d_q, NQ, LQ, d_simt, HRC_PATH_SIMT, NULL, 0, NULL));
   HK(hrc_topk(d_tc, NULL, N_DOCS, NQ, K, 0, d_keys, d_ws, ws_bytes, NULL));
   HK(hrc_keys_unpack(d_keys, (int64_t)NQ * K, d_ids, d_top, NULL));
   CK(cudaDeviceSynchronize());

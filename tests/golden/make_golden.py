@@ -8,6 +8,10 @@ SURVEY.md F4), so those imports are stubbed with MagicMock exactly as in SURVEY.
   literal_maxsim.npz  inputs + outputs of the reference's `_maxsim_score` (what it literally computes)
   literal_bf16.npz    the same on bf16-REPRESENTABLE inputs (so the packed bf16 store loses nothing) plus the
                       reference's own search() / rerank() results on them: pins the GPU "reference_literal" path
+  maxsim_pin.npz      the degenerate shapes on which the reference's mean-pool cosine (:821-829) IS MaxSim — every
+                      query token the same vector, every document token the same vector, all vectors exactly
+                      unit-norm with dyadic coordinates — so `_maxsim_score` of the REAL reference pins the MaxSim
+                      kernels' dot-product core, max over tokens and sum over query tokens bit for bit
   api_shapes.json     search()/rerank()/index()/load() observable behaviour with a fake encoder
   rrf.json            `_reciprocal_rank_fusion` ids + fp64 scores (repr round-trips) incl. tie order
   api_signatures.json the reference's method signatures (names, parameter names, defaults) and RAGConfig fields
@@ -110,6 +114,41 @@ def main():
         rerank_index=np.array([r['result_index'] for r in r5], dtype=np.int64),
         rerank_scores=np.array([r['score'] for r in r5], dtype=np.float64),
     )
+
+    # ---- 1c. where mean-pool cosine == MaxSim: the reference itself pins the MaxSim arithmetic ------------
+    # Rows with coordinates in {0, +-1/2, +-1/4, +-1/8} and squared norm exactly 1 (16a + 4b + c = 64 non-zeros of
+    # each size): every dot product is a multiple of 1/64, exact in fp32 under ANY summation order, the norms are
+    # exactly 1, and the mean of 1, 2 or 4 identical rows is that row.  Then cos(mean q, mean d) == <q, d> ==
+    # (1 / Lq) * sum_i max_t <q_i, d_t>: the reference's function equals MaxSim (mean-reduced) bit for bit.
+    def dyadic_unit_rows(n, gen):
+        combos = [(2, 4, 16), (0, 8, 32), (1, 6, 24), (3, 2, 8), (0, 0, 64), (0, 16, 0), (1, 8, 16), (2, 0, 32)]
+        rows = torch.zeros((n, 128))
+        for i in range(n):
+            a, b, c = combos[int(torch.randint(0, len(combos), (1,), generator=gen))]
+            pos = torch.randperm(128, generator=gen)[: a + b + c]
+            mag = torch.cat([torch.full((a,), 0.5), torch.full((b,), 0.25), torch.full((c,), 0.125)])
+            sign = torch.randint(0, 2, (a + b + c,), generator=gen).float() * 2 - 1
+            rows[i, pos] = mag * sign
+        assert torch.equal(rows.pow(2).sum(-1), torch.ones(n))
+        return rows
+
+    g = torch.Generator().manual_seed(20260107)
+    pin = {}
+    n_pin, bq_pin = 96, 5
+    qrows = dyadic_unit_rows(bq_pin, g)
+    drows = dyadic_unit_rows(n_pin, g)
+    drows[:bq_pin] = qrows                       # a document identical to each query: score exactly 1
+    drows[bq_pin] = -qrows[0]                    # and one exactly opposite: score exactly -1
+    pin["q_rows"], pin["d_rows"] = qrows.numpy(), drows.numpy()
+    exact = (qrows.double() @ drows.double().T).float()            # multiples of 1/64
+    for lq in (1, 2, 4):
+        for ld in (1, 2, 4):
+            qq = qrows[:, None, :].expand(bq_pin, lq, 128).contiguous()
+            dd = drows[:, None, :].expand(n_pin, ld, 128).contiguous()
+            out = R._maxsim_score(qq, dd)                          # the unmodified reference, [Bq, N]
+            assert torch.equal(out, exact), (lq, ld)               # the premise of this fixture
+            pin[f"out_lq{lq}_ld{ld}"] = out.numpy()
+    np.savez_compressed(os.path.join(HERE, "maxsim_pin.npz"), **pin)
 
     # ---- 2. API behaviour with a fake encoder ---------------------------------------------------
     api = {}

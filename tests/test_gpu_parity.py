@@ -13,7 +13,12 @@ from oracle import maxsim_oracle as o
 
 pytestmark = pytest.mark.gpu
 
-RTOL = 1e-3
+RTOL = 1e-3          # the API contract (north_star): fp32-accumulated scores within 1e-3 relative
+# What the kernels are actually held to: <= 10x the largest error observed on the B200 (every check below records its
+# error; tests/conftest.py writes the maxima to gpurun_out/parity_errors.json; profiles/r02_summary.md quotes them).
+# A dropped or doubled document token moves a score by ~1e-3..1e-1 relative, far outside this.
+TIGHT = 2e-5
+OBSERVED = {}        # what -> largest relative error seen (dumped at session end)
 
 
 def _lib():
@@ -34,14 +39,28 @@ def _case(seed, n_docs, min_len, max_len, bq, lq, lens=None):
     return q, tok, off
 
 
-def _assert_scores(got: torch.Tensor, exp: torch.Tensor, what=""):
+def _assert_scores(got: torch.Tensor, exp: torch.Tensor, what="", tol=TIGHT, bucket="maxsim"):
     got = got.float().cpu()
     fin = torch.isfinite(exp)
     assert torch.equal(torch.isfinite(got), fin), f"{what}: finite pattern differs"
     assert torch.equal(got[~fin], exp[~fin]), f"{what}: non-finite values differ"
     scale = exp[fin].abs().max().clamp_min(1e-6) if fin.any() else 1.0
     err = ((got[fin] - exp[fin]).abs().max() / scale).item() if fin.any() else 0.0
-    assert err <= RTOL, f"{what}: max relative error {err:.3e} > {RTOL}"
+    OBSERVED[bucket] = max(OBSERVED.get(bucket, 0.0), err)
+    assert err <= tol, f"{what}: max relative error {err:.3e} > {tol}"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _dump_observed_errors():
+    yield
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "parity_errors.json"), "w") as f:
+        json.dump({"tight_tolerance": TIGHT, "api_tolerance": RTOL, "max_relative_error_observed": OBSERVED}, f, indent=1)
+
+
+def _path(L, name):
+    return {"tc": L.PATH_TC, "simt": L.PATH_SIMT, "tc_m64": L.PATH_TC_M64, "auto": L.PATH_AUTO}[name]
 
 
 SHAPES = [
@@ -60,45 +79,31 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-@pytest.mark.parametrize("path", ["tc", "simt"])
+@pytest.mark.parametrize("path", ["tc", "simt", "tc_m64"])
 def test_maxsim_scores_match_oracle(cuda_dev, shape, path):
+    """Every scoring path: tcgen05 (default), CUDA cores, and the M=64 tensor-core variant for 1-2 queries
+    (HRC_PATH_TC_M64; with more queries it is the default kernel)."""
     L = _lib()
     q, tok, off = _case(hash(shape) % 10_000, *shape)
     exp = o.maxsim_scores(q.float(), tok.float(), off)
-    got = L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev),
-                          path=L.PATH_TC if path == "tc" else L.PATH_SIMT)
+    got = L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev), path=_path(L, path))
     torch.cuda.synchronize()
-    _assert_scores(got, exp, f"{path} {shape}")
-
-
-@pytest.mark.parametrize("shape", [(64, 32, 512, 9, 32), (33, 95, 97, 5, 32), (300, 1, 40, 16, 20)])
-def test_batched_ts_kernel_matches_oracle(cuda_dev, shape, monkeypatch):
-    """The optional A-operand-in-TMEM batched kernel (env HRC_TC_TS=1, 96-token tiles)."""
-    L = _lib()
-    monkeypatch.setenv("HRC_TC_TS", "1")
-    q, tok, off = _case(77, *shape)
-    exp = o.maxsim_scores(q.float(), tok.float(), off)
-    got = L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev), path=L.PATH_TC)
-    torch.cuda.synchronize()
-    _assert_scores(got, exp, f"ts {shape}")
+    _assert_scores(got, exp, f"{path} {shape}", bucket=path)
 
 
 @pytest.mark.parametrize("shape", [(64, 32, 512, 9, 32), (33, 127, 129, 5, 32), (120, 1, 200, 21, 32), (300, 1, 40, 16, 20),
-                                   (3000, 16, 200, 40, 32), (1, 700, 700, 17, 32)])
-@pytest.mark.parametrize("pair", ["1", "0", "epi1", "epi2", "epi3"])
-def test_batched_kernel_more_shapes(cuda_dev, shape, pair, monkeypatch):
-    """Batched (MT=2) kernels — CTA pairs (cta_group::2, the default from two query groups up, with an odd last
-    group on the single-CTA kernel) and single CTAs (HRC_TC_PAIR=0): 40 queries over many segments, 17 queries on
-    one 6-tile document, short documents, partial query groups."""
+                                   (3000, 16, 200, 40, 32), (1, 700, 700, 17, 32), (500, 1, 300, 2, 32), (77, 30, 34, 1, 32)])
+@pytest.mark.parametrize("path", ["tc", "tc_m64"])
+def test_batched_and_m64_kernels_more_shapes(cuda_dev, shape, path):
+    """Batched (MT=2) kernels — CTA pairs (cta_group::2, from two query groups up, with an odd last group on the
+    single-CTA kernel) and single CTAs: 40 queries over many segments, 17 queries on one 6-tile document, short
+    documents, partial query groups — and the 1-2 query shapes on both single-query kernels (M=128 / M=64)."""
     L = _lib()
-    monkeypatch.setenv("HRC_TC_PAIR", "0" if pair == "0" else "1")
-    if pair.startswith("epi"):                 # optional epilogue organisations (per-M-tile accumulator units)
-        monkeypatch.setenv("HRC_TC_EPI", pair[3:])
     q, tok, off = _case(78, *shape)
     exp = o.maxsim_scores(q.float(), tok.float(), off)
-    got = L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev), path=L.PATH_TC)
+    got = L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev), path=_path(L, path))
     torch.cuda.synchronize()
-    _assert_scores(got, exp, f"batched pair={pair} {shape}")
+    _assert_scores(got, exp, f"batched {path} {shape}", bucket=path)
 
 
 def test_reference_literal_path_matches_reference_outputs(cuda_dev, golden_dir):
@@ -113,9 +118,9 @@ def test_reference_literal_path_matches_reference_outputs(cuda_dev, golden_dir):
     tok = D.reshape(n * ld, 128).to(torch.bfloat16).to(cuda_dev)
     off = torch.arange(0, (n + 1) * ld, ld, dtype=torch.int64, device=cuda_dev)
     got = L.meanpool_cosine_scores(tok, off, q.unsqueeze(0).to(torch.bfloat16).to(cuda_dev))
-    _assert_scores(got[0], torch.from_numpy(z["out_q_D"]), "literal q")
+    _assert_scores(got[0], torch.from_numpy(z["out_q_D"]), "literal q", tol=RTOL, bucket="literal")
     gotb = L.meanpool_cosine_scores(tok, off, qb.to(torch.bfloat16).to(cuda_dev))
-    _assert_scores(gotb, torch.from_numpy(z["out_qb_D"]), "literal qb")
+    _assert_scores(gotb, torch.from_numpy(z["out_qb_D"]), "literal qb", tol=RTOL, bucket="literal")
 
     class FixedEncoder:                       # the encoder make_golden.py gave the reference
         def encode(self, x, **kw):
@@ -136,7 +141,7 @@ def test_reference_literal_path_matches_reference_outputs(cuda_dev, golden_dir):
     # _maxsim_score(mode=...) keeps the reference's shapes (:813-817, :831)
     s = r._maxsim_score(q, D)
     assert s.shape == (n,)
-    _assert_scores(s, exp_scores, "_maxsim_score literal")
+    _assert_scores(s, exp_scores, "_maxsim_score literal", tol=RTOL, bucket="literal")
     assert r._maxsim_score(q, D, mode="maxsim").shape == (n,) and float(r._maxsim_score(q, D, mode="maxsim").min()) > 2.0
     # ragged store + empty document: NaN like torch's mean over an empty axis
     q3, tok3, off3 = _case(5, 0, 0, 0, 2, 32, lens=[3, 0, 130, 1, 77])
@@ -160,7 +165,8 @@ def test_fused_search_and_rerank_calls(cuda_dev):
     g = torch.Generator().manual_seed(2)
     cand = torch.randint(0, 20_000, (3, 50), generator=g, dtype=torch.int32).to(cuda_dev)
     cand[1, 4] = -1
-    pos, dids, rs, cs = L.rerank(tok_d, off_d, cand, q_d, 10)
+    pos, dids, rs, cs = L.rerank(tok_d, off_d, cand, q_d, 10, want_cand_scores=True)
+    assert L.rerank(tok_d, off_d, cand, q_d, 10)[3] is None
     cs2 = L.maxsim_scores_ids(tok_d, off_d, cand, q_d)
     assert torch.equal(cs, cs2)
     p2, s2 = L.keys_unpack(L.topk(cs2, 10))
@@ -374,7 +380,8 @@ def test_retriever_api_shapes_and_ranking(cuda_dev, tmp_path):
     r = hrc.JinaColBERTRetriever(cfg)
     corpus = [f"document number {i} about topic {i % 7} and late interaction {i * 3}" for i in range(120)]
     r.index(corpus)
-    assert os.path.exists(os.path.join(cfg.colbert_index_path, "index.pt"))
+    assert os.path.exists(os.path.join(cfg.colbert_index_path, "index.hrc.pt"))        # packed store: its own file name
+    assert not os.path.exists(os.path.join(cfg.colbert_index_path, "index.pt"))        # never a fake reference index
     res = r.search(query="late interaction topic 3", k=10)
     assert len(res) == 10 and all(sorted(x) == ["document_id", "score", "text"] for x in res)
     assert all(isinstance(x["document_id"], int) and isinstance(x["score"], float) for x in res)
@@ -521,15 +528,16 @@ def test_full_size_properties_c2(cuda_dev):
 
 
 def test_full_size_properties_c3(cuda_dev):
-    """BASELINE config C3 shape at full corpus size (1M documents of 32..512 tokens, ~70 GB) with 24 queries
-    (a CTA-pair launch for two query groups plus the odd group on the single-CTA kernel): size-independent checks."""
+    """BASELINE config C3 at FULL size — 256 queries x 32 tokens over 1M documents of 32..512 tokens (~70 GB) —
+    plus a 24-query run of the same corpus (a CTA-pair launch plus the odd group on the single-CTA kernel):
+    size-independent checks."""
     import hybrid_rag_colbertv2_b200 as hrc
     from hybrid_rag_colbertv2_b200.synth import plant, synth_queries, synth_store
     L = _lib()
     free, _ = torch.cuda.mem_get_info()
     n_docs = 1_000_000 if free > 100e9 else 100_000
     store = synth_store(n_docs, 32, 512, seed=20260103, device=cuda_dev)
-    nq = 24
+    nq = 256 if n_docs == 1_000_000 else 24
     q = synth_queries(nq, 32, device=cuda_dev)
     planted = plant(store, q[:2], n_planted=60)
     r = hrc.JinaColBERTRetriever(hrc.RAGConfig())
@@ -550,10 +558,10 @@ def test_full_size_properties_c3(cuda_dev):
     _assert_scores(scores[:, sample.to(cuda_dev)], exp, "C3 sample")
     # (2) every query of the batch equals the single-query kernel on the same corpus (different kernels,
     #     same fp32 accumulation): within tolerance everywhere
-    for qi in (0, 7, 8, 15, 16, 23):
+    for qi in (0, 7, 8, 15, 16, 23, nq - 1):
         single = L.maxsim_scores(store.tokens, store.offsets, q[qi:qi + 1])
         scale = float(single.abs().max())
-        assert float((single[0] - scores[qi]).abs().max()) <= RTOL * scale, f"query {qi}"
+        assert float((single[0] - scores[qi]).abs().max()) <= TIGHT * scale, f"query {qi}"
     # (3) top-100 per query: sorted, unique, consistent with the score matrix and with torch.topk's values
     ids, sc = r.search_embeddings(q, 100)
     for qi in range(nq):
@@ -566,9 +574,13 @@ def test_full_size_properties_c3(cuda_dev):
         full_exp = torch.full((n_docs,), float('-inf'))
         full_exp[sample] = exp[qi]
         assert o.check_ranking(ids[qi].cpu().tolist()[:30], sc[qi].cpu().tolist()[:30], full_exp, 30, RTOL) is None
-    # (5) shard invariance: a 3-way document split gives bit-identical scores
-    parts = [L.maxsim_scores(s.tokens, s.offsets, q) for s in (store.shard(rk, 3) for rk in range(3))]
-    assert torch.equal(torch.cat(parts, 1), scores)
+    # (5) shard invariance: a 3-way document split gives bit-identical scores; and the first 24 queries alone
+    #     (CTA pairs + the odd group on the single-CTA kernel) equal their rows of the full batch bit for bit
+    q24 = q[:24].contiguous()
+    s24 = L.maxsim_scores(store.tokens, store.offsets, q24)
+    assert torch.equal(s24, scores[:24])
+    parts = [L.maxsim_scores(s.tokens, s.offsets, q24) for s in (store.shard(rk, 3) for rk in range(3))]
+    assert torch.equal(torch.cat(parts, 1), s24)
 
 
 def test_randomised_shapes_against_oracle(cuda_dev):
@@ -621,3 +633,233 @@ def test_plain_c_client_of_the_abi(cuda_dev, tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "c_abi_client ok" in out.stdout
+
+
+# ======================================================================================================
+# Round 2 hardening (VERDICT r1 "Next" #2): adversarial boundaries, reference pin, float64 known answers,
+# full-size C4, ownership of returned buffers, large k.
+# ======================================================================================================
+BOUNDARY_POS = [0, 1, 31, 32, 33, 63, 64, 65, 95, 96, 97, 126, 127]      # positions inside a 128-token tile
+DOC_POS = [0, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257]      # positions inside a document
+
+
+def _boundary_corpus(nq, lq, seed=5):
+    """A corpus in which every document holds exactly ONE decisive token — an exact copy of one query token, cosine
+    ~1 against a background <= ~0.35 — placed at a chosen position relative to the document start AND to the
+    128-token tile (filler documents shift the alignment), so that losing or doubling a single accumulator column at
+    a 32-column chunk edge, the pulled-back last load, the CTA-pair half-tile seam (column 64) or a tile edge moves
+    the score by > 0.5.  Returns q, tok, off and, per document, (query, query token, token row)."""
+    g = torch.Generator().manual_seed(seed)
+    q = torch.nn.functional.normalize(torch.randn((nq, lq, 128), generator=g), dim=-1).to(torch.bfloat16)
+    lens, plant_at = [], []
+    cur = 0
+    for tpos in BOUNDARY_POS:
+        for dpos in DOC_POS:
+            fill = (tpos - dpos - cur) % 128              # filler document so that (cur + fill + dpos) % 128 == tpos
+            if fill:
+                lens.append(fill)
+                plant_at.append(fill - 1)                 # fillers are planted too: at their LAST token
+                cur += fill
+            extra = [0, 1, 31, 40, 130][(tpos + dpos) % 5]   # tokens after the decisive one (0: it is the last token)
+            lens.append(dpos + 1 + extra)
+            plant_at.append(dpos)
+            cur += dpos + 1 + extra
+    off = torch.zeros(len(lens) + 1, dtype=torch.int64)
+    off[1:] = torch.cumsum(torch.tensor(lens), 0)
+    tok = torch.nn.functional.normalize(torch.randn((int(off[-1]), 128), generator=g), dim=-1).to(torch.bfloat16)
+    planted = []
+    for d, p in enumerate(plant_at):
+        qi, ti = d % nq, (d * 7) % lq
+        row = int(off[d]) + p
+        tok[row] = q[qi, ti]
+        planted.append((qi, ti, row))
+    return q, tok, off, planted
+
+
+@pytest.mark.parametrize("nq,path", [(1, "tc"), (2, "tc"), (3, "tc"), (1, "tc_m64"), (2, "tc_m64"), (8, "tc"), (16, "tc"),
+                                     (24, "tc"), (2, "simt")])
+def test_decisive_token_at_every_chunk_and_tile_boundary(cuda_dev, nq, path):
+    L = _lib()
+    q, tok, off, planted = _boundary_corpus(nq, 32)
+    n_docs = off.numel() - 1
+    assert int(off[-1]) > 148 * 128 * 2                    # several tiles per CTA segment, every SM busy
+    covered = {(row % 128) for _, _, row in planted}
+    assert set(BOUNDARY_POS) <= covered
+    exp = o.maxsim_scores(q.float(), tok.float(), off)
+    # premise: without its decisive token a document scores > 0.5 lower for the query it was planted for
+    blind = tok.clone().float()
+    for _, _, row in planted:
+        blind[row] = 0.0
+    exp_blind = o.maxsim_scores(q.float(), blind, off)
+    for d, (qi, _, _) in enumerate(planted):
+        assert float(exp[qi, d] - exp_blind[qi, d]) > 0.5
+    tok_d, off_d, q_d = tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev)
+    got = L.maxsim_scores(tok_d, off_d, q_d, path=_path(L, path))
+    _assert_scores(got, exp, f"boundary nq={nq} {path}", bucket="boundary")
+    worst = float((got.float().cpu() - exp).abs().max())
+    assert worst < 1e-3, f"a boundary column was lost or doubled: {worst}"
+    if path == "tc":       # the candidate (rerank) entry point walks ONE document per CTA: same positions, other code path
+        cand = torch.arange(n_docs, dtype=torch.int32).flip(0).unsqueeze(0).repeat(nq, 1).contiguous()
+        gotc = L.maxsim_scores_ids(tok_d, off_d, cand.to(cuda_dev), q_d, path=L.PATH_TC)
+        _assert_scores(gotc, exp.flip(1), f"boundary candidates nq={nq}", bucket="boundary")
+
+
+@pytest.mark.parametrize("path", ["tc", "simt", "tc_m64"])
+def test_maxsim_kernels_reproduce_the_reference_where_it_computes_maxsim(cuda_dev, golden_dir, path):
+    """REFERENCE PIN for the MaxSim kernels: tests/golden/maxsim_pin.npz holds outputs of the UNMODIFIED reference
+    `_maxsim_score` (local_rag_complete.py:821-829) on inputs where its mean-pool cosine equals MaxSim (identical
+    query tokens, identical document tokens, exactly unit-norm dyadic rows; make_golden.py asserts the premise).
+    hrc_maxsim_scores / Lq must reproduce them BIT FOR BIT (every partial sum is exactly representable)."""
+    import hybrid_rag_colbertv2_b200 as hrc
+    L = _lib()
+    z = np.load(os.path.join(golden_dir, "maxsim_pin.npz"))
+    qrows, drows = torch.from_numpy(z["q_rows"]), torch.from_numpy(z["d_rows"])
+    for lq in (1, 2, 4):
+        for ld in (1, 2, 4):
+            ref = torch.from_numpy(z[f"out_lq{lq}_ld{ld}"])
+            q = qrows[:, None, :].expand(-1, lq, -1).contiguous().to(torch.bfloat16)
+            tok = drows[:, None, :].expand(-1, ld, -1).reshape(-1, 128).contiguous().to(torch.bfloat16)
+            off = torch.arange(0, drows.shape[0] * ld + 1, ld, dtype=torch.int64)
+            for qs in (q, q[:1].contiguous(), q[:2].contiguous()):          # batched (5) and the 1- / 2-query kernels
+                got = L.maxsim_scores(tok.to(cuda_dev), off.to(cuda_dev), qs.to(cuda_dev), path=_path(L, path))
+                assert torch.equal(got.cpu() / lq, ref[: qs.shape[0]]), (path, lq, ld, qs.shape[0])
+    # through the reference-shaped API: score_reduction="mean" is the reference's scale on these inputs
+    r = hrc.JinaColBERTRetriever(hrc.RAGConfig(score_reduction="mean", maxsim_path=_path(L, path)))
+    dense = drows[:, None, :].expand(-1, 4, -1).contiguous()
+    r.index_embeddings(dense)
+    ref = torch.from_numpy(z["out_lq2_ld4"])
+    s = r._maxsim_score(qrows[:, None, :].expand(-1, 2, -1).contiguous(), dense)           # [Bq, N], as :831
+    assert torch.equal(s.cpu(), ref)
+    ids, sc = r.search_embeddings(qrows[0][None, :].expand(2, -1).contiguous(), 7)
+    assert torch.equal(sc[0].cpu(), torch.topk(ref[0], 7).values)                          # the reference's :767
+    assert ids[0, 0].item() == 0 and sc[0, 0].item() == 1.0                                # the query's own copy
+
+
+@pytest.mark.parametrize("path", ["tc", "simt", "tc_m64"])
+def test_maxsim_kernels_match_float64_known_answers(cuda_dev, golden_dir, path):
+    L = _lib()
+    z = np.load(os.path.join(golden_dir, "maxsim_kat_f64.npz"))
+    for name in ("a", "b"):
+        q, tok, off = (torch.from_numpy(z[f"{name}_{k}"]) for k in ("q", "tok", "off"))
+        got = L.maxsim_scores(tok.to(torch.bfloat16).to(cuda_dev), off.to(cuda_dev), q.to(torch.bfloat16).to(cuda_dev),
+                              path=_path(L, path))
+        _assert_scores(got, torch.from_numpy(z[f"{name}_scores_f64"]).float(), f"kat {name} {path}", bucket="kat_f64")
+
+
+def test_search_host_results_belong_to_the_caller(cuda_dev):
+    """two consecutive search_host results held at once must not alias (pinned staging is reused)."""
+    import hybrid_rag_colbertv2_b200 as hrc
+    q, tok, off = _case(43, 3000, 8, 60, 2, 32)
+    r = hrc.JinaColBERTRetriever(hrc.RAGConfig())
+    r.index_embeddings(tok, off, packed=True)
+    a_ids, a_sc = r.search_host(q[0].float(), 20)
+    keep_ids, keep_sc = a_ids.clone(), a_sc.clone()
+    b_ids, b_sc = r.search_host(q[1].float(), 20)
+    assert torch.equal(a_ids, keep_ids) and torch.equal(a_sc, keep_sc)
+    assert not torch.equal(a_ids, b_ids)
+    z_ids, _ = r.search_host(q[0].float(), 20, copy=False)                 # explicit zero-copy: the staging buffer
+    assert z_ids.is_pinned() and torch.equal(z_ids, keep_ids)
+
+
+def test_k_beyond_the_selection_limit_and_absent_candidates(cuda_dev):
+    """the reference's torch.topk / argsort take any k; k > HRC_MAX_TOPK goes through a device sort with the
+    kernels' order.  Candidates this store does not hold score -inf and are dropped from _colbert_rerank."""
+    import hybrid_rag_colbertv2_b200 as hrc
+    q, tok, off = _case(47, 4000, 4, 30, 1, 32)
+    r = hrc.JinaColBERTRetriever(hrc.RAGConfig())
+    r.index_embeddings(tok, off, packed=True, corpus=[f"t{i}" for i in range(4000)])
+    ids_big, sc_big = r.search_embeddings(q, 3000)
+    ids_small, sc_small = r.search_embeddings(q, 2048)
+    assert ids_big.shape == (1, 3000) and torch.equal(ids_big[:, :2048], ids_small) and torch.equal(sc_big[:, :2048], sc_small)
+    assert len(r.search("anything", k=2500)) == 2500
+    cand = torch.arange(4000, dtype=torch.int32).unsqueeze(0)
+    pos, dids, sc = r.rerank_ids(q, cand, k=2100)
+    assert torch.equal(dids[:, :2048], ids_small) and pos.shape == (1, 2100)
+    idx = hrc.DualIndexer(hrc.RAGConfig(final_top_k=5))
+    idx.colbert_retriever = r
+    h = hrc.HybridRetriever(idx.config, idx, None, verbose=False)
+    chunks = [{"chunk_id": c, "text": f"t{c}", "document_id": c, "metadata": {}} for c in (5, 999_999, 7, -3)]
+    out = h._colbert_rerank("a query", chunks, top_k=4)
+    assert [x["chunk_id"] for x in out] and all(x["chunk_id"] in (5, 7) for x in out) and len(out) == 2
+    assert [x["rank"] for x in out] == [1, 2] and all(np.isfinite(x["score"]) for x in out)
+
+
+def test_index_files_and_reference_compatible_export(cuda_dev, tmp_path):
+    """the packed store is saved as index.hrc.pt (never as a file the reference would mis-read), doc_id_base
+    is persisted, and reference_compatible_index=True additionally writes the reference's own dense layout."""
+    import hybrid_rag_colbertv2_b200 as hrc
+    cfg = hrc.RAGConfig(colbert_index_path=str(tmp_path / "ix"), reference_compatible_index=True)
+    r = hrc.JinaColBERTRetriever(cfg, encoder=hrc.SyntheticEncoder(doc_tokens=8))
+    corpus = [f"text {i} of the corpus" for i in range(40)]
+    r.index(corpus)
+    ref_file = torch.load(os.path.join(cfg.colbert_index_path, "index.pt"))
+    assert sorted(ref_file) == ["corpus", "embeddings", "lengths"]
+    assert ref_file["embeddings"].shape == (40, 8, 128) and ref_file["embeddings"].dtype == torch.float32   # :735-746
+    r.store.doc_id_base = 1234
+    r._save_index()
+    back = hrc.JinaColBERTRetriever(cfg, encoder=hrc.SyntheticEncoder(doc_tokens=8))
+    back.load()
+    assert back.store.doc_id_base == 1234 and torch.equal(back.store.tokens, r.store.tokens) and back.corpus == corpus
+    os.remove(os.path.join(cfg.colbert_index_path, "index.hrc.pt"))
+    dense_only = hrc.JinaColBERTRetriever(cfg, encoder=hrc.SyntheticEncoder(doc_tokens=8))
+    dense_only.load()                                                      # falls back to the reference's file
+    assert torch.equal(dense_only.store.tokens, r.store.tokens) and dense_only.store.n_docs == 40
+
+
+def test_full_size_c4_fused_equals_staged_equals_stagewise_oracle(cuda_dev):
+    """BASELINE config C4 at full size: 1,000 queries through the hybrid pipeline over 1M passages x 128 tokens.
+    fused (hrc_hybrid_retrieve, batches of 64) == staged calls bit for bit for all 1,000 queries; for sampled queries
+    every stage is re-derived with the oracle: the ColBERT top-100 against oracle re-scores, RRF against the restated
+    reference (:960-978, exact), and the final top-10 against oracle re-scores of the 50 candidates."""
+    import hybrid_rag_colbertv2_b200 as hrc
+    from hybrid_rag_colbertv2_b200.synth import plant, synth_queries, synth_store
+    free, _ = torch.cuda.mem_get_info()
+    n_docs = 1_000_000 if free > 60e9 else 50_000
+    n_queries = 1000 if n_docs == 1_000_000 else 128
+    store = synth_store(n_docs, 128, 128, seed=20260102, device=cuda_dev)
+    queries = synth_queries(n_queries, 32, seed=99, device=cuda_dev)
+    sample_q = [0, 63, 64, n_queries // 2, n_queries - 1]
+    plant(store, queries[sample_q], n_planted=120, seed=17)
+    cfg = hrc.RAGConfig(colbert_top_k=100, bm25_top_k=100, rerank_candidates=50, final_top_k=10)
+    idx = hrc.DualIndexer(cfg)
+    idx.colbert_retriever.store = store
+    h = hrc.HybridRetriever(cfg, idx, None, verbose=False)
+    g = torch.Generator().manual_seed(4)
+    bm25 = torch.randint(0, n_docs, (n_queries, 100), generator=g, dtype=torch.int32).to(cuda_dev)
+    fused_ids, fused_sc, staged_ids, staged_sc, col = [], [], [], [], []
+    for b in range(0, n_queries, 64):
+        qb = queries[b:b + 64]
+        col_ids, _ = idx.colbert_retriever.search_embeddings(qb, 100)
+        bm = bm25[b:b + 64].clone()
+        bm[:, :30] = col_ids[:, torch.randperm(100, generator=g)[:30].to(cuda_dev)]       # 30 % overlap (SURVEY §8(d))
+        bm25[b:b + 64] = bm
+        col.append(col_ids)
+        i_f, s_f = h.retrieve_batch(qb, bm)
+        i_s, s_s = h._retrieve_batch_staged(qb, bm, 10)
+        fused_ids.append(i_f); fused_sc.append(s_f); staged_ids.append(i_s); staged_sc.append(s_s)
+    fused_ids, fused_sc = torch.cat(fused_ids), torch.cat(fused_sc)
+    assert torch.equal(fused_ids, torch.cat(staged_ids)) and torch.equal(fused_sc, torch.cat(staged_sc))
+    assert fused_ids.shape == (n_queries, 10) and bool((fused_ids >= 0).all())
+    assert bool((fused_sc[:, :-1] >= fused_sc[:, 1:]).all())
+    col = torch.cat(col)
+    view = store.tokens.view(n_docs, 128, 128)
+    for qi in sample_q:
+        qf = queries[qi:qi + 1].float().cpu()
+        # stage 2: the ColBERT list re-scored by the oracle (+ 2000 random documents: nothing outside beats the k-th)
+        extra = torch.randint(0, n_docs, (2000,), generator=g)
+        docs = torch.unique(torch.cat([col[qi].cpu().long(), extra]))
+        sub = view[docs.to(cuda_dev)].reshape(-1, 128).float().cpu()
+        exp = o.maxsim_scores(qf, sub, torch.arange(0, docs.numel() * 128 + 1, 128))[0]
+        full = torch.full((n_docs,), float("-inf"))
+        full[docs] = exp
+        _, sc100 = idx.colbert_retriever.search_embeddings(queries[qi:qi + 1], 100)
+        assert o.check_ranking(col[qi].cpu().tolist(), sc100[0].cpu().tolist(), full, 100, RTOL) is None, f"query {qi}"
+        # stage 3: RRF, exact
+        ri, _ = o.rrf_ids(bm25[qi].cpu().tolist(), col[qi].cpu().tolist(), 60)
+        cand = ri[:50]
+        # stage 5: rerank of the 50 candidates against oracle re-scores
+        cdocs = torch.tensor(cand)
+        csub = view[cdocs.to(cuda_dev)].reshape(-1, 128).float().cpu()
+        cexp = o.maxsim_scores(qf, csub, torch.arange(0, 50 * 128 + 1, 128))[0]
+        got_pos = [cand.index(i) for i in fused_ids[qi].cpu().tolist()]
+        assert o.check_ranking(got_pos, fused_sc[qi].cpu().tolist(), cexp, 10, RTOL) is None, f"query {qi}"

@@ -29,7 +29,8 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/hrc.h but not exported by libhrc.so"
     assert sorted(_lib.SYMBOLS) == declared, "ctypes table and header disagree"
-    assert lib.hrc_version() == 100
+    assert lib.hrc_version() == _lib.ABI_VERSION == 200
+    assert _lib.maxsim_workspace_bytes(1000, 2, 32) == 0 and _lib.maxsim_workspace_bytes(1000, 2, 33) == 2 * 2 * 1000 * 4
     assert lib.hrc_last_error() == b""
     assert _lib.topk_workspace_bytes(1000, 4, 10) == 0
     assert _lib.topk_workspace_bytes(1_000_000, 1, 100) > 123 * 100 * 8
@@ -49,12 +50,29 @@ def test_no_cpu_fallback():
     with pytest.raises(hrc.HrcError):
         _lib.HostSearch()(tok, off, torch.zeros((1, 32, 128)), 1)
     with pytest.raises(hrc.HrcError):
+        _lib.search(tok, off, q, 1)
+    with pytest.raises(hrc.HrcError):
+        _lib.rerank(tok, off, torch.zeros((1, 1), dtype=torch.int32), q, 1)
+    with pytest.raises(hrc.HrcError):
+        _lib.store_register(tok)
+    with pytest.raises(hrc.HrcError):
         _lib.hybrid_retrieve(tok, off, q, torch.zeros((1, 4), dtype=torch.int32), colbert_k=1, rrf_k=60, n_candidates=1, final_k=1)
     src = open(os.path.join(ROOT, "hybrid-rag-colbertv2_b200", "retriever.py")).read()
     for mod in ("_lib.py", "retriever.py", "store.py", "sharded.py", "synth.py", "encoder.py", "__init__.py"):
         text = open(os.path.join(ROOT, "hybrid-rag-colbertv2_b200", mod)).read()
         assert "oracle" not in text.replace("oracle for", ""), f"{mod} must not import the oracle"
     assert "einsum" not in src
+
+
+def test_product_library_reads_no_environment_variables():
+    """no getenv in the shipped library (experiment hooks live behind -DHRC_EXPERIMENTS in
+    libhrc_exp.so) and no experiment knob names in its strings."""
+    lib = os.path.join(ROOT, "hybrid-rag-colbertv2_b200", "libhrc.so")
+    blob = open(lib, "rb").read()        # (the statically linked CUDA runtime has its own getenv; ours must not)
+    assert b"HRC_TC_" not in blob and b"hrc_exp_set_debug" not in blob
+    for src in os.listdir(os.path.join(ROOT, "hybrid-rag-colbertv2_b200", "csrc")):
+        if src.endswith((".cu", ".cuh")):
+            assert "getenv" not in open(os.path.join(ROOT, "hybrid-rag-colbertv2_b200", "csrc", src)).read(), src
 
 
 def test_store_from_dense_ragged_packed_agree():

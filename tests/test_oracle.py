@@ -51,6 +51,48 @@ def test_reference_is_not_maxsim(golden_dir):
     assert float(true.min()) > 2.0 and float(lit.abs().max()) < 1.0
 
 
+def _pin_cases(golden_dir):
+    z = np.load(os.path.join(golden_dir, "maxsim_pin.npz"))
+    qrows, drows = torch.from_numpy(z["q_rows"]), torch.from_numpy(z["d_rows"])
+    for lq in (1, 2, 4):
+        for ld in (1, 2, 4):
+            q = qrows[:, None, :].expand(-1, lq, -1).contiguous()
+            tok = drows[:, None, :].expand(-1, ld, -1).reshape(-1, 128).contiguous()
+            off = torch.arange(0, drows.shape[0] * ld + 1, ld, dtype=torch.int64)
+            yield lq, ld, q, tok, off, torch.from_numpy(z[f"out_lq{lq}_ld{ld}"])
+
+
+def test_maxsim_oracle_pinned_by_the_reference_where_meanpool_equals_maxsim(golden_dir):
+    """maxsim_pin.npz holds outputs of the UNMODIFIED reference `_maxsim_score` (:821-829) on shapes where its
+    mean-pool cosine IS MaxSim (identical query tokens, identical document tokens, exactly unit-norm dyadic rows):
+    reference == (1/Lq) * sum_i max_t <q_i, d_t>, bit for bit.  This pins the oracle's dot product, max over document
+    tokens and sum over query tokens to the real reference — packed, dense and pure-loop forms."""
+    n_cases = 0
+    for lq, ld, q, tok, off, ref in _pin_cases(golden_dir):
+        assert torch.equal(o.round_bf16(q), q) and torch.equal(o.round_bf16(tok), tok)      # bf16 store loses nothing
+        assert torch.equal(o.maxsim_scores(q, tok, off) / lq, ref), (lq, ld)
+        assert torch.equal(o.maxsim_dense(q, tok.view(-1, ld, 128)) / lq, ref), (lq, ld)
+        assert torch.equal(o.literal_reference(q, tok.view(-1, ld, 128)), ref), (lq, ld)
+        if lq * ld <= 2:
+            naive = o.maxsim_naive(q.numpy(), tok.numpy(), off.numpy())
+            assert (naive / lq == ref.numpy()).all(), (lq, ld)
+        n_cases += 1
+    assert n_cases == 9 and float(ref.max()) == 1.0 and float(ref.min()) == -1.0
+
+
+def test_maxsim_oracle_matches_float64_known_answers(golden_dir):
+    """maxsim_kat_f64.npz: numpy float64 loop results (tests/golden/make_kat.py), independent of torch — ragged case A
+    and case B with lengths around the 32-column chunk and the 128-token tile."""
+    z = np.load(os.path.join(golden_dir, "maxsim_kat_f64.npz"))
+    for name in ("a", "b"):
+        q, tok, off = (torch.from_numpy(z[f"{name}_{k}"]) for k in ("q", "tok", "off"))
+        exp = z[f"{name}_scores_f64"]
+        got = o.maxsim_scores(q, tok, off).double().numpy()
+        assert np.abs(got - exp).max() <= 2e-6 * np.abs(exp).max(), name
+        naive = o.maxsim_naive(q.numpy(), tok.numpy(), off.numpy()).astype(np.float64)
+        assert np.abs(naive - exp).max() <= 2e-6 * np.abs(exp).max(), name
+
+
 def test_rrf_reference_matches_reference_outputs(golden_dir):
     cases = json.load(open(os.path.join(golden_dir, "rrf.json")))
     assert len(cases) >= 8

@@ -41,6 +41,27 @@ def test_c_maxsim_matches_python_oracle(clib):
     np.testing.assert_allclose(out[fin], exp[fin], rtol=1e-5, atol=1e-6)
 
 
+def test_c_maxsim_pinned_by_reference_and_float64_vectors(clib, golden_dir):
+    """The C restatement of MaxSim reproduces (a) the unmodified reference bit for bit on the shapes where its
+    mean-pool cosine is MaxSim (maxsim_pin.npz) and (b) the float64 known answers (maxsim_kat_f64.npz)."""
+    z = np.load(os.path.join(golden_dir, "maxsim_pin.npz"))
+    qrows, drows = z["q_rows"], z["d_rows"]
+    for lq in (1, 2, 4):
+        for ld in (1, 2, 4):
+            q = np.ascontiguousarray(np.repeat(qrows[:, None, :], lq, 1))
+            tok = np.ascontiguousarray(np.repeat(drows[:, None, :], ld, 1).reshape(-1, 128))
+            off = np.arange(0, drows.shape[0] * ld + 1, ld, dtype=np.int64)
+            out = np.empty((qrows.shape[0], drows.shape[0]), dtype=np.float32)
+            clib.oracle_maxsim_scores(_p(q), q.shape[0], lq, _p(tok), _p(off), ctypes.c_int64(drows.shape[0]), _p(out))
+            assert (out / lq == z[f"out_lq{lq}_ld{ld}"]).all(), (lq, ld)
+    k = np.load(os.path.join(golden_dir, "maxsim_kat_f64.npz"))
+    for name in ("a", "b"):
+        q, tok, off = (np.ascontiguousarray(k[f"{name}_{x}"]) for x in ("q", "tok", "off"))
+        out = np.empty(k[f"{name}_scores_f64"].shape, dtype=np.float32)
+        clib.oracle_maxsim_scores(_p(q), q.shape[0], q.shape[1], _p(tok), _p(off), ctypes.c_int64(len(off) - 1), _p(out))
+        assert np.abs(out - k[f"{name}_scores_f64"]).max() <= 2e-6 * np.abs(k[f"{name}_scores_f64"]).max()
+
+
 def test_c_literal_matches_reference_outputs(clib, golden_dir):
     """The C restatement of what the reference's `_maxsim_score` literally computes, against the vectors the
     unmodified reference produced (both fixtures)."""
