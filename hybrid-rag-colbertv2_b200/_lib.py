@@ -36,13 +36,13 @@ SYMBOLS = {
     "hrc_maxsim_scores": (_I, [_P, _P, _I64, _I64, _P, _I, _I, _P, _I, _P, _SZ, _P]),
     "hrc_maxsim_scores_ids": (_I, [_P, _P, _I64, _I64, _P, _I, _P, _I, _I, _P, _I, _P, _SZ, _P]),
     "hrc_meanpool_cosine_scores": (_I, [_P, _P, _I64, _I64, _P, _I, _I, _P, _P]),
-    "hrc_search_workspace_bytes": (_SZ, [_I64, _I, _I, _I]),
+    "hrc_search_workspace_bytes": (_SZ, [_I64, _I64, _I, _I, _I, _I]),
     "hrc_search": (_I, [_P, _P, _I64, _I64, _P, _I, _I, _I, _I32, _P, _SZ, _P, _P, _P, _I, _P]),
-    "hrc_search_host_workspace_bytes": (_SZ, [_I64, _I, _I, _I]),
+    "hrc_search_host_workspace_bytes": (_SZ, [_I64, _I64, _I, _I, _I, _I]),
     "hrc_search_host": (_I, [_P, _P, _I64, _I64, _P, _I, _I, _I, _I32, _P, _SZ, _P, _P, _I, _P]),
     "hrc_rerank_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "hrc_rerank": (_I, [_P, _P, _I64, _I64, _P, _I, _P, _I, _I, _I, _P, _SZ, _P, _P, _P, _P, _I, _P]),
-    "hrc_hybrid_retrieve_workspace_bytes": (_SZ, [_I64, _I, _I, _I, _I, _I]),
+    "hrc_hybrid_retrieve_workspace_bytes": (_SZ, [_I64, _I64, _I, _I, _I, _I, _I, _I]),
     "hrc_hybrid_retrieve": (_I, [_P, _P, _I64, _I64, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I32, _P, _SZ, _P, _P, _I, _P]),
     "hrc_topk_workspace_bytes": (_SZ, [_I64, _I, _I]),
     "hrc_topk": (_I, [_P, _P, _I64, _I, _I, _I32, _P, _P, _SZ, _P]),
@@ -253,7 +253,8 @@ def search(tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.Tensor, k
     _check_queries(queries)
     n_docs = offsets.numel() - 1
     nq, lq = int(queries.shape[0]), int(queries.shape[1])
-    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, int(load().hrc_search_workspace_bytes(n_docs, nq, lq, k)))
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, int(load().hrc_search_workspace_bytes(n_docs, int(tokens.shape[0]), nq,
+                                                                                        lq, k, path)))
     keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
     ids = torch.empty((nq, k), dtype=torch.int32, device=dev) if unpack else None
     scores = torch.empty((nq, k), dtype=torch.float32, device=dev) if unpack else None
@@ -271,10 +272,10 @@ class HostSearch:
     def __init__(self):
         self.key = None
 
-    def _ensure(self, dev, nq: int, lq: int, n_docs: int, k: int):
-        key = (str(dev), nq, lq, n_docs, k)
+    def _ensure(self, dev, nq: int, lq: int, n_docs: int, total_tokens: int, k: int, path: int):
+        key = (str(dev), nq, lq, n_docs, total_tokens, k, path)
         if self.key != key:
-            need = int(load().hrc_search_host_workspace_bytes(n_docs, nq, lq, k))
+            need = int(load().hrc_search_host_workspace_bytes(n_docs, total_tokens, nq, lq, k, path))
             self.ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
             self.ws_bytes = need
             self.q_pinned = torch.empty((nq, lq, DIM), dtype=torch.float32).pin_memory()
@@ -294,7 +295,7 @@ class HostSearch:
         assert queries_host.shape[2] == DIM and queries_host.is_contiguous()
         n_docs = offsets.numel() - 1
         nq, lq = int(queries_host.shape[0]), int(queries_host.shape[1])
-        self._ensure(dev, nq, lq, n_docs, k)
+        self._ensure(dev, nq, lq, n_docs, int(tokens.shape[0]), k, path)
         src = queries_host
         if not src.is_pinned():
             self.q_pinned.copy_(src)
@@ -322,7 +323,8 @@ def hybrid_retrieve(tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.
     assert bm25_ids.dtype == torch.int32 and bm25_ids.dim() == 2 and bm25_ids.shape[0] == queries.shape[0]
     n_docs = offsets.numel() - 1
     nq, lq = int(queries.shape[0]), int(queries.shape[1])
-    need = int(load().hrc_hybrid_retrieve_workspace_bytes(n_docs, nq, lq, colbert_k, n_candidates, final_k))
+    need = int(load().hrc_hybrid_retrieve_workspace_bytes(n_docs, int(tokens.shape[0]), nq, lq, colbert_k, n_candidates,
+                                                          final_k, path))
     ws_ptr, ws_bytes, _keep = _ws(workspace, dev, need)
     ids = torch.empty((nq, final_k), dtype=torch.int32, device=dev)
     scores = torch.empty((nq, final_k), dtype=torch.float32, device=dev)

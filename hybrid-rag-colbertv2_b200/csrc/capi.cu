@@ -60,7 +60,15 @@ void set_debug(int);
 #endif
 size_t topk_workspace_bytes(int64_t, int, int);
 int launch_topk(const float*, const int32_t*, int64_t, int, int, int32_t, uint64_t*, void*, size_t, cudaStream_t);
-int launch_topk_merge(const uint64_t*, int, int, int, uint64_t*, cudaStream_t);
+int launch_topk_merge(const uint64_t*, int, int, int, uint64_t*, cudaStream_t, int32_t* = nullptr, float* = nullptr);
+bool tc_topk_supported(int64_t, int, int);
+bool tc_rerank_supported(int64_t, int, int, int);
+int launch_maxsim_tc_rerank(const void*, const int64_t*, int64_t, int64_t, const int32_t*, int, const void*, int, int, int,
+                            float*, uint32_t*, int32_t*, int32_t*, float*, cudaStream_t);
+int tc_topk_segments(int64_t);
+int tc_topk_list_len();
+int launch_maxsim_tc_topk(const void*, const int64_t*, int64_t, int64_t, const void*, int, int, int, int32_t, float*,
+                          uint64_t*, cudaStream_t);
 int launch_keys_unpack(const uint64_t*, int64_t, int32_t*, float*, cudaStream_t);
 int launch_rerank_unpack(const uint64_t*, int, int, const int32_t*, int, int32_t*, int32_t*, float*, cudaStream_t);
 int launch_rrf(const int32_t*, int, const int32_t*, int, int, int, int, int32_t*, double*, int32_t*, cudaStream_t);
@@ -130,28 +138,44 @@ __global__ void shift_ids_kernel(int32_t* ids, int64_t n, int32_t delta) {
 }
 
 // ---- workspace layouts (every sub-buffer 256-byte aligned) -------------------------------------------------
-struct SearchLayout {      // hrc_search: score matrix, slot partials (lq > 32), top-k scratch
-  size_t scores, part, topk, total, part_bytes, topk_bytes;
+// hrc_search takes the FUSED route (MaxSim kernel with per-segment top-k in its epilogue, then one merge launch: the
+// score matrix is never written) when the tensor-core path applies, the query has <= 32 tokens and k <= 128;
+// otherwise score matrix -> radix top-k.
+static bool search_is_fused(int64_t total_tokens, int lq, int k, int path) {
+  return (path == HRC_PATH_AUTO || path == HRC_PATH_TC) && tc_topk_supported(total_tokens, lq, k);
+}
+
+struct SearchLayout {      // fused: candidate keys.  staged: score matrix, slot partials (lq > 32), top-k scratch
+  size_t cand, scores, part, topk, total, part_bytes, topk_bytes;
+  bool fused;
+  int n_seg;
 };
-static SearchLayout search_layout(int64_t n_docs, int nq, int lq, int k) {
-  SearchLayout L;
+static SearchLayout search_layout(int64_t n_docs, int64_t total_tokens, int nq, int lq, int k, int path) {
+  SearchLayout L = {};
   size_t o = 0;
-  L.scores = o; o += align256(size_t(nq) * size_t(n_docs) * sizeof(float));
-  L.part_bytes = maxsim_tc_workspace_bytes(n_docs, nq, lq);
-  L.part = o; o += align256(L.part_bytes);
-  L.topk_bytes = topk_workspace_bytes(n_docs, nq, k);
-  L.topk = o; o += align256(L.topk_bytes);
+  L.fused = search_is_fused(total_tokens, lq, k, path);
+  if (L.fused) {
+    L.n_seg = tc_topk_segments(total_tokens);
+    L.cand = o; o += align256(size_t(nq) * size_t(L.n_seg) * size_t(tc_topk_list_len()) * sizeof(uint64_t));
+  } else {
+    L.scores = o; o += align256(size_t(nq) * size_t(n_docs) * sizeof(float));
+    L.part_bytes = maxsim_tc_workspace_bytes(n_docs, nq, lq);
+    L.part = o; o += align256(L.part_bytes);
+    L.topk_bytes = topk_workspace_bytes(n_docs, nq, k);
+    L.topk = o; o += align256(L.topk_bytes);
+  }
   L.total = o;
   return L;
 }
 
-struct RerankLayout {      // hrc_rerank: candidate scores, slot partials, top-k scratch, keys
-  size_t scores, part, topk, keys, total, part_bytes, topk_bytes;
+struct RerankLayout {      // hrc_rerank: candidate scores, per-query arrival counters, slot partials, top-k scratch, keys
+  size_t scores, counter, part, topk, keys, total, part_bytes, topk_bytes;
 };
 static RerankLayout rerank_layout(int n_cand, int nq, int lq, int k) {
   RerankLayout L;
   size_t o = 0;
   L.scores = o; o += align256(size_t(nq) * size_t(n_cand) * sizeof(float));
+  L.counter = o; o += align256(size_t(nq) * sizeof(uint32_t));
   L.part_bytes = maxsim_tc_workspace_bytes(n_cand, nq, lq);
   L.part = o; o += align256(L.part_bytes);
   L.topk_bytes = topk_workspace_bytes(n_cand, nq, k);
@@ -164,10 +188,11 @@ static RerankLayout rerank_layout(int n_cand, int nq, int lq, int k) {
 struct HybridLayout {
   size_t search, keys, col_ids, fused_ids, fused_scores, counts, rerank, pos, total, search_bytes, rerank_bytes;
 };
-static HybridLayout hybrid_layout(int64_t n_docs, int nq, int lq, int colbert_k, int n_cand, int final_k) {
+static HybridLayout hybrid_layout(int64_t n_docs, int64_t total_tokens, int nq, int lq, int colbert_k, int n_cand,
+                                  int final_k, int path) {
   HybridLayout L;
   size_t o = 0;
-  L.search_bytes = search_layout(n_docs, nq, lq, colbert_k).total;
+  L.search_bytes = search_layout(n_docs, total_tokens, nq, lq, colbert_k, path).total;
   L.search = o; o += align256(L.search_bytes);
   L.keys = o; o += align256(size_t(nq) * colbert_k * sizeof(uint64_t));
   L.col_ids = o; o += align256(size_t(nq) * colbert_k * sizeof(int32_t));
@@ -184,12 +209,12 @@ static HybridLayout hybrid_layout(int64_t n_docs, int nq, int lq, int colbert_k,
 struct HostSearchLayout {
   size_t q32, q16, search, keys, ids, out_scores, total, search_bytes;
 };
-static HostSearchLayout host_search_layout(int64_t n_docs, int n_queries, int lq, int k) {
+static HostSearchLayout host_search_layout(int64_t n_docs, int64_t total_tokens, int n_queries, int lq, int k, int path) {
   HostSearchLayout L;
   size_t o = 0;
   L.q32 = o; o += align256(size_t(n_queries) * lq * HRC_DIM * sizeof(float));
   L.q16 = o; o += align256(size_t(n_queries) * lq * HRC_DIM * 2);
-  L.search_bytes = search_layout(n_docs, n_queries, lq, k).total;
+  L.search_bytes = search_layout(n_docs, total_tokens, n_queries, lq, k, path).total;
   L.search = o; o += align256(L.search_bytes);
   L.keys = o; o += align256(size_t(n_queries) * k * sizeof(uint64_t));
   L.ids = o; o += align256(size_t(n_queries) * k * sizeof(int32_t));
@@ -285,22 +310,34 @@ int hrc_meanpool_cosine_scores(const void* d_tokens, const int64_t* d_offsets, i
                                 static_cast<cudaStream_t>(stream));
 }
 
-size_t hrc_search_workspace_bytes(int64_t n_docs, int n_queries, int lq, int k) {
-  if (n_docs < 0 || n_queries < 0 || lq < 1 || k < 0) return 0;
-  return search_layout(n_docs, n_queries, lq, k).total;
+size_t hrc_search_workspace_bytes(int64_t n_docs, int64_t total_tokens, int n_queries, int lq, int k, int path) {
+  if (n_docs < 0 || total_tokens < 0 || n_queries < 0 || lq < 1 || k < 0) return 0;
+  return search_layout(n_docs, total_tokens, n_queries, lq, k, path).total;
 }
 
 int hrc_search(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens, const void* d_queries,
                int n_queries, int lq, int k, int32_t id_base, void* d_workspace, size_t workspace_bytes,
                uint64_t* d_keys_out, int32_t* d_ids_out, float* d_scores_out, int path, void* stream) {
+  if (int rc = check_device()) return rc;
   HRC_REQUIRE(n_queries >= 0 && lq >= 1 && k >= 0 && k <= n_docs, "search: k=%d must be in [0, n_docs]", k);
   if (n_queries == 0 || k == 0) return 0;
-  HRC_REQUIRE(d_keys_out != nullptr && d_workspace != nullptr, "search: null buffer");
-  const SearchLayout L = search_layout(n_docs, n_queries, lq, k);
+  HRC_REQUIRE(d_keys_out != nullptr && d_workspace != nullptr && d_tokens != nullptr && d_offsets != nullptr &&
+                  d_queries != nullptr, "search: null buffer");
+  const SearchLayout L = search_layout(n_docs, total_tokens, n_queries, lq, k, path);
   HRC_REQUIRE(workspace_bytes >= L.total, "search: workspace too small (%zu < %zu)", workspace_bytes, L.total);
   HRC_REQUIRE(aligned256(d_workspace), "search: workspace must be 256-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+  if (L.fused) {
+    // MaxSim with the per-segment top-k fused into its epilogue, then ONE launch that merges the segments' lists,
+    // sorts and unpacks: two launches per search, no [n_queries x n_docs] matrix in HBM.
+    HRC_REQUIRE(n_queries <= 65535, "search: too many queries (%d)", n_queries);
+    uint64_t* cand = reinterpret_cast<uint64_t*>(ws + L.cand);
+    if (int rc = launch_maxsim_tc_topk(d_tokens, d_offsets, n_docs, total_tokens, d_queries, n_queries, lq, k, id_base,
+                                       nullptr, cand, st))
+      return rc;
+    return launch_topk_merge(cand, L.n_seg * tc_topk_list_len(), n_queries, k, d_keys_out, st, d_ids_out, d_scores_out);
+  }
   float* scores = reinterpret_cast<float*>(ws + L.scores);
   if (int rc = maxsim_dispatch(d_tokens, d_offsets, n_docs, total_tokens, nullptr, n_docs, d_queries, n_queries, lq,
                                scores, path, ws + L.part, L.part_bytes, st))
@@ -312,9 +349,9 @@ int hrc_search(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, i
   return 0;
 }
 
-size_t hrc_search_host_workspace_bytes(int64_t n_docs, int n_queries, int lq, int k) {
-  if (n_docs < 0 || n_queries < 0 || lq < 1 || k < 0) return 0;
-  return host_search_layout(n_docs, n_queries, lq, k).total;
+size_t hrc_search_host_workspace_bytes(int64_t n_docs, int64_t total_tokens, int n_queries, int lq, int k, int path) {
+  if (n_docs < 0 || total_tokens < 0 || n_queries < 0 || lq < 1 || k < 0) return 0;
+  return host_search_layout(n_docs, total_tokens, n_queries, lq, k, path).total;
 }
 
 int hrc_search_host(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
@@ -325,7 +362,7 @@ int hrc_search_host(const void* d_tokens, const int64_t* d_offsets, int64_t n_do
   if (n_queries == 0 || k == 0) return 0;
   HRC_REQUIRE(h_queries != nullptr && h_ids_out != nullptr && h_scores_out != nullptr && d_workspace != nullptr,
               "search_host: null buffer");
-  const HostSearchLayout L = host_search_layout(n_docs, n_queries, lq, k);
+  const HostSearchLayout L = host_search_layout(n_docs, total_tokens, n_queries, lq, k, path);
   HRC_REQUIRE(workspace_bytes >= L.total, "search_host: workspace too small (%zu < %zu)", workspace_bytes, L.total);
   HRC_REQUIRE(aligned256(d_workspace), "search_host: workspace must be 256-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -367,6 +404,16 @@ int hrc_rerank(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, i
   uint8_t* ws = static_cast<uint8_t*>(d_workspace);
   float* scores = d_cand_scores_out != nullptr ? d_cand_scores_out : reinterpret_cast<float*>(ws + L.scores);
   uint64_t* keys = reinterpret_cast<uint64_t*>(ws + L.keys);
+  if ((path == HRC_PATH_AUTO || path == HRC_PATH_TC) && tc_rerank_supported(total_tokens, lq, n_cand, k) &&
+      n_queries <= 65535) {
+    // ONE launch: every CTA scores one candidate, the last CTA of a query ranks them and writes the sorted top-k
+    if (int rc = check_device()) return rc;
+    HRC_REQUIRE(d_tokens != nullptr && d_offsets != nullptr && d_queries != nullptr && d_pos_out != nullptr &&
+                    d_scores_out != nullptr, "rerank: null buffer");
+    return launch_maxsim_tc_rerank(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_cand, d_queries, n_queries, lq,
+                                   k, scores, reinterpret_cast<uint32_t*>(ws + L.counter), d_pos_out, d_ids_out,
+                                   d_scores_out, st);
+  }
   if (int rc = maxsim_dispatch(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_cand, d_queries, n_queries, lq,
                                scores, path, ws + L.part, L.part_bytes, st))
     return rc;
@@ -374,10 +421,10 @@ int hrc_rerank(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, i
   return launch_rerank_unpack(keys, k, n_queries, d_cand_ids, n_cand, d_pos_out, d_ids_out, d_scores_out, st);
 }
 
-size_t hrc_hybrid_retrieve_workspace_bytes(int64_t n_docs, int n_queries, int lq, int colbert_k, int n_candidates,
-                                           int final_k) {
-  if (n_docs < 0 || n_queries < 0 || lq < 1 || colbert_k < 0 || n_candidates < 0 || final_k < 0) return 0;
-  return hybrid_layout(n_docs, n_queries, lq, colbert_k, n_candidates, final_k).total;
+size_t hrc_hybrid_retrieve_workspace_bytes(int64_t n_docs, int64_t total_tokens, int n_queries, int lq, int colbert_k,
+                                           int n_candidates, int final_k, int path) {
+  if (n_docs < 0 || total_tokens < 0 || n_queries < 0 || lq < 1 || colbert_k < 0 || n_candidates < 0 || final_k < 0) return 0;
+  return hybrid_layout(n_docs, total_tokens, n_queries, lq, colbert_k, n_candidates, final_k, path).total;
 }
 
 int hrc_hybrid_retrieve(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
@@ -391,7 +438,7 @@ int hrc_hybrid_retrieve(const void* d_tokens, const int64_t* d_offsets, int64_t 
   if (n_queries == 0) return 0;
   HRC_REQUIRE(d_workspace != nullptr && d_ids_out != nullptr && d_scores_out != nullptr && (n_bm25 == 0 || d_bm25_ids != nullptr),
               "hybrid_retrieve: null buffer");
-  const HybridLayout L = hybrid_layout(n_docs, n_queries, lq, colbert_k, n_candidates, final_k);
+  const HybridLayout L = hybrid_layout(n_docs, total_tokens, n_queries, lq, colbert_k, n_candidates, final_k, path);
   HRC_REQUIRE(workspace_bytes >= L.total, "hybrid_retrieve: workspace too small (%zu < %zu)", workspace_bytes, L.total);
   HRC_REQUIRE(aligned256(d_workspace), "hybrid_retrieve: workspace must be 256-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -54,6 +54,14 @@ constexpr int kTmemCols = 512;
 constexpr int kEpiWarp0 = 2;
 constexpr int kMaxSmem = 232448;                  // 227 KB opt-in limit per CTA
 
+// Fused top-k (TK kernels): every epilogue warp keeps, per query it scores, a shared-memory list of the best keys it
+// has emitted: [0, k) survivors of the last compaction + appended keys above the current k-th best.  A full list is
+// compacted by a warp-wide bitonic sort; at the end the warps of a CTA that share a query merge their lists and the
+// CTA hands kListOut keys per (query, segment) to the merge kernel.  The [n_queries x n_docs] score matrix is never
+// written (unless the caller asks for it).
+constexpr int kListCap = 256;                     // keys per list
+constexpr int kListOut = 128;                     // keys per (query, segment) handed to the merge: k <= 128
+
 #ifdef HRC_EXPERIMENTS
 #define HRC_DBG(p, bit) (((p).debug & (bit)) != 0)
 #else
@@ -78,7 +86,16 @@ __host__ __device__ constexpr int cta_threads(int mt, int zp) {
 struct TcParams {
   const int64_t* offsets;
   const int32_t* cand_ids;  // nullptr: corpus mode
-  float* scores;
+  float* scores;            // TK kernels: may be nullptr (scores are not materialised)
+  uint64_t* cand_keys;      // TK kernels: [n_queries][n_segments][kListOut] best keys per (query, segment), sorted
+  int k;                    // TK kernels: 1 <= k <= kListOut
+  int32_t id_base;          // TK kernels: global id of document 0
+  // candidate mode, fused rerank (all null / 0 otherwise): the LAST CTA of a query to finish ranks its n_items scores
+  uint32_t* rr_counter;     // [n_queries] zero on entry; reset to zero by the last CTA
+  int rr_k;                 // results per query
+  int32_t* rr_pos;          // [n_queries][rr_k] position in the candidate list
+  int32_t* rr_ids;          // [n_queries][rr_k] candidate document id (optional)
+  float* rr_scores;         // [n_queries][rr_k]
   int64_t n_docs;
   int64_t total_tokens;
   int64_t n_items;          // row stride of scores (n_docs, or n_cand)
@@ -146,7 +163,29 @@ __device__ __forceinline__ float max32_masked_acc(const uint32_t (&v)[32], uint3
   return max32_acc(t, m);
 }
 
-template <int MT, int ZP, int CG>
+// In-place descending bitonic sort of 256 keys in shared memory by ONE warp (36 compare-exchange stages, 4 pairs per
+// lane and stage).  ~2.5k cycles; runs a handful of times per warp and launch.
+__device__ __forceinline__ void warp_sort256_desc(uint64_t* a, int lane) {
+#pragma unroll 1
+  for (int size = 2; size <= kListCap; size <<= 1) {
+#pragma unroll 1
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < kListCap / 64; ++r) {
+        const int i = lane + 32 * r;
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const uint64_t x = a[lo], y = a[hi];
+        if ((x < y) == desc) { a[lo] = y; a[hi] = x; }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int MT, int ZP, int CG, bool TK>
 __global__ void __launch_bounds__(cta_threads(MT, ZP), 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_q,
                  const TcParams p) {
@@ -164,6 +203,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   static_assert(kTileBytes % 2048 == 0, "tile slabs must stay 1024-byte aligned for the 128B swizzle");
   static_assert((MT == 1 && (ZP == 1 || ZP == 2) && CG == 1) || (MT == 2 && ZP == 0 && (CG == 1 || CG == 2)),
                 "instantiations: <1,1,1> <1,2,1> <2,0,1> <2,0,2>");
+  static_assert(!(TK && ZP == 2), "fused top-k: not for the M=64 variant (its scores are combined with atomicAdd)");
   // A tile's accumulators (all M-tiles) are ONE unit: one tfull / tempty pair per stage.  The warps of a lane group
   // alternate DOCUMENTS and each reads all M-tiles of a tile in one walk.
   // HBM-bound kernels (MT == 1): ONE tcgen05.commit per tile (tfull); the shared-memory slot is released by the
@@ -184,6 +224,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   uint64_t* qfull = bars + 28;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
   int64_t* seg = reinterpret_cast<int64_t*>(bars + 30);  // [0]=doc_begin [1]=doc_end [2]=tok_begin [3]=tok_end
+  uint64_t* lists = bars + 64;                           // TK: [kEpiWarps][MT][kListCap] keys
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -406,6 +447,31 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
 #pragma unroll
     for (int j = 0; j < MT; ++j) pend_m[j] = 0.f;
 
+    // TK: this warp's key lists (one per M-tile).  The emitting lanes — lane 0 for M-tile 0, lane 16 for M-tile 1 —
+    // own their list's fill count and threshold (the k-th best key so far; 0 = accept everything).
+    const int lidx = slot * rep + sub;                       // 0 .. kEpiWarps-1
+    uint64_t* my_lists = lists + size_t(lidx) * MT * kListCap;
+    uint64_t* lst = my_lists + ((MT == 2 && lane >= 16) ? kListCap : 0);
+    uint32_t cnt = 0;
+    uint64_t thr = 0;
+    if constexpr (TK) {
+      for (int i = lane; i < MT * kListCap; i += 32) my_lists[i] = 0;
+      __syncwarp();
+    }
+    auto append = [&](float score, int64_t doc) {           // emitting lane only
+      const uint64_t key = make_key(score, int32_t(p.id_base + int32_t(doc)));
+      if (key > thr) lst[cnt++] = key;
+    };
+    auto compact_full = [&]() {                              // whole warp: sort the full list(s), keep the best k
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        if (__shfl_sync(0xffffffffu, cnt, j * 16) >= uint32_t(kListCap)) {
+          warp_sort256_desc(my_lists + j * kListCap, lane);
+          if (lane == j * 16) { cnt = uint32_t(p.k); thr = lst[p.k - 1]; }
+        }
+      }
+    };
+
     auto emit_pending = [&]() {
       if constexpr (MT == 2) {
         // both M-tiles in ONE butterfly: after the first exchange lanes 0-15 carry M-tile 0 and lanes 16-31 M-tile 1
@@ -417,14 +483,24 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
         for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         const bool act = lo_half ? active[0] : active[1];
         const int64_t row = lo_half ? out_row[0] : out_row[1];
-        if ((lane & 15) == 0 && act) p.scores[row + pend_col] = a;
+        if ((lane & 15) == 0 && act) {
+          if (!TK || p.scores != nullptr) p.scores[row + pend_col] = a;
+          if constexpr (TK) append(a, pend_col);
+        }
       } else {
         // M=64: only lanes 0-15 of a lane group hold accumulator rows (16 query tokens)
         const float sc = warp_sum((ZP == 2 && lane >= 16) ? 0.f : pend_m[0]);
         if (lane == 0 && active[0]) {
           if constexpr (ZP == 2) atomicAdd(&p.scores[out_row[0] + pend_col], sc);   // the other token half adds its part
-          else p.scores[out_row[0] + pend_col] = sc;
+          else if (!TK || p.scores != nullptr) p.scores[out_row[0] + pend_col] = sc;
+          if constexpr (TK) append(sc, pend_col);
+          if constexpr (ZP == 1 && !TK) {
+            if (p.rr_counter != nullptr) __threadfence();   // fused rerank: the score must be visible to the last CTA
+          }
         }
+      }
+      if constexpr (TK) {
+        if (__any_sync(0xffffffffu, cnt >= uint32_t(kListCap))) compact_full();
       }
       pending = false;
     };
@@ -521,6 +597,35 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     }
     while (have_doc) finish_doc();          // trailing empty documents (no tokens, no tile): -inf
     if (pending) emit_pending();
+
+    if constexpr (TK) {
+      // every list sorted, best first
+#pragma unroll
+      for (int j = 0; j < MT; ++j) warp_sort256_desc(my_lists + j * kListCap, lane);
+      // the `rep` warps of a lane group scored disjoint documents for the same queries: tree-merge their lists
+      // (partner's best kListOut into the upper half, sort).  All epilogue warps meet at the named barrier.
+      for (int st = 1; st < rep; st <<= 1) {
+        asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
+        if ((sub & (2 * st - 1)) == 0 && sub + st < rep) {
+          const uint64_t* other = lists + size_t(lidx + st) * MT * kListCap;
+#pragma unroll
+          for (int j = 0; j < MT; ++j) {
+            for (int i = lane; i < kListOut; i += 32) my_lists[j * kListCap + kListOut + i] = other[j * kListCap + i];
+            warp_sort256_desc(my_lists + j * kListCap, lane);
+          }
+        }
+      }
+      if (sub == 0) {
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          if (active[j]) {
+            const int q = q_base + 4 * j + slot;
+            uint64_t* out = p.cand_keys + (int64_t(q) * p.n_segments + item) * kListOut;
+            for (int i = lane; i < kListOut; i += 32) out[i] = my_lists[j * kListCap + i];
+          }
+        }
+      }
+    }
   }
 
   tc_fence_before_sync();
@@ -530,6 +635,43 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   } else {
     __syncthreads();
     if (warp == 1) tmem_dealloc(acc_base, kTmemCols);
+  }
+
+  if constexpr (MT == 1 && ZP == 1 && !TK) {
+    // Fused rerank (candidate mode): every CTA scored ONE candidate; the last CTA of a query to get here ranks the
+    // query's n_items scores (rank by counting over 64-bit (score, position) keys: n_items <= 1024) and writes the
+    // sorted top rr_k — what torch.argsort(descending)[:k] does at local_rag_complete.py:789-792 — so that a rerank
+    // is ONE launch.  The tile ring is idle by now and holds the keys.
+    if (p.rr_counter != nullptr) {
+      volatile int* s_last = reinterpret_cast<volatile int*>(bars + 40);   // (no static shared memory: the dynamic
+                                                                            //  allocation already takes the whole 227 KB)
+      const int q = q_base;                               // candidate mode: one (virtual = real) query per blockIdx.y
+      if (threadIdx.x == 0) {
+        __threadfence();
+        *s_last = atomicAdd(&p.rr_counter[q], 1u) == uint32_t(p.n_items) - 1u;
+      }
+      __syncthreads();
+      if (*s_last) {
+        __threadfence();
+        const int n = int(p.n_items);
+        uint64_t* keys = reinterpret_cast<uint64_t*>(sD);
+        const float* row = p.scores + int64_t(q) * n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = make_key(__ldcg(row + i), i);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+          const uint64_t ki = keys[i];
+          int rank = 0;
+          for (int j = 0; j < n; ++j) rank += keys[j] > ki ? 1 : 0;
+          if (rank < p.rr_k) {
+            const int64_t o = int64_t(q) * p.rr_k + rank;
+            p.rr_pos[o] = i;
+            if (p.rr_ids != nullptr) p.rr_ids[o] = p.cand_ids[int64_t(q) * n + i];
+            p.rr_scores[o] = key_score(ki);
+          }
+        }
+        if (threadIdx.x == 0) p.rr_counter[q] = 0;
+      }
+    }
   }
 }
 
@@ -623,7 +765,7 @@ uint64_t g_watchdog_ns = 20ull * 1000000000ull;   // hrc_set_watchdog_ms
 int g_debug = 0;                                  // hrc_exp_set_debug
 #endif
 
-template <int MT, int ZP, int CG>
+template <int MT, int ZP, int CG, bool TK = false>
 int launch_cfg(const void* d_tokens, const void* d_queries, int lq, int n_real_queries, TcParams p, dim3 grid,
                cudaStream_t stream) {
   constexpr int kTileBytes = (TN / CG) * HRC_DIM * 2;   // what ONE CTA stages per tile
@@ -632,14 +774,15 @@ int launch_cfg(const void* d_tokens, const void* d_queries, int lq, int n_real_q
   if (int rc = cached_map(d_tokens, uint64_t(p.total_tokens), 0, TN / CG, &tmap_d)) return rc;
   if (int rc = cached_map(d_queries, uint64_t(lq), uint64_t(n_real_queries), 32, &tmap_q)) return rc;
   const int q_bytes = MT * kQBytes;
-  int stages = (kMaxSmem - 1024 - 512 - q_bytes) / kTileBytes;
+  const int list_bytes = TK ? epi_warps(MT, ZP) * MT * kListCap * 8 : 0;
+  int stages = (kMaxSmem - 1024 - 512 - q_bytes - list_bytes) / kTileBytes;
   if (stages > 8) stages = 8;
   p.n_stages = stages;
-  const int smem_bytes = 1024 + q_bytes + stages * kTileBytes + 512;
+  const int smem_bytes = 1024 + q_bytes + stages * kTileBytes + 512 + list_bytes;
   static PerDeviceOnce once;
   int dev;
   if (once.pending(&dev)) {
-    HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT, ZP, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT, ZP, CG, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kMaxSmem));
     once.mark(dev);
   }
@@ -659,9 +802,9 @@ int launch_cfg(const void* d_tokens, const void* d_queries, int lq, int n_real_q
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    HRC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, maxsim_tc_kernel<MT, ZP, CG>, tmap_d, tmap_q, p));
+    HRC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, maxsim_tc_kernel<MT, ZP, CG, TK>, tmap_d, tmap_q, p));
   } else {
-    maxsim_tc_kernel<MT, ZP, CG><<<grid, cta_threads(MT, ZP), smem_bytes, stream>>>(tmap_d, tmap_q, p);
+    maxsim_tc_kernel<MT, ZP, CG, TK><<<grid, cta_threads(MT, ZP), smem_bytes, stream>>>(tmap_d, tmap_q, p);
   }
   trace_end(stream);
   count_launch();
@@ -680,9 +823,24 @@ __global__ void sum_slots_kernel(const float* __restrict__ part, int q_slots, in
   out[i] = acc;
 }
 
+struct TopkOut {            // fused top-k request (corpus mode, lq <= 32, k <= kListOut)
+  uint64_t* cand_keys;
+  int k;
+  int32_t id_base;
+};
+struct RerankOut {          // fused rerank request (candidate mode, lq <= 32, n_cand <= kRerankFusedMax)
+  uint32_t* counter;
+  int k;
+  int32_t* pos;
+  int32_t* ids;
+  float* scores;
+};
+constexpr int kRerankFusedMax = 1024;
+
 int launch_tc_slots(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
                     const int32_t* d_cand_ids, int64_t n_items, const void* d_queries, int n_real_queries,
-                    int q_slots, int lq, float* d_scores, bool m64, cudaStream_t stream) {
+                    int q_slots, int lq, float* d_scores, bool m64, const TopkOut* tk, const RerankOut* rr,
+                    cudaStream_t stream) {
   const int n_queries = n_real_queries * q_slots;      // virtual queries from here on
   HRC_REQUIRE(total_tokens > 0 && total_tokens < (1ll << 31), "tc path: total_tokens=%lld out of range",
               (long long)total_tokens);
@@ -693,6 +851,14 @@ int launch_tc_slots(const void* d_tokens, const int64_t* d_offsets, int64_t n_do
   p.offsets = d_offsets;
   p.cand_ids = d_cand_ids;
   p.scores = d_scores;
+  p.cand_keys = tk ? tk->cand_keys : nullptr;
+  p.k = tk ? tk->k : 0;
+  p.id_base = tk ? tk->id_base : 0;
+  p.rr_counter = rr ? rr->counter : nullptr;
+  p.rr_k = rr ? rr->k : 0;
+  p.rr_pos = rr ? rr->pos : nullptr;
+  p.rr_ids = rr ? rr->ids : nullptr;
+  p.rr_scores = rr ? rr->scores : nullptr;
   p.n_docs = n_docs;
   p.total_tokens = total_tokens;
   p.n_items = n_items;
@@ -719,6 +885,7 @@ int launch_tc_slots(const void* d_tokens, const int64_t* d_offsets, int64_t n_do
   p.n_segments = int(tiles < sm_count() ? tiles : sm_count());
   if (n_queries <= 4) {
     p.slots_used = n_queries == 1 ? 1 : (n_queries == 2 ? 2 : 4);
+    if (tk) return launch_cfg<1, 1, 1, true>(d_tokens, d_queries, lq, n_real_queries, p, dim3((unsigned)p.n_segments), stream);
     if (m64 && n_queries <= 2)
       return launch_cfg<1, 2, 1>(d_tokens, d_queries, lq, n_real_queries, p, dim3((unsigned)p.n_segments), stream);
     return launch_cfg<1, 1, 1>(d_tokens, d_queries, lq, n_real_queries, p, dim3((unsigned)p.n_segments), stream);
@@ -735,21 +902,25 @@ int launch_tc_slots(const void* d_tokens, const int64_t* d_offsets, int64_t n_do
     TcParams pp = p;
     pp.n_qgroups = paired;
     pp.n_queries = n_queries < paired * 8 ? n_queries : paired * 8;
-    int rc = launch_cfg<2, 0, 2>(d_tokens, d_queries, lq, n_real_queries, pp, dim3((unsigned)(pp.n_segments * paired)),
-                                 stream);
+    const dim3 pgrid((unsigned)(pp.n_segments * paired));
+    int rc = tk ? launch_cfg<2, 0, 2, true>(d_tokens, d_queries, lq, n_real_queries, pp, pgrid, stream)
+                : launch_cfg<2, 0, 2>(d_tokens, d_queries, lq, n_real_queries, pp, pgrid, stream);
     if (rc != 0 || paired == p.n_qgroups) return rc;
     TcParams pl = p;                                    // the odd group: (virtual) queries [paired * 8, n_queries)
     pl.n_qgroups = 1;
     pl.vq_base = paired * 8;
-    return launch_cfg<2, 0, 1>(d_tokens, d_queries, lq, n_real_queries, pl, dim3((unsigned)pl.n_segments), stream);
+    return tk ? launch_cfg<2, 0, 1, true>(d_tokens, d_queries, lq, n_real_queries, pl, dim3((unsigned)pl.n_segments), stream)
+              : launch_cfg<2, 0, 1>(d_tokens, d_queries, lq, n_real_queries, pl, dim3((unsigned)pl.n_segments), stream);
   }
-  return launch_cfg<2, 0, 1>(d_tokens, d_queries, lq, n_real_queries, p, dim3((unsigned)(p.n_segments * p.n_qgroups)),
-                             stream);
+  const dim3 grid((unsigned)(p.n_segments * p.n_qgroups));
+  return tk ? launch_cfg<2, 0, 1, true>(d_tokens, d_queries, lq, n_real_queries, p, grid, stream)
+            : launch_cfg<2, 0, 1>(d_tokens, d_queries, lq, n_real_queries, p, grid, stream);
 }
 
 }  // namespace
 
 void set_watchdog_ns(uint64_t ns) { g_watchdog_ns = ns; }
+uint64_t get_watchdog_ns() { return g_watchdog_ns; }
 #ifdef HRC_EXPERIMENTS
 void set_debug(int bits) { g_debug = bits; }
 #endif
@@ -768,6 +939,48 @@ void store_release(const void* base) {
     if (g_maps[i].base == base) g_maps[i] = MapEntry();
 }
 
+// ---- fused MaxSim + per-segment top-k (hrc_search's default) -------------------------------------------------------
+bool tc_topk_supported(int64_t total_tokens, int lq, int k) {
+  return total_tokens > 0 && total_tokens < (1ll << 31) && lq >= 1 && lq <= HRC_TC_MAX_LQ && k >= 1 && k <= kListOut;
+}
+int tc_topk_segments(int64_t total_tokens) {     // CTAs along the corpus = key lists per query
+  const int64_t tiles = (total_tokens + TN - 1) / TN;
+  return int(tiles < sm_count() ? tiles : sm_count());
+}
+int tc_topk_list_len() { return kListOut; }
+// d_cand_keys: uint64 [n_queries][tc_topk_segments()][kListOut]; d_scores optional (the full matrix, if wanted)
+int launch_maxsim_tc_topk(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                          const void* d_queries, int n_queries, int lq, int k, int32_t id_base, float* d_scores,
+                          uint64_t* d_cand_keys, cudaStream_t stream) {
+  if (n_docs == 0 || n_queries == 0) return 0;
+  HRC_REQUIRE(tc_topk_supported(total_tokens, lq, k), "fused top-k: needs lq <= %d and k <= %d", HRC_TC_MAX_LQ, kListOut);
+  HRC_REQUIRE(d_cand_keys != nullptr, "fused top-k: null candidate buffer");
+  const TopkOut tk{d_cand_keys, k, id_base};
+  return launch_tc_slots(d_tokens, d_offsets, n_docs, total_tokens, nullptr, n_docs, d_queries, n_queries, 1, lq, d_scores,
+                         false, &tk, nullptr, stream);
+}
+
+// ---- fused rerank: candidate MaxSim + sorted top-k in ONE launch (hrc_rerank's default) ----------------------------
+bool tc_rerank_supported(int64_t total_tokens, int lq, int n_cand, int k) {
+  return total_tokens > 0 && total_tokens < (1ll << 31) && lq >= 1 && lq <= HRC_TC_MAX_LQ && n_cand >= 1 &&
+         n_cand <= kRerankFusedMax && k >= 1 && k <= n_cand;
+}
+// d_scores: fp32 [n_queries][n_cand] (every candidate's score); d_counter: uint32 [n_queries], zeroed here
+int launch_maxsim_tc_rerank(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                            const int32_t* d_cand_ids, int n_cand, const void* d_queries, int n_queries, int lq, int k,
+                            float* d_scores, uint32_t* d_counter, int32_t* d_pos, int32_t* d_ids, float* d_scores_out,
+                            cudaStream_t stream) {
+  if (n_queries == 0) return 0;
+  HRC_REQUIRE(tc_rerank_supported(total_tokens, lq, n_cand, k), "fused rerank: needs lq <= %d, n_cand <= %d", HRC_TC_MAX_LQ,
+              kRerankFusedMax);
+  HRC_REQUIRE(d_scores != nullptr && d_counter != nullptr && d_pos != nullptr && d_scores_out != nullptr,
+              "fused rerank: null buffer");
+  HRC_CHECK_CUDA(cudaMemsetAsync(d_counter, 0, size_t(n_queries) * sizeof(uint32_t), stream));
+  const RerankOut rr{d_counter, k, d_pos, d_ids, d_scores_out};
+  return launch_tc_slots(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_cand, d_queries, n_queries, 1, lq,
+                         d_scores, false, nullptr, &rr, stream);
+}
+
 // bytes of caller workspace the tensor-core path needs: the per-slot partial scores of queries longer than 32 tokens
 size_t maxsim_tc_workspace_bytes(int64_t n_items, int n_queries, int lq) {
   const int q_slots = (lq + HRC_TC_MAX_LQ - 1) / HRC_TC_MAX_LQ;
@@ -784,7 +997,7 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
   const int q_slots = (lq + HRC_TC_MAX_LQ - 1) / HRC_TC_MAX_LQ;
   if (q_slots == 1)
     return launch_tc_slots(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_items, d_queries, n_queries, 1, lq,
-                           d_scores, m64, stream);
+                           d_scores, m64, nullptr, nullptr, stream);
   // A query of more than 32 tokens is scored as q_slots virtual queries of <= 32 tokens (rows beyond lq arrive as
   // zeros from TMA and add max_t <0, d_t> = 0); their partial scores (caller workspace) are summed in slot order.
   HRC_REQUIRE(int64_t(n_queries) * q_slots <= 65535, "tc path: too many query slots (%d x %d)", n_queries, q_slots);
@@ -795,7 +1008,7 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
   float* part = static_cast<float*>(d_workspace);
   const int64_t total = int64_t(n_queries) * n_items;
   if (int rc = launch_tc_slots(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_items, d_queries, n_queries,
-                               q_slots, lq, part, m64, stream))
+                               q_slots, lq, part, m64, nullptr, nullptr, stream))
     return rc;
   sum_slots_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(part, q_slots, n_items, total, d_scores);
   count_launch();

@@ -13,6 +13,8 @@
 //            shared memory) the same select over candidate keys; the last level bitonic-sorts.
 // The same stage-2 kernel is hrc_topk_merge, the on-device merge of all-gathered per-GPU lists.
 // HBM traffic: 4 B per score, once.
+#include <cstdio>
+
 #include "hrc_common.cuh"
 
 namespace hrc {
@@ -178,9 +180,11 @@ select_scores_kernel(const float* __restrict__ scores, const int32_t* __restrict
   select_topk(keys, cn, k, dst, final_sorted != 0, sort_buf, sc);
 }
 
+// ids_out / scores_out (optional, final level only): the unpacked result, so that no separate unpack launch is needed
 __global__ void __launch_bounds__(kSelThreads)
 select_keys_kernel(const uint64_t* __restrict__ keys_in, int n_in, int k, uint64_t* __restrict__ out,
-                   int n_groups, int group_len, int final_sorted) {
+                   int n_groups, int group_len, int final_sorted, int32_t* __restrict__ ids_out,
+                   float* __restrict__ scores_out) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem);
   uint64_t* sort_buf = keys + group_len;
@@ -195,6 +199,61 @@ select_keys_kernel(const uint64_t* __restrict__ keys_in, int n_in, int k, uint64
   __syncthreads();
   uint64_t* dst = out + (row * n_groups + group) * k;
   select_topk(keys, gn, k, dst, final_sorted != 0, sort_buf, sc);
+  if (final_sorted && (ids_out != nullptr || scores_out != nullptr)) {     // sort_buf still holds the sorted keys
+    for (int i = threadIdx.x; i < k; i += kSelThreads) {
+      const uint64_t key = sort_buf[i];
+      if (ids_out) ids_out[row * k + i] = key ? key_id(key) : -1;
+      if (scores_out) scores_out[row * k + i] = key ? key_score(key) : -INFINITY;
+    }
+  }
+}
+
+// Merge of per-rank key lists (the multi-GPU exchange step): row r's input is parts[p * part_stride + r * k + j] for
+// p < n_parts, j < k — the layout an all-gather of [n_rows][k] blocks produces.  With `flags` (P2P transport) the CTA
+// first ACQUIRES flags[0..n_flags) >= seq at system scope: the peers' stores of this step's keys are then visible.
+__global__ void __launch_bounds__(kSelThreads)
+merge_parts_kernel(const uint64_t* __restrict__ parts, int n_parts, int64_t part_stride, int k, uint64_t* __restrict__ out,
+                   int32_t* __restrict__ ids_out, float* __restrict__ scores_out, const uint64_t* flags, uint64_t seq,
+                   int n_flags, uint64_t watchdog_ns) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem);
+  const int n = n_parts * k;
+  uint64_t* sort_buf = keys + n;
+  __shared__ SelectScratch sc;
+  if (flags != nullptr) {
+    if (int(threadIdx.x) < n_flags) {
+      uint64_t t0 = 0, v = 0;
+      uint32_t spins = 0;
+      while (true) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+        if (v >= seq) break;
+        if ((++spins & 0xffu) == 0 && watchdog_ns != 0) {
+          uint64_t now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          if (now - t0 > watchdog_ns) {
+            printf("hrc: peer %d never published step %llu\n", int(threadIdx.x), (unsigned long long)seq);
+            __trap();
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int64_t row = blockIdx.x;
+  for (int i = threadIdx.x; i < n; i += kSelThreads) {
+    const int p = i / k, j = i - p * k;
+    keys[i] = __ldcg(parts + int64_t(p) * part_stride + row * k + j);
+  }
+  __syncthreads();
+  select_topk(keys, n, k, out + row * k, true, sort_buf, sc);
+  if (ids_out != nullptr || scores_out != nullptr) {
+    for (int i = threadIdx.x; i < k; i += kSelThreads) {
+      const uint64_t key = sort_buf[i];
+      if (ids_out) ids_out[row * k + i] = key ? key_id(key) : -1;
+      if (scores_out) scores_out[row * k + i] = key ? key_score(key) : -INFINITY;
+    }
+  }
 }
 
 __global__ void keys_unpack_kernel(const uint64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ ids,
@@ -234,13 +293,15 @@ int configure_smem() {
                                       kChunk * 8 + kSortMax * 8));
   HRC_CHECK_CUDA(cudaFuncSetAttribute(select_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       kMergeMax * 8 + kSortMax * 8));
+  HRC_CHECK_CUDA(cudaFuncSetAttribute(merge_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kMergeMax * 8 + kSortMax * 8));
   once.mark(dev);
   return 0;
 }
 
 // levels of stage 2 over n_in keys per row; writes sorted top-k to d_out.  tmp holds intermediates.
 int run_key_levels(const uint64_t* d_in, int64_t n_in, int n_rows, int k, uint64_t* d_out, uint64_t* tmp0,
-                   uint64_t* tmp1, cudaStream_t stream) {
+                   uint64_t* tmp1, cudaStream_t stream, int32_t* d_ids_out = nullptr, float* d_scores_out = nullptr) {
   const uint64_t* cur = d_in;
   int64_t cur_n = n_in;
   int flip = 0;
@@ -251,8 +312,9 @@ int run_key_levels(const uint64_t* d_in, int64_t n_in, int n_rows, int k, uint64
     uint64_t* dst = last ? d_out : (flip ? tmp1 : tmp0);
     HRC_REQUIRE(dst != nullptr, "top-k: %lld candidate keys per row need workspace", (long long)cur_n);
     const size_t smem = size_t(group_len) * 8 + (last ? sort_buf_bytes(k) : 0);
-    select_keys_kernel<<<dim3(n_groups, n_rows), kSelThreads, smem, stream>>>(cur, int(cur_n), k, dst, n_groups,
-                                                                             group_len, last ? 1 : 0);
+    select_keys_kernel<<<dim3(n_groups, n_rows), kSelThreads, smem, stream>>>(
+        cur, int(cur_n), k, dst, n_groups, group_len, last ? 1 : 0, last ? d_ids_out : nullptr,
+        last ? d_scores_out : nullptr);
     count_launch();
     HRC_CHECK_CUDA(cudaGetLastError());
     if (last) break;
@@ -308,7 +370,7 @@ int launch_topk(const float* d_scores, const int32_t* d_ids, int64_t n, int n_ro
 }
 
 int launch_topk_merge(const uint64_t* d_keys_in, int n_in, int n_rows, int k, uint64_t* d_keys_out,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, int32_t* d_ids_out, float* d_scores_out) {
   if (n_rows == 0 || k == 0) return 0;
   HRC_REQUIRE(k >= 1 && k <= HRC_MAX_TOPK, "top-k merge: k=%d not in [1,%d]", k, HRC_MAX_TOPK);
   HRC_REQUIRE(n_in >= 0 && n_in <= kMergeMax, "top-k merge: n_in=%d exceeds %d", n_in, kMergeMax);
@@ -318,7 +380,25 @@ int launch_topk_merge(const uint64_t* d_keys_in, int n_in, int n_rows, int k, ui
     HRC_CHECK_CUDA(cudaMemsetAsync(d_keys_out, 0, size_t(n_rows) * k * 8, stream));
     return 0;
   }
-  return run_key_levels(d_keys_in, n_in, n_rows, k, d_keys_out, nullptr, nullptr, stream);
+  return run_key_levels(d_keys_in, n_in, n_rows, k, d_keys_out, nullptr, nullptr, stream, d_ids_out, d_scores_out);
+}
+
+uint64_t get_watchdog_ns();
+
+int launch_topk_merge_parts(const uint64_t* d_parts, int n_parts, int part_stride, int n_rows, int k, uint64_t* d_keys_out,
+                            cudaStream_t stream, int32_t* d_ids_out, float* d_scores_out, const uint64_t* d_flags,
+                            uint64_t seq, int n_flags, uint64_t) {
+  if (n_rows == 0 || k == 0) return 0;
+  HRC_REQUIRE(k >= 1 && k <= HRC_MAX_TOPK, "merge: k=%d not in [1,%d]", k, HRC_MAX_TOPK);
+  HRC_REQUIRE(n_parts >= 1 && int64_t(n_parts) * k <= kMergeMax, "merge: %d x %d keys exceed %d", n_parts, k, kMergeMax);
+  HRC_REQUIRE(n_rows <= 65535 && n_flags <= kSelThreads, "merge: too many rows (%d)", n_rows);
+  if (configure_smem()) return 1;
+  const size_t smem = size_t(n_parts) * k * 8 + sort_buf_bytes(k);
+  merge_parts_kernel<<<n_rows, kSelThreads, smem, stream>>>(d_parts, n_parts, part_stride, k, d_keys_out, d_ids_out,
+                                                            d_scores_out, d_flags, seq, n_flags, get_watchdog_ns());
+  count_launch();
+  HRC_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int launch_rerank_unpack(const uint64_t* d_keys, int k, int n_rows, const int32_t* d_cand, int n_cand, int32_t* d_pos,

@@ -123,11 +123,14 @@ int hrc_meanpool_cosine_scores(const void* d_tokens, const int64_t* d_offsets, i
 /*
  * Fused search: MaxSim of every query against the whole store, per-query top-k, optional unpacking —
  * the body of JinaColBERTRetriever.search (local_rag_complete.py:764-775) in one call.
- *   d_workspace  : hrc_search_workspace_bytes(n_docs, n_queries, lq, k) bytes of scratch, 256-B aligned
+ * With the tensor-core path, lq <= 32 and k <= 128 this is TWO launches: the MaxSim kernel keeps a per-warp top-k of
+ * the scores its epilogue emits (the [n_queries x n_docs] score matrix is never written) and hands 128 keys per
+ * (query, corpus segment) to one merge-sort-unpack launch.  Otherwise: score matrix -> radix top-k -> unpack.
+ *   d_workspace  : hrc_search_workspace_bytes(n_docs, total_tokens, n_queries, lq, k, path) bytes of scratch, 256-B aligned
  *   d_keys_out   : uint64 [n_queries][k]; d_ids_out / d_scores_out optional int32 / fp32 [n_queries][k]
  * k <= HRC_MAX_TOPK and k <= n_docs.
  */
-size_t hrc_search_workspace_bytes(int64_t n_docs, int n_queries, int lq, int k);
+size_t hrc_search_workspace_bytes(int64_t n_docs, int64_t total_tokens, int n_queries, int lq, int k, int path);
 int hrc_search(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
                const void* d_queries, int n_queries, int lq, int k, int32_t id_base, void* d_workspace,
                size_t workspace_bytes, uint64_t* d_keys_out, int32_t* d_ids_out, float* d_scores_out, int path,
@@ -140,10 +143,10 @@ int hrc_search(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, i
  * D2H copies of ids and scores.  Everything is enqueued on `stream`; the caller synchronises the stream before
  * reading h_ids_out / h_scores_out.  Host buffers should be pinned (page-locked) for the copies to be asynchronous.
  *   h_queries    : fp32 [n_queries][lq][128] host
- *   d_workspace  : hrc_search_host_workspace_bytes(n_docs, n_queries, lq, k) bytes of device scratch, 256-B aligned
+ *   d_workspace  : hrc_search_host_workspace_bytes(n_docs, total_tokens, n_queries, lq, k, path) bytes of device scratch, 256-B aligned
  *   h_ids_out    : int32 [n_queries][k] host;  h_scores_out : fp32 [n_queries][k] host
  */
-size_t hrc_search_host_workspace_bytes(int64_t n_docs, int n_queries, int lq, int k);
+size_t hrc_search_host_workspace_bytes(int64_t n_docs, int64_t total_tokens, int n_queries, int lq, int k, int path);
 int hrc_search_host(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
                     const float* h_queries, int n_queries, int lq, int k, int32_t id_base, void* d_workspace,
                     size_t workspace_bytes, int32_t* h_ids_out, float* h_scores_out, int path, void* stream);
@@ -176,8 +179,8 @@ int hrc_rerank(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, i
  *   d_scores_out : fp32  [n_queries][final_k] MaxSim scores
  * Requires 1 <= colbert_k <= n_docs, 1 <= final_k <= n_candidates, n_bm25 + colbert_k <= 16384.
  */
-size_t hrc_hybrid_retrieve_workspace_bytes(int64_t n_docs, int n_queries, int lq, int colbert_k, int n_candidates,
-                                           int final_k);
+size_t hrc_hybrid_retrieve_workspace_bytes(int64_t n_docs, int64_t total_tokens, int n_queries, int lq, int colbert_k,
+                                           int n_candidates, int final_k, int path);
 int hrc_hybrid_retrieve(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
                         const void* d_queries, int n_queries, int lq, const int32_t* d_bm25_ids, int n_bm25,
                         int colbert_k, int rrf_k, int n_candidates, int final_k, int32_t id_base, void* d_workspace,

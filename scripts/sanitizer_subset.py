@@ -75,7 +75,7 @@ exp70[1, 3] = float("-inf")
 close(L.maxsim_scores_ids(tok_d, off_d, cand[:2].contiguous().to(dev), q70.to(dev)), exp70, "candidates lq=70")
 
 lit = L.meanpool_cosine_scores(tok_d, off_d, q_d).cpu()
-for d in (1, 5, 300):
+for d in (1, 5, 301):
     e = o.literal_reference(q.float(), tok[int(off[d]):int(off[d + 1])].float())
     assert float((lit[:, d] - e).abs().max()) < 1e-4
 print("ok meanpool cosine", flush=True)
