@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--secondary", default="sustained,read_peak,c4,c3,c1,ragged,c5",
                     help="comma-separated subset of the secondary measurements")
     ap.add_argument("--c5-global-docs", type=int, default=10_000_000)
+    ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p", "torch"],
+                    help="exchange step of the sharded search (N > 1): ncclAllGather inside libhrc (default), peer stores + "
+                         "flags inside libhrc, or torch.distributed")
     return ap.parse_args()
 
 
@@ -299,7 +302,7 @@ def run_ours(args):
     store = synth_store(n_global, DOC_LEN, DOC_LEN, seed=SEED, device=dev, rank=rank, world_size=world)
     retr = hrc.JinaColBERTRetriever(hrc.RAGConfig(device=str(dev)))
     retr.store = store
-    searcher = hrc.ShardedSearcher(retr) if world > 1 else None
+    searcher = hrc.ShardedSearcher(retr, transport=args.transport) if world > 1 else None
     n_q = 8
     queries = synth_queries(n_q, LQ, device=dev)                    # rotate queries; the corpus is what streams
     q_host = [synth_queries(n_q, LQ)[i:i + 1].float().pin_memory() for i in range(n_q)]   # what an encoder hands over
@@ -372,7 +375,7 @@ def run_ours(args):
     parity_check, breakdown = None, None
     if world > 1:
         parity_check = sharded_parity_check(torch, dist, _lib, retr, searcher, queries, rank, world, dev, args)
-        breakdown = sharded_breakdown(torch, dist, _lib, retr, searcher, queries, dev, max_over_ranks, barrier)
+        breakdown = sharded_breakdown(torch, dist, hrc, _lib, retr, searcher, queries, dev, max_over_ranks, barrier)
 
     # ---- secondary: sustained C2, read peak, C4 on the C2 corpus -------------------------------------------------
     if "sustained" in want:
@@ -482,8 +485,8 @@ def run_ours(args):
                 "ms_per_step": e2e["ms_per_step"], "step_ms": e2e["step_ms"],
                 "api": ("JinaColBERTRetriever.search_host: pinned fp32 query -> hrc_search_host (H2D, bf16, MaxSim, top-k, "
                         "unpack, D2H) -> ids/scores on the host" if world == 1 else
-                        "ShardedSearcher.search_host: pinned fp32 query -> H2D -> local search -> NCCL all-gather -> merge -> "
-                        "unpack -> D2H (pinned) -> ids/scores on the host")},
+                        f"ShardedSearcher.search_host (transport {args.transport}): pinned fp32 query -> hrc_sharded_search_host "
+                        "(H2D, bf16, local MaxSim + top-k, exchange of k keys per rank, merge + unpack, D2H), one C call per rank")},
         "gpu_launches": head["launches"],
         "clocks": head.get("clocks"),
     }
@@ -636,15 +639,24 @@ def sharded_parity_check(torch, dist, _lib, retr, searcher, queries, rank, world
         return f"parity check raised {type(exc).__name__}: {exc}"
 
 
-def sharded_breakdown(torch, dist, _lib, retr, searcher, queries, dev, max_over_ranks, barrier):
-    """Device time of the three parts of a sharded step, each timed alone (20 reps, CUDA events, max over ranks)."""
+def sharded_breakdown(torch, dist, hrc, _lib, retr, searcher, queries, dev, max_over_ranks, barrier):
+    """Device time of the parts of a sharded step, each timed alone (20 reps back to back, CUDA events, max over ranks):
+    the local search, and the exchange + merge with each transport."""
     from hybrid_rag_colbertv2_b200.sharded import all_gather_keys
     q = queries[0:1]
-    local = retr.search_keys(q, K)
-    gathered = all_gather_keys(local, K)
+    local = retr.search_keys(q, K).contiguous()
+    ws = _lib.Workspace()
+    p2p = searcher if searcher.transport == "p2p" else hrc.ShardedSearcher(retr, transport="p2p")
+    nccl_comm = searcher.comm if searcher.transport == "nccl" else p2p.comm
     parts = {"local_search_us": lambda: retr.search_keys(q, K),
-             "allgather_us": lambda: all_gather_keys(local, K),
-             "merge_us": lambda: _lib.topk_merge(gathered, K)}
+             "exchange_merge_nccl_us": lambda: _lib.allgather_merge_topk(nccl_comm, local, K, transport=_lib.TRANSPORT_NCCL, workspace=ws),
+             "exchange_merge_p2p_us": lambda: _lib.allgather_merge_topk(p2p.comm, local, K, transport=_lib.TRANSPORT_P2P, workspace=ws),
+             "exchange_merge_torch_us": lambda: _lib.topk_merge(all_gather_keys(local, K), K),
+             "step_nccl_us": lambda: _lib.sharded_search(nccl_comm, retr.store.tokens, retr.store.offsets, q, K,
+                                                         id_base=retr.store.doc_id_base, workspace=ws, unpack=False),
+             "step_p2p_us": lambda: _lib.sharded_search(p2p.comm, retr.store.tokens, retr.store.offsets, q, K,
+                                                        id_base=retr.store.doc_id_base, transport=_lib.TRANSPORT_P2P,
+                                                        workspace=ws, unpack=False)}
     out = {}
     for name, fn in parts.items():
         for _ in range(3):
@@ -657,8 +669,10 @@ def sharded_breakdown(torch, dist, _lib, retr, searcher, queries, dev, max_over_
         e1.record()
         barrier()
         out[name] = max_over_ranks(e0.elapsed_time(e1)) / 20 * 1e3
-    out["overhead_us"] = out["allgather_us"] + out["merge_us"]
-    out["note"] = "each part timed alone back to back; allgather = NCCL all_gather_into_tensor of k x 8 bytes per rank"
+    out["overhead_us"] = out[f"exchange_merge_{searcher.transport}_us"]
+    out["transport"] = searcher.transport
+    out["note"] = ("each part timed alone, 20 reps back to back; exchange = k x 8 bytes per rank; nccl = ncclAllGather + merge "
+                   "kernel, p2p = push kernel (peer stores + release flag) + merge kernel (acquires the flags), both inside libhrc")
     return out
 
 

@@ -51,7 +51,26 @@ SYMBOLS = {
     "hrc_rrf_fuse": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "hrc_synth_tokens": (_I, [_P, _I64, _I64, _U64, _P]),
     "hrc_read_probe": (_I, [_P, _SZ, _P, _P]),
+    "hrc_store_read_file": (_I, [_c.c_char_p, _I64, _I64, _P, _SZ, _P, _P]),
+    "hrc_store_write_file": (_I, [_c.c_char_p, _I64, _I64, _P, _SZ, _P, _P]),
+    "hrc_comm_unique_id": (_I, [_P]),
+    "hrc_comm_init": (_I, [_P, _I, _I, _P]),
+    "hrc_comm_enable_p2p": (_I, [_P, _I, _P]),
+    "hrc_comm_world": (_I, [_P]),
+    "hrc_comm_rank": (_I, [_P]),
+    "hrc_comm_destroy": (_I, [_P]),
+    "hrc_allgather_merge_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "hrc_allgather_merge_topk": (_I, [_P, _P, _I, _I, _I, _P, _SZ, _P, _P, _P, _P]),
+    "hrc_sharded_search_workspace_bytes": (_SZ, [_I, _I64, _I64, _I, _I, _I, _I]),
+    "hrc_sharded_search": (_I, [_P, _I, _P, _P, _I64, _I64, _P, _I, _I, _I, _I32, _P, _SZ, _P, _P, _P, _I, _P]),
+    "hrc_sharded_search_host_workspace_bytes": (_SZ, [_I, _I64, _I64, _I, _I, _I, _I]),
+    "hrc_sharded_search_host": (_I, [_P, _I, _P, _P, _I64, _I64, _P, _I, _I, _I, _I32, _P, _SZ, _P, _P, _I, _P]),
+    "hrc_sharded_hybrid_workspace_bytes": (_SZ, [_I, _I64, _I64, _I, _I, _I, _I, _I, _I]),
+    "hrc_sharded_hybrid_retrieve": (_I, [_P, _I, _P, _P, _I64, _I64, _I64, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I32, _P, _SZ,
+                                         _P, _P, _I, _P]),
 }
+TRANSPORT_NCCL, TRANSPORT_P2P = 0, 1
+COMM_ID_BYTES = 128
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -442,3 +461,170 @@ def read_probe(buf: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.T
         rc = load().hrc_read_probe(_ptr(buf), buf.numel() * buf.element_size(), _ptr(out), _stream(dev))
     _check(rc, "hrc_read_probe")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# multi-GPU exchange inside libhrc (one process per GPU)
+# ------------------------------------------------------------------------------------------------------------------
+class Comm:
+    """A libhrc communicator over the ranks of a torch.distributed group: NCCL all-gather or direct peer stores over
+    NVLink (transport P2P), both inside libhrc.so.  torch.distributed is only used ONCE, to hand rank 0's 128-byte id
+    to the other ranks."""
+
+    def __init__(self, device: torch.device, group=None, p2p_max_keys: int = 0):
+        import torch.distributed as dist
+        self.device = device
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        lib = load()
+        idbuf = (ctypes.c_uint8 * COMM_ID_BYTES)()
+        if self.rank == 0:
+            _check(lib.hrc_comm_unique_id(idbuf), "hrc_comm_unique_id")
+        payload = [bytes(idbuf)]
+        dist.broadcast_object_list(payload, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = (ctypes.c_uint8 * COMM_ID_BYTES).from_buffer_copy(payload[0])
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _check(lib.hrc_comm_init(raw, self.world, self.rank, ctypes.byref(handle)), "hrc_comm_init")
+        self.handle = handle
+        self.p2p_max_keys = 0
+        if p2p_max_keys:
+            self.enable_p2p(p2p_max_keys)
+
+    def enable_p2p(self, max_keys: int) -> None:
+        with torch.cuda.device(self.device):
+            _check(load().hrc_comm_enable_p2p(self.handle, int(max_keys), _stream(self.device)), "hrc_comm_enable_p2p")
+        self.p2p_max_keys = max(self.p2p_max_keys, int(max_keys))
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            load().hrc_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def allgather_merge_topk(comm: Comm, local_keys: torch.Tensor, k: int, *, transport: int = TRANSPORT_NCCL,
+                         workspace: Optional[Workspace] = None, unpack: bool = False):
+    """local_keys int64 [n_rows, k] (0 = empty) -> merged keys int64 [n_rows, k] (+ ids, scores with unpack=True)."""
+    dev = _require_cuda(local_keys)
+    assert local_keys.dtype == torch.int64 and local_keys.dim() == 2 and local_keys.shape[1] == k
+    n_rows = int(local_keys.shape[0])
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, int(load().hrc_allgather_merge_workspace_bytes(comm.world, n_rows, k)))
+    keys = torch.empty((n_rows, k), dtype=torch.int64, device=dev)
+    ids = torch.empty((n_rows, k), dtype=torch.int32, device=dev) if unpack else None
+    scores = torch.empty((n_rows, k), dtype=torch.float32, device=dev) if unpack else None
+    with torch.cuda.device(dev):
+        rc = load().hrc_allgather_merge_topk(comm.handle, _ptr(local_keys), n_rows, k, transport, ws_ptr, ws_bytes,
+                                             _ptr(keys), _ptr(ids), _ptr(scores), _stream(dev))
+    _check(rc, "hrc_allgather_merge_topk")
+    return keys, ids, scores
+
+
+def sharded_search(comm: Comm, tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.Tensor, k: int, *,
+                   id_base: int = 0, path: int = PATH_AUTO, transport: int = TRANSPORT_NCCL,
+                   workspace: Optional[Workspace] = None, unpack: bool = True):
+    """Local search over this rank's shard + exchange + merge in ONE C call.  Returns (keys, ids | None, scores | None)."""
+    dev = _require_cuda(tokens, offsets, queries)
+    _check_store(tokens, offsets)
+    _check_queries(queries)
+    n_docs = offsets.numel() - 1
+    nq, lq = int(queries.shape[0]), int(queries.shape[1])
+    need = int(load().hrc_sharded_search_workspace_bytes(comm.world, n_docs, int(tokens.shape[0]), nq, lq, k, path))
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, need)
+    keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    ids = torch.empty((nq, k), dtype=torch.int32, device=dev) if unpack else None
+    scores = torch.empty((nq, k), dtype=torch.float32, device=dev) if unpack else None
+    with torch.cuda.device(dev):
+        rc = load().hrc_sharded_search(comm.handle, transport, _ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]),
+                                       _ptr(queries), nq, lq, k, id_base, ws_ptr, ws_bytes, _ptr(keys), _ptr(ids),
+                                       _ptr(scores), path, _stream(dev))
+    _check(rc, "hrc_sharded_search")
+    return keys, ids, scores
+
+
+class ShardedHostSearch:
+    """hrc_sharded_search_host: pinned fp32 queries in, pinned ids / scores out, one C call and one synchronisation."""
+
+    def __init__(self, comm: Comm):
+        self.comm = comm
+        self.key = None
+
+    def __call__(self, tokens, offsets, queries_host, k, *, id_base=0, path=PATH_AUTO, transport=TRANSPORT_NCCL, copy=True):
+        dev = _require_cuda(tokens, offsets)
+        _check_store(tokens, offsets)
+        assert not queries_host.is_cuda and queries_host.dtype == torch.float32 and queries_host.dim() == 3
+        n_docs, total = offsets.numel() - 1, int(tokens.shape[0])
+        nq, lq = int(queries_host.shape[0]), int(queries_host.shape[1])
+        key = (str(dev), nq, lq, n_docs, total, k, path)
+        if self.key != key:
+            need = int(load().hrc_sharded_search_host_workspace_bytes(self.comm.world, n_docs, total, nq, lq, k, path))
+            self.ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+            self.ws_bytes = need
+            self.q_pinned = torch.empty((nq, lq, DIM), dtype=torch.float32).pin_memory()
+            self.ids = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+            self.scores = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+            self.key = key
+        src = queries_host.contiguous()
+        if not src.is_pinned():
+            self.q_pinned.copy_(src)
+            src = self.q_pinned
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            rc = load().hrc_sharded_search_host(self.comm.handle, transport, _ptr(tokens), _ptr(offsets), n_docs, total,
+                                                src.data_ptr(), nq, lq, k, id_base, _ptr(self.ws), self.ws_bytes,
+                                                self.ids.data_ptr(), self.scores.data_ptr(), path, stream.cuda_stream)
+            _check(rc, "hrc_sharded_search_host")
+            stream.synchronize()
+        return (self.ids.clone(), self.scores.clone()) if copy else (self.ids, self.scores)
+
+
+def sharded_hybrid_retrieve(comm: Comm, tokens: torch.Tensor, offsets: torch.Tensor, n_docs_global: int,
+                            queries: torch.Tensor, bm25_ids: torch.Tensor, *, colbert_k: int, rrf_k: int,
+                            n_candidates: int, final_k: int, id_base: int = 0, path: int = PATH_AUTO,
+                            transport: int = TRANSPORT_NCCL, workspace: Optional[Workspace] = None):
+    """The document-sharded hybrid pipeline, one C call per rank; every rank gets the same (ids, scores)."""
+    dev = _require_cuda(tokens, offsets, queries, bm25_ids)
+    _check_store(tokens, offsets)
+    _check_queries(queries)
+    assert bm25_ids.dtype == torch.int32 and bm25_ids.dim() == 2 and bm25_ids.shape[0] == queries.shape[0]
+    n_docs, total = offsets.numel() - 1, int(tokens.shape[0])
+    nq, lq = int(queries.shape[0]), int(queries.shape[1])
+    need = int(load().hrc_sharded_hybrid_workspace_bytes(comm.world, n_docs, total, nq, lq, colbert_k, n_candidates, final_k, path))
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, need)
+    ids = torch.empty((nq, final_k), dtype=torch.int32, device=dev)
+    scores = torch.empty((nq, final_k), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = load().hrc_sharded_hybrid_retrieve(comm.handle, transport, _ptr(tokens), _ptr(offsets), n_docs, total,
+                                                int(n_docs_global), _ptr(queries), nq, lq, _ptr(bm25_ids),
+                                                int(bm25_ids.shape[1]), colbert_k, rrf_k, n_candidates, final_k, id_base,
+                                                ws_ptr, ws_bytes, _ptr(ids), _ptr(scores), path, _stream(dev))
+    _check(rc, "hrc_sharded_hybrid_retrieve")
+    return ids, scores
+
+
+def store_read_file(path: str, file_offset: int, dst: torch.Tensor, chunk_bytes: int = 0) -> float:
+    """Stream dst.nbytes bytes of `path` from `file_offset` straight into the CUDA tensor `dst` (pinned double buffer,
+    one cudaMemcpyAsync per chunk).  Returns the elapsed seconds."""
+    dev = _require_cuda(dst)
+    secs = ctypes.c_double(0.0)
+    with torch.cuda.device(dev):
+        rc = load().hrc_store_read_file(os.fsencode(path), int(file_offset), dst.numel() * dst.element_size(), _ptr(dst),
+                                        int(chunk_bytes), _stream(dev), ctypes.byref(secs))
+    _check(rc, "hrc_store_read_file")
+    return float(secs.value)
+
+
+def store_write_file(path: str, file_offset: int, src: torch.Tensor, chunk_bytes: int = 0) -> float:
+    """Stream the CUDA tensor `src` into `path` at `file_offset` (pinned double buffer).  Returns the elapsed seconds."""
+    dev = _require_cuda(src)
+    secs = ctypes.c_double(0.0)
+    with torch.cuda.device(dev):
+        rc = load().hrc_store_write_file(os.fsencode(path), int(file_offset), src.numel() * src.element_size(), _ptr(src),
+                                         int(chunk_bytes), _stream(dev), ctypes.byref(secs))
+    _check(rc, "hrc_store_write_file")
+    return float(secs.value)

@@ -57,6 +57,7 @@ int store_register(const void*, int64_t);
 void store_release(const void*);
 #ifdef HRC_EXPERIMENTS
 void set_debug(int);
+void set_stages(int);
 #endif
 size_t topk_workspace_bytes(int64_t, int, int);
 int launch_topk(const float*, const int32_t*, int64_t, int, int, int32_t, uint64_t*, void*, size_t, cudaStream_t);
@@ -268,6 +269,7 @@ int hrc_trace_collect(float* ms_out, int max_n) {
 
 #ifdef HRC_EXPERIMENTS
 void hrc_exp_set_debug(int bits) { set_debug(bits); }
+void hrc_exp_set_stages(int n) { set_stages(n); }
 #endif
 
 int hrc_store_register(const void* d_tokens, int64_t total_tokens) {

@@ -22,6 +22,9 @@ namespace hrc {
 
 int launch_topk_merge_parts(const uint64_t*, int, int, int, int, uint64_t*, cudaStream_t, int32_t*, float*, const uint64_t*,
                             uint64_t, int, uint64_t);
+int launch_keys_unpack(const uint64_t*, int64_t, int32_t*, float*, cudaStream_t);
+int launch_rerank_unpack(const uint64_t*, int, int, const int32_t*, int, int32_t*, int32_t*, float*, cudaStream_t);
+int launch_rrf(const int32_t*, int, const int32_t*, int, int, int, int, int32_t*, double*, int32_t*, cudaStream_t);
 
 namespace {
 
@@ -99,6 +102,99 @@ p2p_push_kernel(uint8_t* const* __restrict__ peers, const uint64_t* __restrict__
     uint64_t* flag = reinterpret_cast<uint64_t*>(base) + parity * kMaxWorld + my_rank;
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
   }
+}
+
+// global candidate ids -> ids local to this shard (-1: not mine)
+__global__ void localize_ids_kernel(const int32_t* __restrict__ ids, int64_t n, int32_t id_base, int64_t n_docs,
+                                    int32_t* __restrict__ local) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t l = int64_t(ids[i]) - id_base;
+  local[i] = (ids[i] >= 0 && l >= 0 && l < n_docs) ? int32_t(l) : -1;
+}
+
+// (score, candidate position) keys of the candidates THIS rank answers for: the ones its shard holds, and — on rank 0 —
+// the ones no shard holds (absent / out of range: -inf, exactly what the single-GPU rerank gives them).  Others: 0.
+__global__ void owned_rerank_keys_kernel(const float* __restrict__ scores, const int32_t* __restrict__ global_ids,
+                                         int n_cand, int64_t n, int32_t id_base, int64_t n_docs, int64_t n_docs_global,
+                                         int rank, uint64_t* __restrict__ keys) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t id = global_ids[i];
+  const int pos = int(i % n_cand);
+  const int64_t l = int64_t(id) - id_base;
+  uint64_t key = 0;
+  if (id >= 0 && l >= 0 && l < n_docs) key = make_key(scores[i], pos);
+  else if (rank == 0 && (id < 0 || id >= n_docs_global)) key = make_key(-INFINITY, pos);
+  keys[i] = key;
+}
+
+size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct ShardedSearchLayout { size_t search, local, gather, total, search_bytes, gather_bytes; };
+ShardedSearchLayout sharded_search_layout(int world, int64_t n_docs, int64_t total_tokens, int nq, int lq, int k, int path) {
+  ShardedSearchLayout L;
+  size_t o = 0;
+  // (a shard with fewer than k documents searches with k_local = n_docs, possibly on the other route)
+  const size_t a = hrc_search_workspace_bytes(n_docs, total_tokens, nq, lq, k, path);
+  const size_t b = hrc_search_workspace_bytes(n_docs, total_tokens, nq, lq, int(n_docs < k ? n_docs : k), path);
+  L.search_bytes = a > b ? a : b;
+  L.search = o; o += al256(L.search_bytes);
+  L.local = o; o += al256(size_t(nq) * k * sizeof(uint64_t));
+  L.gather_bytes = hrc_allgather_merge_workspace_bytes(world, nq, k);
+  L.gather = o; o += al256(L.gather_bytes);
+  L.total = o;
+  return L;
+}
+
+struct ShardedHostLayout { size_t q32, q16, inner, ids, scores, total, inner_bytes; };
+ShardedHostLayout sharded_host_layout(int world, int64_t n_docs, int64_t total_tokens, int nq, int lq, int k, int path) {
+  ShardedHostLayout L;
+  size_t o = 0;
+  L.q32 = o; o += al256(size_t(nq) * lq * HRC_DIM * sizeof(float));
+  L.q16 = o; o += al256(size_t(nq) * lq * HRC_DIM * 2);
+  L.inner_bytes = sharded_search_layout(world, n_docs, total_tokens, nq, lq, k, path).total + al256(size_t(nq) * k * 8);
+  L.inner = o; o += al256(L.inner_bytes);
+  L.ids = o; o += al256(size_t(nq) * k * sizeof(int32_t));
+  L.scores = o; o += al256(size_t(nq) * k * sizeof(float));
+  L.total = o;
+  return L;
+}
+
+struct ShardedHybridLayout {
+  size_t search, local, gather, gkeys, col_ids, fused, fused_scores, counts, local_cand, cand_scores, part, rr_keys, gather2,
+      fkeys, pos, total, search_bytes, gather_bytes, part_bytes, gather2_bytes;
+};
+ShardedHybridLayout sharded_hybrid_layout(int world, int64_t n_docs, int64_t total_tokens, int nq, int lq, int ck, int nc,
+                                          int fk, int path) {
+  ShardedHybridLayout L;
+  size_t o = 0;
+  L.search_bytes = sharded_search_layout(world, n_docs, total_tokens, nq, lq, ck, path).search_bytes;
+  L.search = o; o += al256(L.search_bytes);
+  L.local = o; o += al256(size_t(nq) * ck * 8);
+  L.gather_bytes = hrc_allgather_merge_workspace_bytes(world, nq, ck);
+  L.gather = o; o += al256(L.gather_bytes);
+  L.gkeys = o; o += al256(size_t(nq) * ck * 8);
+  L.col_ids = o; o += al256(size_t(nq) * ck * 4);
+  L.fused = o; o += al256(size_t(nq) * nc * 4);
+  L.fused_scores = o; o += al256(size_t(nq) * nc * 8);
+  L.counts = o; o += al256(size_t(nq) * 4);
+  L.local_cand = o; o += al256(size_t(nq) * nc * 4);
+  L.cand_scores = o; o += al256(size_t(nq) * nc * 4);
+  L.part_bytes = hrc_maxsim_workspace_bytes(nc, nq, lq);
+  L.part = o; o += al256(L.part_bytes);
+  L.rr_keys = o; o += al256(size_t(nq) * nc * 8);
+  L.gather2_bytes = hrc_allgather_merge_workspace_bytes(world, nq, nc);
+  L.gather2 = o; o += al256(L.gather2_bytes);
+  L.fkeys = o; o += al256(size_t(nq) * fk * 8);
+  L.pos = o; o += al256(size_t(nq) * fk * 4);
+  L.total = o;
+  return L;
+}
+
+__global__ void f32_to_bf16_rows_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
 }
 
 }  // namespace
@@ -238,6 +334,152 @@ int hrc_allgather_merge_topk(hrc_comm_t* comm, const uint64_t* d_local_keys, int
   HRC_CHECK_NCCL(g_nccl.AllGather(d_local_keys, gathered, size_t(n_keys), ncclUint64, c->nccl, st));
   return launch_topk_merge_parts(gathered, c->world, n_keys, n_rows, k, d_keys_out, st, d_ids_out, d_scores_out, nullptr, 0,
                                  0, 0);
+}
+
+size_t hrc_sharded_search_workspace_bytes(int world, int64_t n_docs, int64_t total_tokens, int n_queries, int lq, int k,
+                                          int path) {
+  if (world < 1 || n_docs < 0 || total_tokens < 0 || n_queries < 0 || lq < 1 || k < 0) return 0;
+  return sharded_search_layout(world, n_docs, total_tokens, n_queries, lq, k, path).total;
+}
+
+int hrc_sharded_search(hrc_comm_t* comm, int transport, const void* d_tokens, const int64_t* d_offsets, int64_t n_docs,
+                       int64_t total_tokens, const void* d_queries, int n_queries, int lq, int k, int32_t id_base,
+                       void* d_workspace, size_t workspace_bytes, uint64_t* d_keys_out, int32_t* d_ids_out,
+                       float* d_scores_out, int path, void* stream) {
+  Comm* c = reinterpret_cast<Comm*>(comm);
+  HRC_REQUIRE(c != nullptr, "sharded_search: null communicator");
+  HRC_REQUIRE(n_queries >= 0 && lq >= 1 && k >= 0 && k <= HRC_MAX_TOPK, "sharded_search: bad sizes");
+  if (n_queries == 0 || k == 0) return 0;
+  const ShardedSearchLayout L = sharded_search_layout(c->world, n_docs, total_tokens, n_queries, lq, k, path);
+  HRC_REQUIRE(d_workspace != nullptr && workspace_bytes >= L.total, "sharded_search: workspace too small (%zu < %zu)",
+              workspace_bytes, L.total);
+  HRC_REQUIRE((reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, "sharded_search: workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+  uint64_t* local = reinterpret_cast<uint64_t*>(ws + L.local);
+  const int k_local = int(n_docs < k ? n_docs : k);       // a shard with fewer than k documents pads with empty slots
+  if (k_local < k) HRC_CHECK_CUDA(cudaMemsetAsync(local, 0, size_t(n_queries) * k * sizeof(uint64_t), st));
+  if (k_local > 0) {
+    // (a shard smaller than k writes rows of k_local keys; re-spread them to rows of k below)
+    uint64_t* dst = k_local == k ? local : reinterpret_cast<uint64_t*>(ws + L.gather);
+    if (int rc = hrc_search(d_tokens, d_offsets, n_docs, total_tokens, d_queries, n_queries, lq, k_local, id_base, ws + L.search,
+                            L.search_bytes, dst, nullptr, nullptr, path, stream))
+      return rc;
+    if (k_local != k)
+      HRC_CHECK_CUDA(cudaMemcpy2DAsync(local, size_t(k) * 8, dst, size_t(k_local) * 8, size_t(k_local) * 8, n_queries,
+                                       cudaMemcpyDeviceToDevice, st));
+  }
+  return hrc_allgather_merge_topk(comm, local, n_queries, k, transport, ws + L.gather, L.gather_bytes, d_keys_out, d_ids_out,
+                                  d_scores_out, stream);
+}
+
+size_t hrc_sharded_search_host_workspace_bytes(int world, int64_t n_docs, int64_t total_tokens, int n_queries, int lq,
+                                               int k, int path) {
+  if (world < 1 || n_docs < 0 || total_tokens < 0 || n_queries < 0 || lq < 1 || k < 0) return 0;
+  return sharded_host_layout(world, n_docs, total_tokens, n_queries, lq, k, path).total;
+}
+
+int hrc_sharded_search_host(hrc_comm_t* comm, int transport, const void* d_tokens, const int64_t* d_offsets,
+                            int64_t n_docs, int64_t total_tokens, const float* h_queries, int n_queries, int lq, int k,
+                            int32_t id_base, void* d_workspace, size_t workspace_bytes, int32_t* h_ids_out,
+                            float* h_scores_out, int path, void* stream) {
+  Comm* c = reinterpret_cast<Comm*>(comm);
+  HRC_REQUIRE(c != nullptr, "sharded_search_host: null communicator");
+  HRC_REQUIRE(n_queries >= 0 && lq >= 1 && k >= 0 && k <= HRC_MAX_TOPK, "sharded_search_host: bad sizes");
+  if (n_queries == 0 || k == 0) return 0;
+  HRC_REQUIRE(h_queries != nullptr && h_ids_out != nullptr && h_scores_out != nullptr, "sharded_search_host: null buffer");
+  const ShardedHostLayout L = sharded_host_layout(c->world, n_docs, total_tokens, n_queries, lq, k, path);
+  HRC_REQUIRE(d_workspace != nullptr && workspace_bytes >= L.total, "sharded_search_host: workspace too small (%zu < %zu)",
+              workspace_bytes, L.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+  float* q32 = reinterpret_cast<float*>(ws + L.q32);
+  __nv_bfloat16* q16 = reinterpret_cast<__nv_bfloat16*>(ws + L.q16);
+  const int64_t n = int64_t(n_queries) * lq * HRC_DIM;
+  HRC_CHECK_CUDA(cudaMemcpyAsync(q32, h_queries, size_t(n) * sizeof(float), cudaMemcpyHostToDevice, st));
+  f32_to_bf16_rows_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(q32, q16, n);
+  count_launch();
+  const size_t inner = sharded_search_layout(c->world, n_docs, total_tokens, n_queries, lq, k, path).total;
+  uint64_t* keys = reinterpret_cast<uint64_t*>(ws + L.inner + inner);
+  int32_t* d_ids = reinterpret_cast<int32_t*>(ws + L.ids);
+  float* d_sc = reinterpret_cast<float*>(ws + L.scores);
+  if (int rc = hrc_sharded_search(comm, transport, d_tokens, d_offsets, n_docs, total_tokens, q16, n_queries, lq, k, id_base,
+                                  ws + L.inner, inner, keys, d_ids, d_sc, path, stream))
+    return rc;
+  HRC_CHECK_CUDA(cudaMemcpyAsync(h_ids_out, d_ids, size_t(n_queries) * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  HRC_CHECK_CUDA(cudaMemcpyAsync(h_scores_out, d_sc, size_t(n_queries) * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+size_t hrc_sharded_hybrid_workspace_bytes(int world, int64_t n_docs, int64_t total_tokens, int n_queries, int lq,
+                                          int colbert_k, int n_candidates, int final_k, int path) {
+  if (world < 1 || n_docs < 0 || total_tokens < 0 || n_queries < 0 || lq < 1 || colbert_k < 0 || n_candidates < 0 || final_k < 0)
+    return 0;
+  return sharded_hybrid_layout(world, n_docs, total_tokens, n_queries, lq, colbert_k, n_candidates, final_k, path).total;
+}
+
+int hrc_sharded_hybrid_retrieve(hrc_comm_t* comm, int transport, const void* d_tokens, const int64_t* d_offsets,
+                                int64_t n_docs, int64_t total_tokens, int64_t n_docs_global, const void* d_queries,
+                                int n_queries, int lq, const int32_t* d_bm25_ids, int n_bm25, int colbert_k, int rrf_k,
+                                int n_candidates, int final_k, int32_t id_base, void* d_workspace, size_t workspace_bytes,
+                                int32_t* d_ids_out, float* d_scores_out, int path, void* stream) {
+  Comm* c = reinterpret_cast<Comm*>(comm);
+  HRC_REQUIRE(c != nullptr, "sharded_hybrid: null communicator");
+  HRC_REQUIRE(n_queries >= 0 && lq >= 1 && n_bm25 >= 0 && colbert_k >= 1 && colbert_k <= n_docs_global && n_candidates >= 1 &&
+                  final_k >= 1 && final_k <= n_candidates && colbert_k <= HRC_MAX_TOPK,
+              "sharded_hybrid: need 1 <= colbert_k <= n_docs_global and 1 <= final_k <= n_candidates");
+  if (n_queries == 0) return 0;
+  HRC_REQUIRE(d_ids_out != nullptr && d_scores_out != nullptr && (n_bm25 == 0 || d_bm25_ids != nullptr), "sharded_hybrid: null buffer");
+  const ShardedHybridLayout L =
+      sharded_hybrid_layout(c->world, n_docs, total_tokens, n_queries, lq, colbert_k, n_candidates, final_k, path);
+  HRC_REQUIRE(d_workspace != nullptr && workspace_bytes >= L.total, "sharded_hybrid: workspace too small (%zu < %zu)",
+              workspace_bytes, L.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+  uint64_t* gkeys = reinterpret_cast<uint64_t*>(ws + L.gkeys);
+  int32_t* col_ids = reinterpret_cast<int32_t*>(ws + L.col_ids);
+  int32_t* fused = reinterpret_cast<int32_t*>(ws + L.fused);
+  int32_t* local_cand = reinterpret_cast<int32_t*>(ws + L.local_cand);
+  float* cand_scores = reinterpret_cast<float*>(ws + L.cand_scores);
+  uint64_t* rr_keys = reinterpret_cast<uint64_t*>(ws + L.rr_keys);
+  uint64_t* fkeys = reinterpret_cast<uint64_t*>(ws + L.fkeys);
+  // stage 2 (:908-911): the GLOBAL ColBERT list — local top-k, exchange, merge; ids unpacked by the merge kernel
+  const size_t inner = sharded_search_layout(c->world, n_docs, total_tokens, n_queries, lq, colbert_k, path).total;
+  HRC_REQUIRE(inner <= L.gkeys, "sharded_hybrid: internal layout error");
+  if (int rc = hrc_sharded_search(comm, transport, d_tokens, d_offsets, n_docs, total_tokens, d_queries, n_queries, lq,
+                                  colbert_k, id_base, ws, inner, gkeys, col_ids, nullptr, path, stream))
+    return rc;
+  // stage 3 (:914-916): RRF on global ids; every rank computes the same fusion
+  if (int rc = launch_rrf(d_bm25_ids, n_bm25, col_ids, colbert_k, n_queries, rrf_k, n_candidates, fused,
+                          reinterpret_cast<double*>(ws + L.fused_scores), reinterpret_cast<int32_t*>(ws + L.counts), st))
+    return rc;
+  // stage 5 (:926-929): every rank scores the candidates it owns, the (score, position) keys are exchanged and merged
+  const int64_t n_fused = int64_t(n_queries) * n_candidates;
+  localize_ids_kernel<<<unsigned((n_fused + 255) / 256), 256, 0, st>>>(fused, n_fused, id_base, n_docs, local_cand);
+  count_launch();
+  if (total_tokens > 0) {
+    if (int rc = hrc_maxsim_scores_ids(d_tokens, d_offsets, n_docs, total_tokens, local_cand, n_candidates, d_queries, n_queries,
+                                       lq, cand_scores, path, ws + L.part, L.part_bytes, stream))
+      return rc;
+  }
+  owned_rerank_keys_kernel<<<unsigned((n_fused + 255) / 256), 256, 0, st>>>(cand_scores, fused, n_candidates, n_fused, id_base,
+                                                                           total_tokens > 0 ? n_docs : 0, n_docs_global,
+                                                                           c->rank, rr_keys);
+  count_launch();
+  HRC_CHECK_CUDA(cudaGetLastError());
+  // merge to final_k: hrc_allgather_merge_topk merges world x n_candidates keys per row down to n_candidates; the top
+  // final_k of that sorted list are the result
+  if (int rc = hrc_allgather_merge_topk(comm, rr_keys, n_queries, n_candidates, transport, ws + L.gather2, L.gather2_bytes,
+                                        rr_keys, nullptr, nullptr, stream))
+    return rc;
+  if (final_k == n_candidates) {
+    return launch_rerank_unpack(rr_keys, final_k, n_queries, fused, n_candidates, reinterpret_cast<int32_t*>(ws + L.pos),
+                                d_ids_out, d_scores_out, st);
+  }
+  HRC_CHECK_CUDA(cudaMemcpy2DAsync(fkeys, size_t(final_k) * 8, rr_keys, size_t(n_candidates) * 8, size_t(final_k) * 8,
+                                   n_queries, cudaMemcpyDeviceToDevice, st));
+  return launch_rerank_unpack(fkeys, final_k, n_queries, fused, n_candidates, reinterpret_cast<int32_t*>(ws + L.pos), d_ids_out,
+                              d_scores_out, st);
 }
 
 }  // extern "C"

@@ -452,27 +452,38 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     const int lidx = slot * rep + sub;                       // 0 .. kEpiWarps-1
     uint64_t* my_lists = lists + size_t(lidx) * MT * kListCap;
     uint64_t* lst = my_lists + ((MT == 2 && lane >= 16) ? kListCap : 0);
+    // The epilogue is instruction-bound in the batched kernels, so the common case must cost next to nothing: after
+    // the butterfly EVERY lane of a half-warp holds its M-tile's score, and every lane keeps a copy of its list's
+    // threshold score (thr_f: the k-th best so far), so "does this score enter the list?" is one float compare and one
+    // vote for the whole warp.  Only when some score passes does the warp take the slow path (form the key, append,
+    // compact a full list with a bitonic sort).
     uint32_t cnt = 0;
     uint64_t thr = 0;
+    float thr_f = -INFINITY;
     if constexpr (TK) {
       for (int i = lane; i < MT * kListCap; i += 32) my_lists[i] = 0;
       __syncwarp();
     }
-    auto append = [&](float score, int64_t doc) {           // emitting lane only
-      const uint64_t key = make_key(score, int32_t(p.id_base + int32_t(doc)));
-      if (key > thr) lst[cnt++] = key;
-    };
-    auto compact_full = [&]() {                              // whole warp: sort the full list(s), keep the best k
+    auto append_slow = [&](bool pass, float score, int64_t doc) {     // whole warp; `pass` per half-warp
+      if (pass && (lane & 15) == 0 && (MT == 2 || lane == 0)) {
+        const uint64_t key = make_key(score, int32_t(p.id_base + int32_t(doc)));
+        if (key > thr) lst[cnt++] = key;
+      }
+      if (!__any_sync(0xffffffffu, cnt >= uint32_t(kListCap))) return;
 #pragma unroll
-      for (int j = 0; j < MT; ++j) {
+      for (int j = 0; j < MT; ++j) {                                   // sort the full list(s), keep the best k
         if (__shfl_sync(0xffffffffu, cnt, j * 16) >= uint32_t(kListCap)) {
           warp_sort256_desc(my_lists + j * kListCap, lane);
-          if (lane == j * 16) { cnt = uint32_t(p.k); thr = lst[p.k - 1]; }
+          float tf = 0.f;
+          if (lane == j * 16) { cnt = uint32_t(p.k); thr = lst[p.k - 1]; tf = key_score(thr); }
+          tf = __shfl_sync(0xffffffffu, tf, j * 16);
+          if (MT == 1 || (lane >> 4) == j) thr_f = tf;
         }
       }
     };
 
     auto emit_pending = [&]() {
+      float sc_all = 0.f;                   // MT == 1: the document's score, on every lane
       if constexpr (MT == 2) {
         // both M-tiles in ONE butterfly: after the first exchange lanes 0-15 carry M-tile 0 and lanes 16-31 M-tile 1
         const bool lo_half = lane < 16;
@@ -483,24 +494,26 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
         for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         const bool act = lo_half ? active[0] : active[1];
         const int64_t row = lo_half ? out_row[0] : out_row[1];
-        if ((lane & 15) == 0 && act) {
-          if (!TK || p.scores != nullptr) p.scores[row + pend_col] = a;
-          if constexpr (TK) append(a, pend_col);
+        if ((lane & 15) == 0 && act && (!TK || p.scores != nullptr)) p.scores[row + pend_col] = a;
+        if constexpr (TK) {
+          const bool pass = act && !(a < thr_f);           // (also true for NaN, which make_key orders as -inf)
+          if (!HRC_DBG(p, 8) && __any_sync(0xffffffffu, pass)) append_slow(pass, a, pend_col);
         }
       } else {
         // M=64: only lanes 0-15 of a lane group hold accumulator rows (16 query tokens)
         const float sc = warp_sum((ZP == 2 && lane >= 16) ? 0.f : pend_m[0]);
+        sc_all = sc;
         if (lane == 0 && active[0]) {
           if constexpr (ZP == 2) atomicAdd(&p.scores[out_row[0] + pend_col], sc);   // the other token half adds its part
           else if (!TK || p.scores != nullptr) p.scores[out_row[0] + pend_col] = sc;
-          if constexpr (TK) append(sc, pend_col);
           if constexpr (ZP == 1 && !TK) {
             if (p.rr_counter != nullptr) __threadfence();   // fused rerank: the score must be visible to the last CTA
           }
         }
       }
-      if constexpr (TK) {
-        if (__any_sync(0xffffffffu, cnt >= uint32_t(kListCap))) compact_full();
+      if constexpr (TK && MT == 1) {
+        const bool pass = active[0] && !(sc_all < thr_f);
+        if (__any_sync(0xffffffffu, pass)) append_slow(pass, sc_all, pend_col);
       }
       pending = false;
     };
@@ -584,7 +597,8 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
             for (int j = 0; j < MT; ++j) m[j] = max32_masked_acc(v[j], bits, m[j]);
           }
         }
-        if (e_tok <= tile1) finish_doc(); else break;   // else: the document continues in the next tile
+        if (e_tok > tile1) break;             // the document continues in the next tile
+        finish_doc();
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -762,7 +776,9 @@ int sm_count() {
 
 uint64_t g_watchdog_ns = 20ull * 1000000000ull;   // hrc_set_watchdog_ms
 #ifdef HRC_EXPERIMENTS
-int g_debug = 0;                                  // hrc_exp_set_debug
+int g_debug = 0;                                  // hrc_exp_set_debug: 1 no epilogue math, 2 no document TMA, 4 no MMA,
+                                                  // 8 fused top-k never appends, 16 non-TK kernels get the TK kernels' smem
+int g_stages = 0;                                 // hrc_exp_set_stages: cap of the shared-memory ring depth (0 = default)
 #endif
 
 template <int MT, int ZP, int CG, bool TK = false>
@@ -774,9 +790,15 @@ int launch_cfg(const void* d_tokens, const void* d_queries, int lq, int n_real_q
   if (int rc = cached_map(d_tokens, uint64_t(p.total_tokens), 0, TN / CG, &tmap_d)) return rc;
   if (int rc = cached_map(d_queries, uint64_t(lq), uint64_t(n_real_queries), 32, &tmap_q)) return rc;
   const int q_bytes = MT * kQBytes;
-  const int list_bytes = TK ? epi_warps(MT, ZP) * MT * kListCap * 8 : 0;
+  int list_bytes = TK ? epi_warps(MT, ZP) * MT * kListCap * 8 : 0;
+#ifdef HRC_EXPERIMENTS
+  if (!TK && (g_debug & 16)) list_bytes = epi_warps(MT, ZP) * MT * kListCap * 8;
+#endif
   int stages = (kMaxSmem - 1024 - 512 - q_bytes - list_bytes) / kTileBytes;
   if (stages > 8) stages = 8;
+#ifdef HRC_EXPERIMENTS
+  if (g_stages > 0 && stages > g_stages) stages = g_stages;
+#endif
   p.n_stages = stages;
   const int smem_bytes = 1024 + q_bytes + stages * kTileBytes + 512 + list_bytes;
   static PerDeviceOnce once;
@@ -923,6 +945,7 @@ void set_watchdog_ns(uint64_t ns) { g_watchdog_ns = ns; }
 uint64_t get_watchdog_ns() { return g_watchdog_ns; }
 #ifdef HRC_EXPERIMENTS
 void set_debug(int bits) { g_debug = bits; }
+void set_stages(int n) { g_stages = n; }
 #endif
 
 int store_register(const void* d_tokens, int64_t total_tokens) {

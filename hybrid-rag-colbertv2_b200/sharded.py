@@ -1,19 +1,28 @@
-"""Document-sharded search: one process per GPU, local top-k, all-gather of k keys, on-device merge.
+"""Document-sharded search: one process per GPU, local top-k, exchange of k keys per rank, on-device merge.
 
 New design (the reference is single-process): the corpus shards by document, each
-rank scores its shard and emits k 64-bit (score, GLOBAL doc id) keys; one all-gather of k*8 bytes per
-rank crosses NVLink (latency-bound: 800 B at k=100), and every rank merges the world_size*k keys with
-hrc_topk_merge.  Keys are totally ordered, so the merged list equals the single-GPU list exactly.
+rank scores its shard and emits k 64-bit (score, GLOBAL doc id) keys; the ranks exchange k*8 bytes each
+over NVLink (latency-bound: 800 B at k=100) and every rank merges the world_size*k keys.  Keys are
+totally ordered, so the merged list equals the single-GPU list exactly.
+
+Transports of the exchange:
+  "nccl"   (default) ncclAllGather inside libhrc.so — the whole sharded step is ONE C call (hrc_sharded_search)
+  "p2p"    direct peer stores into CUDA-IPC-mapped receive buffers + sequence flags, also inside libhrc.so: the
+           exchange is fused into the producer / merge kernels, no collective launch
+  "torch"  torch.distributed all_gather + hrc_topk_merge — backend-agnostic (gloo on CPU tensors in the host-logic
+           tests); the cross-check of the two library transports
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
 from . import _lib
-from .retriever import JinaColBERTRetriever
+from .retriever import JinaColBERTRetriever, _knob
+
+_TRANSPORTS = {"nccl": _lib.TRANSPORT_NCCL, "p2p": _lib.TRANSPORT_P2P}
 
 
 def all_gather_keys(keys: torch.Tensor, k: int, group=None) -> torch.Tensor:
@@ -34,32 +43,78 @@ def all_gather_keys(keys: torch.Tensor, k: int, group=None) -> torch.Tensor:
 
 
 class ShardedSearcher:
-    """search over a corpus sharded across the ranks of a torch.distributed group (one rank per GPU)."""
+    """search / hybrid retrieve over a corpus sharded across the ranks of a torch.distributed group (one rank per GPU)."""
 
-    def __init__(self, retriever: JinaColBERTRetriever, group=None):
+    def __init__(self, retriever: JinaColBERTRetriever, group=None, transport: str = "nccl", p2p_max_keys: int = 1 << 16):
+        if transport not in ("nccl", "p2p", "torch"):
+            raise ValueError(f"transport must be 'nccl', 'p2p' or 'torch', got {transport!r}")
         self.retriever = retriever          # holds THIS rank's shard; store.doc_id_base makes ids global
         self.group = group
+        self.transport = transport
+        self.comm: Optional[_lib.Comm] = None
+        self._ws = _lib.Workspace()
+        self._host: Optional[_lib.ShardedHostSearch] = None
         self._pinned = None
+        self._n_global: Optional[int] = None
+        if transport != "torch":
+            self.comm = _lib.Comm(retriever.device, group, p2p_max_keys=p2p_max_keys if transport == "p2p" else 0)
+            self._host = _lib.ShardedHostSearch(self.comm)
 
-    def search_keys(self, query_embeddings: torch.Tensor, k: int) -> torch.Tensor:
-        local = self.retriever.search_keys(query_embeddings, k)       # [Bq, min(k, n_local)]
-        gathered = all_gather_keys(local, k, self.group)              # [Bq, world * k]
-        return _lib.topk_merge(gathered, k)                           # [Bq, k] sorted, 0 = empty
-
+    # ---- helpers ---------------------------------------------------------------------------------
     def _lq(self, query_embeddings: torch.Tensor) -> int:
         return int(query_embeddings.shape[-2])
 
+    def _path(self) -> int:
+        return _knob(self.retriever.config, "maxsim_path")
+
+    def n_docs_global(self) -> int:
+        """Documents of the whole corpus (sum over the ranks' shards), cached."""
+        if self._n_global is None:
+            t = torch.tensor([self.retriever.store.n_docs], dtype=torch.int64,
+                             device=self.retriever.device if dist.get_backend(self.group) == "nccl" else "cpu")
+            dist.all_reduce(t, group=self.group)
+            self._n_global = int(t[0])
+        return self._n_global
+
+    # ---- search ----------------------------------------------------------------------------------
+    def search_keys(self, query_embeddings: torch.Tensor, k: int) -> torch.Tensor:
+        """Merged, sorted (score, GLOBAL id) keys: int64 [Bq, k] (0 = empty), identical on every rank."""
+        r = self.retriever
+        if self.transport == "torch" or r._literal():
+            local = r.search_keys(query_embeddings, k)                    # [Bq, min(k, n_local)]
+            gathered = all_gather_keys(local, k, self.group)              # [Bq, world * k]
+            return _lib.topk_merge(gathered, k)                           # [Bq, k] sorted, 0 = empty
+        q = r._prep_queries(query_embeddings)
+        s = r.store
+        return _lib.sharded_search(self.comm, s.tokens, s.offsets, q, int(k), id_base=s.doc_id_base, path=self._path(),
+                                   transport=_TRANSPORTS[self.transport], workspace=self._ws, unpack=False)[0]
+
     def search_embeddings(self, query_embeddings: torch.Tensor, k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
-        ids, scores = _lib.keys_unpack(self.search_keys(query_embeddings, k))
-        return ids, self.retriever._finish_scores(scores, self._lq(query_embeddings))   # honours score_reduction="mean"
+        r = self.retriever
+        if self.transport == "torch" or r._literal():
+            ids, scores = _lib.keys_unpack(self.search_keys(query_embeddings, k))
+        else:
+            q = r._prep_queries(query_embeddings)
+            s = r.store
+            _, ids, scores = _lib.sharded_search(self.comm, s.tokens, s.offsets, q, int(k), id_base=s.doc_id_base,
+                                                 path=self._path(), transport=_TRANSPORTS[self.transport],
+                                                 workspace=self._ws, unpack=True)
+        return ids, r._finish_scores(scores, self._lq(query_embeddings))   # honours score_reduction="mean"
 
     def search_host(self, query_embeddings: torch.Tensor, k: int = 10, copy: bool = True
                     ) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Host query embedding (fp32 CPU [Bq, Lq, 128], ideally pinned) -> host (ids, scores): asynchronous H2D,
-        the sharded search, asynchronous D2H into pinned buffers, ONE stream synchronisation.  The returned tensors
-        belong to the caller; copy=False returns the pinned staging buffers, which the next call overwrites."""
-        dev = self.retriever.device
+        """Host query embedding (fp32 CPU [Bq, Lq, 128], ideally pinned) -> host (ids, scores), ONE stream
+        synchronisation.  With the library transports this is one C call (hrc_sharded_search_host: H2D, fp32 -> bf16,
+        local search, exchange, merge + unpack, D2H).  The returned tensors belong to the caller; copy=False returns
+        the pinned staging buffers, which the next call overwrites."""
+        r = self.retriever
+        dev = r.device
         q = query_embeddings if query_embeddings.dim() == 3 else query_embeddings.unsqueeze(0)
+        if self.transport != "torch" and not r._literal() and not q.is_cuda:
+            s = r.store
+            ids, sc = self._host(s.tokens, s.offsets, q.to(torch.float32).contiguous(), int(k), id_base=s.doc_id_base,
+                                 path=self._path(), transport=_TRANSPORTS[self.transport], copy=copy)
+            return ids, r._finish_scores(sc, self._lq(q))
         ids, scores = _lib.keys_unpack(self.search_keys(q.to(dev, non_blocking=True), k))
         if self._pinned is None or self._pinned[0].shape != ids.shape:
             self._pinned = (torch.empty(ids.shape, dtype=torch.int32).pin_memory(),
@@ -68,4 +123,56 @@ class ShardedSearcher:
         self._pinned[1].copy_(scores, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         out_ids, out_sc = (self._pinned[0].clone(), self._pinned[1].clone()) if copy else self._pinned
-        return out_ids, self.retriever._finish_scores(out_sc, self._lq(q))
+        return out_ids, r._finish_scores(out_sc, self._lq(q))
+
+    # ---- hybrid pipeline (local_rag_complete.py:894-935) over the sharded corpus ---------------------
+    def retrieve_batch(self, query_embeddings: torch.Tensor, bm25_ids: torch.Tensor, top_k_final: Optional[int] = None
+                       ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """ColBERT top-k over ALL shards -> RRF with the given BM25 lists (global ids) -> each rank scores the
+        candidates it owns -> merged rerank.  Same result on every rank, bit-equal to HybridRetriever.retrieve_batch
+        over the unsharded store.  bm25_ids: int [Bq, n_bm25] ranked GLOBAL doc ids (negative = absent)."""
+        r = self.retriever
+        cfg = r.config
+        k_final = int(cfg.final_top_k if top_k_final is None else top_k_final)
+        n_cand = int(_knob(cfg, "rerank_candidates"))
+        colbert_k = min(int(cfg.colbert_top_k), self.n_docs_global())
+        q = r._prep_queries(query_embeddings)
+        a = bm25_ids.to(r.device, torch.int32).contiguous()
+        s = r.store
+        if self.transport != "torch" and not r._literal() and k_final <= n_cand:
+            ids, scores = _lib.sharded_hybrid_retrieve(
+                self.comm, s.tokens, s.offsets, self.n_docs_global(), q, a, colbert_k=colbert_k, rrf_k=_knob(cfg, "rrf_k"),
+                n_candidates=n_cand, final_k=k_final, id_base=s.doc_id_base, path=self._path(),
+                transport=_TRANSPORTS[self.transport], workspace=self._ws)
+            return ids, r._finish_scores(scores, q.shape[1])
+        # the same stages with torch.distributed collectives (cross-check; also score_mode="reference_literal")
+        col_ids, _ = _lib.keys_unpack(self.search_keys(q, colbert_k))                       # global ColBERT list
+        fused, _, _ = _lib.rrf_fuse(a, col_ids.contiguous(), _knob(cfg, "rrf_k"), n_cand)   # global ids, every rank
+        local = fused - s.doc_id_base
+        owned = (fused >= 0) & (local >= 0) & (local < s.n_docs)
+        local = torch.where(owned, local, torch.full_like(local, -1)).contiguous()
+        if r._literal():
+            full = r._score_store(s, q)
+            cs = torch.gather(full, 1, local.clamp_min(0).long())
+        else:
+            cs = _lib.maxsim_scores_ids(s.tokens, s.offsets, local, q, path=self._path())
+        pos = torch.arange(n_cand, device=r.device, dtype=torch.int32).unsqueeze(0).expand_as(fused).contiguous()
+        nobody = (fused < 0) | (fused >= self.n_docs_global())
+        mine = owned | (nobody & (dist.get_rank(self.group) == 0))
+        cs = torch.where(owned, cs, torch.full_like(cs, float("-inf"))).contiguous()
+        keys = _lib.topk(cs, n_cand, ids=pos)                                               # sorted (score, pos) keys
+        # drop the keys of candidates this rank does not answer for (their pos would collide with the owner's key)
+        kpos, _ = _lib.keys_unpack(keys)
+        keep = torch.gather(mine, 1, kpos.clamp_min(0).long())
+        keys = torch.where(keep, keys, torch.zeros_like(keys)).contiguous()
+        merged = _lib.topk_merge(all_gather_keys(keys, n_cand, self.group), k_final)
+        mpos, scores = _lib.keys_unpack(merged)
+        ids = torch.where(mpos >= 0, torch.gather(fused, 1, mpos.clamp_min(0).long()), mpos)
+        if r._literal():
+            return ids, scores
+        return ids, r._finish_scores(scores, q.shape[1])
+
+    def close(self) -> None:
+        if self.comm is not None:
+            self.comm.close()
+            self.comm = None

@@ -154,9 +154,17 @@ class PackedStore:
         return PackedStore(self.tokens[t0:t1].to(dev), (off - off[0]).to(dev), self.doc_id_base + d0)
 
     # ---- persistence (native format; the reference-compatible index.pt lives in retriever.py) --
-    def save(self, path: str) -> None:
+    def save(self, path: str, chunk_bytes: int = 0) -> None:
+        """Native store: tokens.bf16.bin (packed rows) + offsets.i64.bin (CSR) + meta.json.  A CUDA store is streamed
+        to disk through two pinned staging buffers (hrc_store_write_file): no whole-store host copy."""
         os.makedirs(path, exist_ok=True)
-        self.tokens.cpu().view(torch.int16).numpy().tofile(os.path.join(path, "tokens.bf16.bin"))
+        tok_file = os.path.join(path, "tokens.bf16.bin")
+        if self.tokens.is_cuda:
+            from . import _lib
+            open(tok_file, "wb").close()
+            self.last_io_seconds = _lib.store_write_file(tok_file, 0, self.tokens, chunk_bytes) if self.total_tokens else 0.0
+        else:
+            self.tokens.view(torch.int16).numpy().tofile(tok_file)
         self.offsets.cpu().numpy().tofile(os.path.join(path, "offsets.i64.bin"))
         with open(os.path.join(path, "meta.json"), "w") as f:
             json.dump({"format": "hrc-packed-v1", "dim": DIM, "n_docs": self.n_docs,
@@ -164,8 +172,10 @@ class PackedStore:
 
     @classmethod
     def load(cls, path: str, device: Union[str, torch.device] = "cuda", rank: int = 0, world_size: int = 1,
-             allow_empty: bool = False) -> "PackedStore":
-        """Load (a document shard of) a native store straight to `device`, reading only that shard's bytes."""
+             allow_empty: bool = False, chunk_bytes: int = 0) -> "PackedStore":
+        """Load (a document shard of) a native store straight to `device`, reading only that shard's bytes.  On a CUDA
+        device the bytes stream file -> pinned staging buffer -> the rank's device slice (hrc_store_read_file, one
+        cudaMemcpyAsync per >= 256 MB chunk): host memory in use is two staging buffers, never the shard."""
         with open(os.path.join(path, "meta.json")) as f:
             meta = json.load(f)
         if meta.get("format") != "hrc-packed-v1" or meta.get("dim") != DIM:
@@ -174,7 +184,15 @@ class PackedStore:
         cls._validate(off, meta["total_tokens"], allow_empty)
         d0, d1 = shard_doc_ranges(off, world_size)[rank]
         t0, t1 = int(off[d0]), int(off[d1])
-        raw = np.fromfile(os.path.join(path, "tokens.bf16.bin"), dtype=np.int16, count=(t1 - t0) * DIM,
-                          offset=t0 * DIM * 2)
+        tok_file = os.path.join(path, "tokens.bf16.bin")
+        dev = torch.device(device)
+        if dev.type == "cuda":
+            from . import _lib
+            tokens = torch.empty((t1 - t0, DIM), dtype=torch.bfloat16, device=dev)
+            secs = _lib.store_read_file(tok_file, t0 * DIM * 2, tokens, chunk_bytes) if t1 > t0 else 0.0
+            store = cls(tokens, (off[d0:d1 + 1] - off[d0]).to(dev), meta.get("doc_id_base", 0) + d0)
+            store.last_io_seconds = secs
+            return store
+        raw = np.fromfile(tok_file, dtype=np.int16, count=(t1 - t0) * DIM, offset=t0 * DIM * 2)
         tokens = torch.from_numpy(raw).view(torch.bfloat16).reshape(t1 - t0, DIM)
         return cls(tokens.to(device), (off[d0:d1 + 1] - off[d0]).to(device), meta.get("doc_id_base", 0) + d0)

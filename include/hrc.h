@@ -240,6 +240,92 @@ int hrc_synth_tokens(void* d_tokens_out, int64_t token_begin, int64_t n_tokens, 
                      void* stream);
 
 /*
+ * ---- multi-GPU: the exchange step of the document-sharded search ------------------------------------------------
+ * The corpus shards by document over the GPUs of one box, ONE PROCESS PER GPU; each rank computes a
+ * local top-k and the ranks exchange k keys each.  The single-process reference has no counterpart
+ * (local_rag_complete.py contains no distributed code); these calls make the N>1 search one C call like the N=1 one.
+ *   hrc_comm_unique_id  rank 0 creates a 128-byte id and hands it to every rank (any host channel)
+ *   hrc_comm_init       collective over the ranks: joins the communicator on the CURRENT device.  libnccl.so.2 is
+ *                       loaded at run time (dlopen); libhrc.so does not link against it
+ *   hrc_comm_enable_p2p collective: maps every rank's receive buffer into every other rank (CUDA IPC over NVLink) for
+ *                       HRC_TRANSPORT_P2P; max_keys = the largest n_rows * k a later call will exchange
+ * Transports of the exchange:
+ *   HRC_TRANSPORT_NCCL  ncclAllGather of n_rows * k keys per rank, then the merge kernel
+ *   HRC_TRANSPORT_P2P   a push kernel STORES this rank's keys into every peer's receive buffer and releases a sequence
+ *                       flag (system scope); the merge kernel acquires the world's flags and merges.  No collective
+ *                       launch; the exchange is part of the producer and the consumer kernels.
+ */
+#define HRC_COMM_ID_BYTES 128
+#define HRC_TRANSPORT_NCCL 0
+#define HRC_TRANSPORT_P2P 1
+typedef struct hrc_comm hrc_comm_t;
+int hrc_comm_unique_id(void* id_out);
+int hrc_comm_init(const void* unique_id, int world, int rank, hrc_comm_t** comm_out);
+int hrc_comm_enable_p2p(hrc_comm_t* comm, int max_keys, void* stream);
+int hrc_comm_world(const hrc_comm_t* comm);
+int hrc_comm_rank(const hrc_comm_t* comm);
+int hrc_comm_destroy(hrc_comm_t* comm);
+
+/*
+ * All-gather of every rank's sorted local keys + merge: d_keys_out[r] = the k best of the world * k keys of row r,
+ * identical on every rank (keys are totally ordered, so this equals the single-GPU result bit for bit).
+ *   d_local_keys : uint64 [n_rows][k] (0 = empty slot)
+ *   d_workspace  : hrc_allgather_merge_workspace_bytes(world, n_rows, k) bytes (NCCL transport only)
+ *   d_ids_out / d_scores_out : optional unpacked result
+ */
+size_t hrc_allgather_merge_workspace_bytes(int world, int n_rows, int k);
+int hrc_allgather_merge_topk(hrc_comm_t* comm, const uint64_t* d_local_keys, int n_rows, int k, int transport,
+                             void* d_workspace, size_t workspace_bytes, uint64_t* d_keys_out, int32_t* d_ids_out,
+                             float* d_scores_out, void* stream);
+
+/*
+ * Document-sharded search in one call per rank: hrc_search over this rank's shard (global ids through id_base), the
+ * exchange above, the merge.  hrc_sharded_search_host is its host-buffer form (H2D of the fp32 queries, fp32 -> bf16,
+ * the sharded search, D2H of ids and scores; the caller synchronises the stream).
+ */
+size_t hrc_sharded_search_workspace_bytes(int world, int64_t n_docs, int64_t total_tokens, int n_queries, int lq, int k,
+                                          int path);
+int hrc_sharded_search(hrc_comm_t* comm, int transport, const void* d_tokens, const int64_t* d_offsets, int64_t n_docs,
+                       int64_t total_tokens, const void* d_queries, int n_queries, int lq, int k, int32_t id_base,
+                       void* d_workspace, size_t workspace_bytes, uint64_t* d_keys_out, int32_t* d_ids_out,
+                       float* d_scores_out, int path, void* stream);
+size_t hrc_sharded_search_host_workspace_bytes(int world, int64_t n_docs, int64_t total_tokens, int n_queries, int lq,
+                                               int k, int path);
+int hrc_sharded_search_host(hrc_comm_t* comm, int transport, const void* d_tokens, const int64_t* d_offsets,
+                            int64_t n_docs, int64_t total_tokens, const float* h_queries, int n_queries, int lq, int k,
+                            int32_t id_base, void* d_workspace, size_t workspace_bytes, int32_t* h_ids_out,
+                            float* h_scores_out, int path, void* stream);
+
+/*
+ * Document-sharded HybridRetriever.retrieve (local_rag_complete.py:894-935) for a batch of queries, one call per rank:
+ * local ColBERT top-colbert_k -> exchange + merge (the GLOBAL ColBERT list, :908-911) -> RRF with the BM25 lists on
+ * global ids (:914-916; every rank computes the same fusion) -> each rank scores the candidates it OWNS -> exchange of
+ * (score, candidate position) keys + merge (:926-929).  Results are identical on every rank and equal to
+ * hrc_hybrid_retrieve over the unsharded store bit for bit.
+ *   n_docs_global : documents of the whole corpus (ids outside [0, n_docs_global) score -inf, as on one GPU)
+ */
+size_t hrc_sharded_hybrid_workspace_bytes(int world, int64_t n_docs, int64_t total_tokens, int n_queries, int lq,
+                                          int colbert_k, int n_candidates, int final_k, int path);
+int hrc_sharded_hybrid_retrieve(hrc_comm_t* comm, int transport, const void* d_tokens, const int64_t* d_offsets,
+                                int64_t n_docs, int64_t total_tokens, int64_t n_docs_global, const void* d_queries,
+                                int n_queries, int lq, const int32_t* d_bm25_ids, int n_bm25, int colbert_k, int rrf_k,
+                                int n_candidates, int final_k, int32_t id_base, void* d_workspace, size_t workspace_bytes,
+                                int32_t* d_ids_out, float* d_scores_out, int path, void* stream);
+
+/*
+ * Streamed transfer between a file and device memory (the native on-disk store: tokens.bf16.bin holds the packed bf16
+ * token rows of the whole corpus; a rank reads only the byte range of its document shard).  Replaces the persistence
+ * half of JinaColBERTRetriever.index / load, local_rag_complete.py:742-753 (torch.save / torch.load of one dense tensor
+ * through host memory).  Two pinned staging buffers of chunk_bytes (0 = 256 MiB): while one chunk travels (ONE
+ * cudaMemcpyAsync per chunk) the next is read / written with pread / pwrite, so host memory in use is 2 x chunk_bytes
+ * whatever the shard size.  Synchronous: returns when the data is in place; *seconds_out (optional) = elapsed time.
+ */
+int hrc_store_read_file(const char* path, int64_t file_offset, int64_t n_bytes, void* d_dst, size_t chunk_bytes,
+                        void* stream, double* seconds_out);
+int hrc_store_write_file(const char* path, int64_t file_offset, int64_t n_bytes, const void* d_src, size_t chunk_bytes,
+                         void* stream, double* seconds_out);
+
+/*
  * Read-bandwidth probe (bench utility, not on the query path): streams `bytes` of device memory once with 16-byte
  * loads and folds them into *d_out (a uint32 the caller zeroes).  bench.py times it over the resident corpus to
  * state the MaxSim kernel's HBM fraction against a pure-READ peak as well as the read+write copy peak.

@@ -1,12 +1,16 @@
 #!/usr/bin/env python
-"""Multi-GPU parity over real NCCL (run under torchrun, one rank per GPU):
-the document-sharded search (local top-k -> all-gather of k keys -> on-device merge) must return
-bit-identical keys to a single-GPU search over the whole corpus, for single and batched queries.
+"""Multi-GPU parity over real NVLink (run under torchrun, one rank per GPU): for every transport of the exchange step —
+"torch" (torch.distributed all_gather), "nccl" (ncclAllGather inside libhrc.so), "p2p" (peer stores + flags inside
+libhrc.so) — the document-sharded search, the host-buffer search and the sharded hybrid pipeline must return results
+bit-identical to a single GPU holding the whole corpus, on every rank, for single and batched queries, including
+shards smaller than k, a rank with an EMPTY shard, and many back-to-back steps (the P2P double buffer).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 \
         scripts/check_sharded_nccl.py [--docs 400000]
+Also prints the device time of the exchange + merge per transport (CUDA events, max over ranks).
 """
 import argparse
+import json
 import os
 import sys
 
@@ -17,6 +21,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import hybrid_rag_colbertv2_b200 as hrc  # noqa: E402
+from hybrid_rag_colbertv2_b200 import _lib  # noqa: E402
 from hybrid_rag_colbertv2_b200.synth import plant, synth_queries, synth_store  # noqa: E402
 
 
@@ -28,33 +33,108 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    ok = True
+
+    def check(cond, what):
+        nonlocal ok
+        flag = torch.tensor([1 if cond else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        good = bool(flag[0])
+        ok = ok and good
+        if rank == 0:
+            print(f"{'ok  ' if good else 'FAIL'} {what}", flush=True)
+
     q = synth_queries(19, 32, device=dev)                      # 19: CTA pairs + an odd query group
+    cfg = hrc.RAGConfig(device=str(dev), colbert_top_k=100, rerank_candidates=50, final_top_k=10)
     # this rank's shard of the global ragged corpus, planted deterministically by GLOBAL doc id
     shard = synth_store(args.docs, 32, 300, seed=77, device=dev, rank=rank, world_size=world)
     plant(shard, q[:3], n_planted=50, n_docs_global=args.docs)
-    r = hrc.JinaColBERTRetriever(hrc.RAGConfig(device=str(dev)))
+    r = hrc.JinaColBERTRetriever(cfg)
     r.store = shard
-    s = hrc.ShardedSearcher(r)
-    keys_1 = s.search_keys(q[:1], 100)
-    keys_b = s.search_keys(q, 100)
-    ok = True
+    # every rank also builds the whole corpus as the single-GPU reference (400k docs x ~166 tokens = 17 GB)
+    full = synth_store(args.docs, 32, 300, seed=77, device=dev)
+    plant(full, q[:3], n_planted=50)
+    one = hrc.JinaColBERTRetriever(cfg)
+    one.store = full
+    ref_1, ref_b = one.search_keys(q[:1], 100), one.search_keys(q, 100)
+    g = torch.Generator().manual_seed(3)
+    bm25 = torch.randint(0, args.docs, (19, 100), generator=g, dtype=torch.int32).to(dev)
+    col_ids = _lib.keys_unpack(ref_b)[0]
+    bm25[:, :30] = col_ids[:, torch.randperm(100, generator=g)[:30].to(dev)]
+    bm25[2, 90:] = -1
+    bm25[3, 5] = args.docs + 7                                 # out of range: -inf on one GPU, -inf here
+    idx = hrc.DualIndexer(cfg)
+    idx.colbert_retriever = one
+    h = hrc.HybridRetriever(cfg, idx, None, verbose=False)
+    hy_ids, hy_sc = h.retrieve_batch(q, bm25)
+    hy1_ids, hy1_sc = h.retrieve_batch(q[:1], bm25[:1])
+
+    timings = {}
+    for transport in ("torch", "nccl", "p2p"):
+        s = hrc.ShardedSearcher(r, transport=transport)
+        check(torch.equal(s.search_keys(q[:1], 100), ref_1), f"[{transport}] 1 query: sharded keys == single-GPU keys")
+        check(torch.equal(s.search_keys(q, 100), ref_b), f"[{transport}] 19 queries: sharded keys == single-GPU keys")
+        ids, sc = s.search_embeddings(q, 100)
+        ri, rs = _lib.keys_unpack(ref_b)
+        check(torch.equal(ids, ri) and torch.equal(sc, rs), f"[{transport}] search_embeddings (unpacked)")
+        hi, hs = s.search_host(q.float().cpu(), 100)
+        check(torch.equal(hi, ri.cpu()) and torch.equal(hs, rs.cpu()), f"[{transport}] search_host")
+        same = True
+        for step in range(40):                                  # back-to-back steps, alternating shapes
+            qq = q[step % 19: step % 19 + 1]
+            same = same and torch.equal(s.search_keys(qq, 100), one.search_keys(qq, 100))
+        check(same, f"[{transport}] 40 back-to-back steps")
+        a_ids, a_sc = s.retrieve_batch(q, bm25)
+        check(torch.equal(a_ids, hy_ids) and torch.equal(a_sc, hy_sc), f"[{transport}] sharded hybrid retrieve, 19 queries")
+        b_ids, b_sc = s.retrieve_batch(q[:1], bm25[:1])
+        check(torch.equal(b_ids, hy1_ids) and torch.equal(b_sc, hy1_sc), f"[{transport}] sharded hybrid retrieve, 1 query")
+        # exchange + merge alone
+        local_keys = r.search_keys(q[:1], 100).contiguous()
+        if transport == "torch":
+            from hybrid_rag_colbertv2_b200.sharded import all_gather_keys
+            fn = lambda: _lib.topk_merge(all_gather_keys(local_keys, 100), 100)  # noqa: E731
+        else:
+            tr = _lib.TRANSPORT_NCCL if transport == "nccl" else _lib.TRANSPORT_P2P
+            ws = _lib.Workspace()
+            fn = lambda: _lib.allgather_merge_topk(s.comm, local_keys, 100, transport=tr, workspace=ws)  # noqa: E731
+        for _ in range(5):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 50 * 1e3], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        timings[transport] = round(float(t[0]), 2)
+        s.close()
+
+    # shards smaller than k and an EMPTY shard: 30 documents over `world` ranks, k = 25
+    tiny_full = synth_store(30, 5, 20, seed=5, device=dev)
+    tiny = hrc.JinaColBERTRetriever(cfg)
+    tiny.store = tiny_full
+    if world > 2:       # leave the last rank without documents
+        lo, hi = (rank * 30) // (world - 1), ((rank + 1) * 30) // (world - 1)
+        lo, hi = (lo, hi) if rank < world - 1 else (30, 30)
+    else:
+        lo, hi = (rank * 30) // world, ((rank + 1) * 30) // world
+    off = tiny_full.offsets
+    t0, t1 = int(off[lo]), int(off[hi])
+    part = hrc.JinaColBERTRetriever(cfg)
+    part.store = hrc.PackedStore(tiny_full.tokens[t0:t1].contiguous() if t1 > t0 else torch.zeros((0, 128), dtype=torch.bfloat16, device=dev),
+                                 (off[lo:hi + 1] - off[lo]).contiguous(), doc_id_base=lo)
+    for transport in ("nccl", "p2p"):
+        s = hrc.ShardedSearcher(part, transport=transport)
+        check(torch.equal(s.search_keys(q[:2], 25), tiny.search_keys(q[:2], 25)), f"[{transport}] shards smaller than k / empty shard")
+        s.close()
     if rank == 0:
-        full = synth_store(args.docs, 32, 300, seed=77, device=dev)
-        plant(full, q[:3], n_planted=50)
-        one = hrc.JinaColBERTRetriever(hrc.RAGConfig(device=str(dev)))
-        one.store = full
-        ref_1, ref_b = one.search_keys(q[:1], 100), one.search_keys(q, 100)
-        ok = bool(torch.equal(ref_1, keys_1)) and bool(torch.equal(ref_b, keys_b))
-        print(f"world={world} docs={args.docs}: sharded == single-GPU keys: {ok} "
-              f"(top id {int(hrc._lib.keys_unpack(keys_1)[0][0, 0])})", flush=True)
-    # every rank holds the same merged list
-    gathered = [torch.empty_like(keys_b) for _ in range(world)]
-    dist.all_gather(gathered, keys_b)
-    same = all(torch.equal(g, keys_b) for g in gathered)
-    if rank == 0:
-        print(f"world={world}: all ranks hold the same merged list: {same}", flush=True)
+        print(json.dumps({"world": world, "exchange_plus_merge_us": timings}), flush=True)
+        print(f"world={world}: {'ALL OK' if ok else 'FAILED'}", flush=True)
     dist.destroy_process_group()
-    if not (ok and same):
+    if not ok:
         sys.exit(1)
 
 

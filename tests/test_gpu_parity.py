@@ -927,6 +927,14 @@ def test_fused_topk_with_empty_and_tiny_inputs(cuda_dev):
     q, tok, off = _case(13, 3, 4, 9, 1, 7)
     tok_d, off_d, q_d = tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev)
     assert torch.equal(L.search(tok_d, off_d, q_d, 3)[0], L.topk(L.maxsim_scores(tok_d, off_d, q_d), 3))
+    # long runs of EMPTY documents (every one a -inf key, none bounded by the tile size): mid-corpus and trailing
+    for nq in (1, 3, 9):
+        lens = [3] * 10 + [0] * 3000 + [5] * 40 + [0] * 700 + [130] + [0] * 2000
+        q, tok, off = _case(14, 0, 0, 0, nq, 32, lens=lens)
+        tok_d, off_d, q_d = tok.to(cuda_dev), off.to(cuda_dev), q.to(cuda_dev)
+        scores = L.maxsim_scores(tok_d, off_d, q_d)
+        for k in (40, 100, 128):
+            assert torch.equal(L.search(tok_d, off_d, q_d, k)[0], L.topk(scores, k)), f"empty runs nq={nq} k={k}"
 
 
 @pytest.mark.parametrize("n_cand,lq,nq", [(50, 32, 1), (50, 32, 5), (1024, 32, 2), (1025, 32, 2), (7, 40, 3), (1, 32, 1), (300, 9, 4)])
@@ -976,3 +984,112 @@ def test_results_are_bitwise_repeatable(cuda_dev):
             else:
                 for a, b in zip(first, res):
                     assert torch.equal(a, b), f"nq={nq} lq={lq}: results differ between runs"
+
+
+# ======================================================================================================
+# SURVEY §8(f) rows 2 and 3 on the device: streamed native store, encoder hook on CUDA
+# ======================================================================================================
+def test_native_store_streams_to_disk_and_back_by_shard(cuda_dev, tmp_path):
+    """f2: PackedStore.save -> load(rank, world) for world in {1, 3}: the token file streams through two pinned staging
+    buffers in both directions (several chunks, the last one partial; never a whole-shard host copy), each rank reads
+    only its byte range, and a search over the loaded shards equals the search over the in-memory store bit for bit."""
+    import hybrid_rag_colbertv2_b200 as hrc
+    from hybrid_rag_colbertv2_b200.synth import plant, synth_queries, synth_store
+    L = _lib()
+    store = synth_store(60_000, 8, 120, seed=9, device=cuda_dev)            # ~3.8M tokens, ~1 GB
+    q = synth_queries(3, 32, device=cuda_dev)
+    plant(store, q, n_planted=30)
+    path = str(tmp_path / "native")
+    store.save(path, chunk_bytes=96 << 20)
+    assert os.path.getsize(os.path.join(path, "tokens.bf16.bin")) == store.total_tokens * 256
+    write_gbs = store.total_tokens * 256 / store.last_io_seconds / 1e9
+    back = hrc.PackedStore.load(path, device=cuda_dev, chunk_bytes=80 << 20)
+    read_gbs = back.total_tokens * 256 / back.last_io_seconds / 1e9
+    print(f"native store: {store.total_tokens * 256 / 1e9:.2f} GB, save {write_gbs:.2f} GB/s, load {read_gbs:.2f} GB/s")
+    assert torch.equal(back.tokens, store.tokens) and torch.equal(back.offsets, store.offsets) and back.doc_id_base == 0
+    one = hrc.JinaColBERTRetriever(hrc.RAGConfig())
+    one.store = store
+    ref = one.search_keys(q, 100)
+    for world in (1, 3):
+        gathered = []
+        for r in range(world):
+            ld = hrc.PackedStore.load(path, device=cuda_dev, rank=r, world_size=world, chunk_bytes=50 << 20)
+            sh = store.shard(r, world)
+            assert ld.doc_id_base == sh.doc_id_base and torch.equal(ld.tokens, sh.tokens) and torch.equal(ld.offsets, sh.offsets)
+            rr = hrc.JinaColBERTRetriever(hrc.RAGConfig())
+            rr.store = ld
+            gathered.append(rr.search_keys(q, 100))
+        assert torch.equal(L.topk_merge(torch.cat(gathered, 1).contiguous(), 100), ref), f"world={world}"
+    with pytest.raises(Exception):                                            # a truncated token file is refused, not mis-read
+        with open(os.path.join(path, "tokens.bf16.bin"), "r+b") as f:
+            f.truncate(store.total_tokens * 256 - 4096)
+        hrc.PackedStore.load(path, device=cuda_dev)
+
+
+class _WordTokenizer:
+    """Minimal tokenizer with the transformers call signature (no vocabulary files exist offline)."""
+    pad_token_id, cls_token_id, sep_token_id, mask_token_id = 0, 1, 2, 3
+
+    def _ids(self, text, add_special_tokens=True):
+        words = [4 + (int.from_bytes(w.encode(), "little") % 900)
+                 for w in text.lower().replace(",", " , ").replace(".", " . ").split()]
+        return ([self.cls_token_id] + words + [self.sep_token_id]) if add_special_tokens else words
+
+    def __call__(self, text, add_special_tokens=True, truncation=False, max_length=None, padding=False, return_tensors=None):
+        single = isinstance(text, str)
+        rows = [self._ids(t, add_special_tokens) for t in ([text] if single else text)]
+        if truncation and max_length:
+            rows = [r[:max_length] for r in rows]
+        if return_tensors is None:
+            return {"input_ids": rows[0] if single else rows}
+        width = max(len(r) for r in rows)
+        ids = torch.tensor([r + [self.pad_token_id] * (width - len(r)) for r in rows])
+        mask = torch.tensor([[1] * len(r) + [0] * (width - len(r)) for r in rows])
+        return {"input_ids": ids, "attention_mask": mask}
+
+
+def test_colbert_encoder_on_cuda_through_index_search_rerank(cuda_dev, tmp_path):
+    """f3: the ColBERT-style encoder hook (transformer backbone + 128-d projection + L2 norm; real weights do not exist
+    offline, so a small randomly initialised backbone) runs ON THE GPU, its ragged output goes device-to-device into the
+    packed store (no host round trip), and index() -> search() -> rerank() -> retrieve() agree with the oracle computed
+    from the same embeddings."""
+    import hybrid_rag_colbertv2_b200 as hrc
+    from transformers import BertConfig, BertModel
+    torch.manual_seed(0)
+    backbone = BertModel(BertConfig(vocab_size=1000, hidden_size=64, num_hidden_layers=2, num_attention_heads=4,
+                                    intermediate_size=128, max_position_embeddings=600), add_pooling_layer=False)
+    enc = hrc.ColBERTEncoder(backbone, _WordTokenizer(), projection=torch.nn.Linear(64, 128, bias=False), device=cuda_dev,
+                             batch_size=16, doc_maxlen=48)
+    words = "late interaction retrieval scores every query token against every document token and keeps the best".split()
+    rng = np.random.default_rng(3)
+    corpus = [" ".join(rng.choice(words, size=int(rng.integers(3, 40)))) + "." for _ in range(150)]
+    cfg = hrc.RAGConfig(colbert_index_path=str(tmp_path / "ix"), colbert_top_k=40, bm25_top_k=40, rerank_candidates=20, final_top_k=5)
+    r = hrc.JinaColBERTRetriever(cfg, encoder=enc)
+    docs = enc.encode(corpus, convert_to_tensor=True)
+    assert all(d.is_cuda and d.shape[1] == 128 for d in docs) and len({d.shape[0] for d in docs}) > 5      # ragged, on the GPU
+    r.index(corpus)
+    assert r.store.tokens.is_cuda and r.store.n_docs == 150 and r.store.total_tokens == sum(d.shape[0] for d in docs)
+    assert torch.equal(r.store.tokens, torch.cat(docs).to(torch.bfloat16))
+    query = "which query token keeps the best score"
+    qe = enc.encode(query, convert_to_tensor=True)
+    assert qe.is_cuda and qe.shape == (32, 128)
+    exp = o.maxsim_scores(o.round_bf16(qe.float().cpu()), r.store.tokens.float().cpu(), r.store.offsets.cpu())[0]
+    res = r.search(query=query, k=10)
+    assert o.check_ranking([x["document_id"] for x in res], [x["score"] for x in res], exp, 10, RTOL) is None
+    assert all(x["text"] == corpus[x["document_id"]] for x in res)
+    picks = [7, 140, 33, 3, 99, 58]
+    rr = r.rerank(query=query, documents=[corpus[i] for i in picks], k=4)          # re-encodes, like the reference (:783)
+    assert o.check_ranking([x["result_index"] for x in rr], [x["score"] for x in rr], exp[picks], 4, RTOL) is None
+    back = hrc.JinaColBERTRetriever(cfg, encoder=enc)
+    back.load()
+    assert torch.equal(back.store.tokens, r.store.tokens) and back.corpus == corpus
+    idx = hrc.DualIndexer(cfg, encoder=enc)
+    idx.colbert_retriever = r
+    bm = rng.permutation(150)[:40].tolist()
+    h = hrc.HybridRetriever(cfg, idx, None, verbose=False,
+                            bm25_search=lambda qq, k: [{"chunk_id": int(i), "score": 1.0, "source": "bm25"} for i in bm[:k]])
+    out = h.retrieve(query)
+    col = h._colbert_search(query, 40)
+    fused = o.rrf_reference([{"chunk_id": int(i)} for i in bm], col)
+    cand = [f["chunk_id"] for f in fused[:20]]
+    assert o.check_ranking([cand.index(x["chunk_id"]) for x in out], [x["score"] for x in out], exp[cand], 5, RTOL) is None
