@@ -482,7 +482,7 @@ def run_ours(args):
                      "kernel_share_of_step": kernel_ms / ms_per_step},
         "e2e": {"value": docs_per_step / (e2e["ms_per_step"] * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": int(q_host[0].numel() * 4), "d2h_bytes_per_step": K * 8,
-                "ms_per_step": e2e["ms_per_step"], "step_ms": e2e["step_ms"],
+                "ms_per_step": e2e["ms_per_step"], "step_ms": e2e["step_ms"], "kernel_ms": e2e["kernel_ms"],
                 "api": ("JinaColBERTRetriever.search_host: pinned fp32 query -> hrc_search_host (H2D, bf16, MaxSim, top-k, "
                         "unpack, D2H) -> ids/scores on the host" if world == 1 else
                         f"ShardedSearcher.search_host (transport {args.transport}): pinned fp32 query -> hrc_sharded_search_host "

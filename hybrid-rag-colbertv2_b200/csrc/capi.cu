@@ -60,9 +60,10 @@ void set_debug(int);
 void set_stages(int);
 #endif
 size_t topk_workspace_bytes(int64_t, int, int);
-int launch_topk(const float*, const int32_t*, int64_t, int, int, int32_t, uint64_t*, void*, size_t, cudaStream_t);
+int launch_topk(const float*, const int32_t*, int64_t, int, int, int32_t, uint64_t*, void*, size_t, cudaStream_t,
+                int32_t* = nullptr, float* = nullptr);
 int launch_topk_merge(const uint64_t*, int, int, int, uint64_t*, cudaStream_t, int32_t* = nullptr, float* = nullptr);
-bool tc_topk_supported(int64_t, int, int);
+bool tc_topk_supported(int64_t, int, int, int);
 bool tc_rerank_supported(int64_t, int, int, int);
 int launch_maxsim_tc_rerank(const void*, const int64_t*, int64_t, int64_t, const int32_t*, int, const void*, int, int, int,
                             float*, uint32_t*, int32_t*, int32_t*, float*, cudaStream_t);
@@ -140,10 +141,10 @@ __global__ void shift_ids_kernel(int32_t* ids, int64_t n, int32_t delta) {
 
 // ---- workspace layouts (every sub-buffer 256-byte aligned) -------------------------------------------------
 // hrc_search takes the FUSED route (MaxSim kernel with per-segment top-k in its epilogue, then one merge launch: the
-// score matrix is never written) when the tensor-core path applies, the query has <= 32 tokens and k <= 128;
-// otherwise score matrix -> radix top-k.
-static bool search_is_fused(int64_t total_tokens, int lq, int k, int path) {
-  return (path == HRC_PATH_AUTO || path == HRC_PATH_TC) && tc_topk_supported(total_tokens, lq, k);
+// score matrix is never written) for a SINGLE query of <= 32 tokens with k <= 128 on the tensor-core path — the
+// HBM-bound kernel, whose epilogue has slack.  Otherwise: score matrix -> streaming / radix top-k.
+static bool search_is_fused(int64_t total_tokens, int nq, int lq, int k, int path) {
+  return (path == HRC_PATH_AUTO || path == HRC_PATH_TC) && tc_topk_supported(total_tokens, nq, lq, k);
 }
 
 struct SearchLayout {      // fused: candidate keys.  staged: score matrix, slot partials (lq > 32), top-k scratch
@@ -154,7 +155,7 @@ struct SearchLayout {      // fused: candidate keys.  staged: score matrix, slot
 static SearchLayout search_layout(int64_t n_docs, int64_t total_tokens, int nq, int lq, int k, int path) {
   SearchLayout L = {};
   size_t o = 0;
-  L.fused = search_is_fused(total_tokens, lq, k, path);
+  L.fused = search_is_fused(total_tokens, nq, lq, k, path);
   if (L.fused) {
     L.n_seg = tc_topk_segments(total_tokens);
     L.cand = o; o += align256(size_t(nq) * size_t(L.n_seg) * size_t(tc_topk_list_len()) * sizeof(uint64_t));
@@ -344,11 +345,8 @@ int hrc_search(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, i
   if (int rc = maxsim_dispatch(d_tokens, d_offsets, n_docs, total_tokens, nullptr, n_docs, d_queries, n_queries, lq,
                                scores, path, ws + L.part, L.part_bytes, st))
     return rc;
-  if (int rc = launch_topk(scores, nullptr, n_docs, n_queries, k, id_base, d_keys_out, ws + L.topk, L.topk_bytes, st))
-    return rc;
-  if (d_ids_out != nullptr || d_scores_out != nullptr)
-    return launch_keys_unpack(d_keys_out, int64_t(n_queries) * k, d_ids_out, d_scores_out, st);
-  return 0;
+  return launch_topk(scores, nullptr, n_docs, n_queries, k, id_base, d_keys_out, ws + L.topk, L.topk_bytes, st, d_ids_out,
+                     d_scores_out);
 }
 
 size_t hrc_search_host_workspace_bytes(int64_t n_docs, int64_t total_tokens, int n_queries, int lq, int k, int path) {

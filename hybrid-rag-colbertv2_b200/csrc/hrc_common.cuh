@@ -120,6 +120,33 @@ __device__ __forceinline__ float bf16lo_to_f32(uint32_t packed) { return __uint_
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
 
 // ---------------------------------------------------------------------------------------------
+// per-warp key lists (fused top-k of the MaxSim epilogue, streaming top-k of topk.cu)
+// ---------------------------------------------------------------------------------------------
+constexpr int kKeyListCap = 256;   // keys per list: [0, k) survivors of the last compaction + appended keys
+constexpr int kKeyListOut = 128;   // sorted keys a list hands on: k <= 128
+// In-place descending bitonic sort of 256 keys in shared memory by ONE warp (36 compare-exchange stages, 4 pairs per
+// lane and stage).  ~2.5k cycles; runs a handful of times per warp and launch.
+__device__ __forceinline__ void warp_sort256_desc(uint64_t* a, int lane) {
+#pragma unroll 1
+  for (int size = 2; size <= kKeyListCap; size <<= 1) {
+#pragma unroll 1
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < kKeyListCap / 64; ++r) {
+        const int i = lane + 32 * r;
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const uint64_t x = a[lo], y = a[hi];
+        if ((x < y) == desc) { a[lo] = y; a[hi] = x; }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

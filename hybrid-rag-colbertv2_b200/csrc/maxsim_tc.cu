@@ -59,8 +59,8 @@ constexpr int kMaxSmem = 232448;                  // 227 KB opt-in limit per CTA
 // compacted by a warp-wide bitonic sort; at the end the warps of a CTA that share a query merge their lists and the
 // CTA hands kListOut keys per (query, segment) to the merge kernel.  The [n_queries x n_docs] score matrix is never
 // written (unless the caller asks for it).
-constexpr int kListCap = 256;                     // keys per list
-constexpr int kListOut = 128;                     // keys per (query, segment) handed to the merge: k <= 128
+constexpr int kListCap = kKeyListCap;             // keys per list (warp_sort256_desc, hrc_common.cuh)
+constexpr int kListOut = kKeyListOut;             // keys per (query, segment) handed to the merge: k <= 128
 
 #ifdef HRC_EXPERIMENTS
 #define HRC_DBG(p, bit) (((p).debug & (bit)) != 0)
@@ -161,28 +161,6 @@ __device__ __forceinline__ float max32_masked_acc(const uint32_t (&v)[32], uint3
 #pragma unroll
   for (int i = 0; i < 32; ++i) t[i] = ((bits >> i) & 1u) ? v[i] : 0xff800000u;   // -inf
   return max32_acc(t, m);
-}
-
-// In-place descending bitonic sort of 256 keys in shared memory by ONE warp (36 compare-exchange stages, 4 pairs per
-// lane and stage).  ~2.5k cycles; runs a handful of times per warp and launch.
-__device__ __forceinline__ void warp_sort256_desc(uint64_t* a, int lane) {
-#pragma unroll 1
-  for (int size = 2; size <= kListCap; size <<= 1) {
-#pragma unroll 1
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      __syncwarp();
-#pragma unroll
-      for (int r = 0; r < kListCap / 64; ++r) {
-        const int i = lane + 32 * r;
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = (lo & size) == 0;
-        const uint64_t x = a[lo], y = a[hi];
-        if ((x < y) == desc) { a[lo] = y; a[hi] = x; }
-      }
-    }
-  }
-  __syncwarp();
 }
 
 template <int MT, int ZP, int CG, bool TK>
@@ -795,7 +773,11 @@ int launch_cfg(const void* d_tokens, const void* d_queries, int lq, int n_real_q
   if (!TK && (g_debug & 16)) list_bytes = epi_warps(MT, ZP) * MT * kListCap * 8;
 #endif
   int stages = (kMaxSmem - 1024 - 512 - q_bytes - list_bytes) / kTileBytes;
-  if (stages > 8) stages = 8;
+  // Ring depth: 8 x 16 KB for the batched kernels; FIVE x 32 KB for the HBM-bound ones — a sixth stage fits but is
+  // slower (libhrc_exp stage sweep, same box: C2 4.67-4.90 ms with 6, 4.69-4.78 with 5, 4.60-4.64 with 4, 5.09 with 3;
+  // ragged single query 10.63 / 9.89 / 9.84 / 10.41): 160 KB in flight per SM already covers the latency-bandwidth
+  // product several times, and more outstanding requests per SM only spread the DRAM access pattern.
+  if (stages > (MT == 1 ? 5 : 8)) stages = MT == 1 ? 5 : 8;
 #ifdef HRC_EXPERIMENTS
   if (g_stages > 0 && stages > g_stages) stages = g_stages;
 #endif
@@ -925,18 +907,14 @@ int launch_tc_slots(const void* d_tokens, const int64_t* d_offsets, int64_t n_do
     pp.n_qgroups = paired;
     pp.n_queries = n_queries < paired * 8 ? n_queries : paired * 8;
     const dim3 pgrid((unsigned)(pp.n_segments * paired));
-    int rc = tk ? launch_cfg<2, 0, 2, true>(d_tokens, d_queries, lq, n_real_queries, pp, pgrid, stream)
-                : launch_cfg<2, 0, 2>(d_tokens, d_queries, lq, n_real_queries, pp, pgrid, stream);
+    int rc = launch_cfg<2, 0, 2>(d_tokens, d_queries, lq, n_real_queries, pp, pgrid, stream);
     if (rc != 0 || paired == p.n_qgroups) return rc;
     TcParams pl = p;                                    // the odd group: (virtual) queries [paired * 8, n_queries)
     pl.n_qgroups = 1;
     pl.vq_base = paired * 8;
-    return tk ? launch_cfg<2, 0, 1, true>(d_tokens, d_queries, lq, n_real_queries, pl, dim3((unsigned)pl.n_segments), stream)
-              : launch_cfg<2, 0, 1>(d_tokens, d_queries, lq, n_real_queries, pl, dim3((unsigned)pl.n_segments), stream);
+    return launch_cfg<2, 0, 1>(d_tokens, d_queries, lq, n_real_queries, pl, dim3((unsigned)pl.n_segments), stream);
   }
-  const dim3 grid((unsigned)(p.n_segments * p.n_qgroups));
-  return tk ? launch_cfg<2, 0, 1, true>(d_tokens, d_queries, lq, n_real_queries, p, grid, stream)
-            : launch_cfg<2, 0, 1>(d_tokens, d_queries, lq, n_real_queries, p, grid, stream);
+  return launch_cfg<2, 0, 1>(d_tokens, d_queries, lq, n_real_queries, p, dim3((unsigned)(p.n_segments * p.n_qgroups)), stream);
 }
 
 }  // namespace
@@ -963,8 +941,15 @@ void store_release(const void* base) {
 }
 
 // ---- fused MaxSim + per-segment top-k (hrc_search's default) -------------------------------------------------------
-bool tc_topk_supported(int64_t total_tokens, int lq, int k) {
-  return total_tokens > 0 && total_tokens < (1ll << 31) && lq >= 1 && lq <= HRC_TC_MAX_LQ && k >= 1 && k <= kListOut;
+// Fused top-k is used for ONE query (the HBM-bound kernel, whose epilogue has slack).  Measured in-process on one box,
+// fused vs score matrix + top-k: C2 one query 4.59-4.69 vs 4.85-5.04 ms, ragged one query 9.6-10.0 vs 10.7-11.0 ms; two
+// and four queries 2 % SLOWER.  In the tensor-bound batched kernels the epilogue IS the critical resource: even a
+// never-taken append costs 2.2 % (registers, code size) and the real thing 5 % (C3 64 queries 109.8 vs 104.4 ms) against
+// a top-k pass that costs 1 %, so everything but the single-query search keeps writing scores and runs the streaming
+// top-k of topk.cu (profiles/r02_summary.md, "fused top-k").
+bool tc_topk_supported(int64_t total_tokens, int n_queries, int lq, int k) {
+  return total_tokens > 0 && total_tokens < (1ll << 31) && n_queries >= 1 && n_queries <= HRC_FUSED_TOPK_MAX_QUERIES &&
+         lq >= 1 && lq <= HRC_TC_MAX_LQ && k >= 1 && k <= kListOut;
 }
 int tc_topk_segments(int64_t total_tokens) {     // CTAs along the corpus = key lists per query
   const int64_t tiles = (total_tokens + TN - 1) / TN;
@@ -976,7 +961,8 @@ int launch_maxsim_tc_topk(const void* d_tokens, const int64_t* d_offsets, int64_
                           const void* d_queries, int n_queries, int lq, int k, int32_t id_base, float* d_scores,
                           uint64_t* d_cand_keys, cudaStream_t stream) {
   if (n_docs == 0 || n_queries == 0) return 0;
-  HRC_REQUIRE(tc_topk_supported(total_tokens, lq, k), "fused top-k: needs lq <= %d and k <= %d", HRC_TC_MAX_LQ, kListOut);
+  HRC_REQUIRE(tc_topk_supported(total_tokens, n_queries, lq, k), "fused top-k: needs <= %d queries, lq <= %d and k <= %d",
+              HRC_FUSED_TOPK_MAX_QUERIES, HRC_TC_MAX_LQ, kListOut);
   HRC_REQUIRE(d_cand_keys != nullptr, "fused top-k: null candidate buffer");
   const TopkOut tk{d_cand_keys, k, id_base};
   return launch_tc_slots(d_tokens, d_offsets, n_docs, total_tokens, nullptr, n_docs, d_queries, n_queries, 1, lq, d_scores,

@@ -35,6 +35,7 @@ extern "C" {
 #define HRC_MAX_TOPK 2048      /* largest k the selection kernels accept                        */
 #define HRC_TC_MAX_LQ 32       /* query tokens per query slot on the tcgen05 path               */
 #define HRC_TC_MAX_SLOTS 8     /* a longer query is scored as up to 8 slots: lq <= 256 on that path */
+#define HRC_FUSED_TOPK_MAX_QUERIES 1   /* hrc_search fuses the top-k into the MaxSim epilogue up to this many queries */
 
 /* scoring path selector */
 #define HRC_PATH_AUTO 0
@@ -123,9 +124,10 @@ int hrc_meanpool_cosine_scores(const void* d_tokens, const int64_t* d_offsets, i
 /*
  * Fused search: MaxSim of every query against the whole store, per-query top-k, optional unpacking —
  * the body of JinaColBERTRetriever.search (local_rag_complete.py:764-775) in one call.
- * With the tensor-core path, lq <= 32 and k <= 128 this is TWO launches: the MaxSim kernel keeps a per-warp top-k of
- * the scores its epilogue emits (the [n_queries x n_docs] score matrix is never written) and hands 128 keys per
- * (query, corpus segment) to one merge-sort-unpack launch.  Otherwise: score matrix -> radix top-k -> unpack.
+ * A single query (the HBM-bound case) with lq <= 32 and k <= 128 on the tensor-core path is TWO launches: the MaxSim
+ * kernel keeps a per-warp top-k of the scores its epilogue emits (the score row is never written) and hands 128 keys per
+ * corpus segment to one merge-sort-unpack launch.  Otherwise: score matrix -> streaming top-k (k <= 128: every warp
+ * streams its slice with a running threshold and a small sorted list) or radix select (larger k) -> merge + unpack.
  *   d_workspace  : hrc_search_workspace_bytes(n_docs, total_tokens, n_queries, lq, k, path) bytes of scratch, 256-B aligned
  *   d_keys_out   : uint64 [n_queries][k]; d_ids_out / d_scores_out optional int32 / fp32 [n_queries][k]
  * k <= HRC_MAX_TOPK and k <= n_docs.

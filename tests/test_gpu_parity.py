@@ -282,6 +282,33 @@ def test_topk_is_exact(cuda_dev, n, k, rows):
     assert torch.equal(sc.cpu()[:, :kk], tv)
 
 
+@pytest.mark.parametrize("pattern", ["ascending", "descending", "constant", "random"])
+def test_streaming_topk_adversarial_rows(cuda_dev, pattern):
+    """The streaming top-k (k <= 128): rows in which EVERY score beats the running threshold (ascending: a compaction
+    every 156 appends), none does, all tie (id order decides), lengths that are not multiples of the 32-lane / 256-score
+    granules, many rows (several chunks per row and one chunk per row), explicit ids — bit-exact against the key sort."""
+    L = _lib()
+    rng = np.random.default_rng(5)
+    for n, rows, k in ((100_003, 3, 100), (70_001, 300, 128), (5_000, 2, 100), (257, 5, 128), (31, 2, 31), (1_000_000, 1, 100)):
+        if pattern == "ascending":
+            s = np.tile(np.linspace(-3, 3, n, dtype=np.float32), (rows, 1))
+        elif pattern == "descending":
+            s = np.tile(np.linspace(3, -3, n, dtype=np.float32), (rows, 1))
+        elif pattern == "constant":
+            s = np.full((rows, n), 0.25, dtype=np.float32)
+        else:
+            s = rng.standard_normal((rows, n)).astype(np.float32)
+            s[:, ::7] = np.round(s[:, ::7])
+        st = torch.from_numpy(s)
+        keys = L.topk(st.to(cuda_dev), k, id_base=11)
+        ref = o.merge_keys(o.make_keys(s, np.broadcast_to(np.arange(n) + 11, s.shape)), k)
+        assert (keys.cpu().numpy().view(np.uint64) == ref).all(), f"{pattern} n={n} rows={rows} k={k}"
+    ids = torch.from_numpy(rng.permutation(2_000_000)[:300_000].astype(np.int32).reshape(3, 100_000))
+    s = torch.from_numpy(rng.standard_normal((3, 100_000)).astype(np.float32))
+    keys = L.topk(s.to(cuda_dev), 64, ids=ids.to(cuda_dev))
+    assert (keys.cpu().numpy().view(np.uint64) == o.merge_keys(o.make_keys(s.numpy(), ids.numpy()), 64)).all()
+
+
 def test_topk_with_explicit_ids_and_merge(cuda_dev):
     L = _lib()
     g = torch.Generator().manual_seed(9)
