@@ -50,7 +50,7 @@ void trace_end(cudaStream_t stream) {
 int launch_maxsim_simt(const void*, const int64_t*, int64_t, const int32_t*, int64_t, const void*, int, int, float*,
                        cudaStream_t);
 int launch_maxsim_tc(const void*, const int64_t*, int64_t, int64_t, const int32_t*, int64_t, const void*, int, int,
-                     float*, bool, void*, size_t, cudaStream_t);
+                     float*, int, void*, size_t, cudaStream_t);
 size_t maxsim_tc_workspace_bytes(int64_t, int, int);
 void set_watchdog_ns(uint64_t);
 int store_register(const void*, int64_t);
@@ -62,7 +62,7 @@ void set_stages(int);
 size_t topk_workspace_bytes(int64_t, int, int);
 int launch_topk(const float*, const int32_t*, int64_t, int, int, int32_t, uint64_t*, void*, size_t, cudaStream_t,
                 int32_t* = nullptr, float* = nullptr);
-int launch_topk_merge(const uint64_t*, int, int, int, uint64_t*, cudaStream_t, int32_t* = nullptr, float* = nullptr);
+int launch_topk_merge(const uint64_t*, int, int, int, uint64_t*, cudaStream_t, int32_t* = nullptr, float* = nullptr, int = 0);
 bool tc_topk_supported(int64_t, int, int, int);
 bool tc_rerank_supported(int64_t, int, int, int);
 int launch_maxsim_tc_rerank(const void*, const int64_t*, int64_t, int64_t, const int32_t*, int, const void*, int, int, int,
@@ -70,7 +70,7 @@ int launch_maxsim_tc_rerank(const void*, const int64_t*, int64_t, int64_t, const
 int tc_topk_segments(int64_t);
 int tc_topk_list_len();
 int launch_maxsim_tc_topk(const void*, const int64_t*, int64_t, int64_t, const void*, int, int, int, int32_t, float*,
-                          uint64_t*, cudaStream_t);
+                          uint64_t*, int, cudaStream_t);
 int launch_keys_unpack(const uint64_t*, int64_t, int32_t*, float*, cudaStream_t);
 int launch_rerank_unpack(const uint64_t*, int, int, const int32_t*, int, int32_t*, int32_t*, float*, cudaStream_t);
 int launch_rrf(const int32_t*, int, const int32_t*, int, int, int, int, int32_t*, double*, int32_t*, cudaStream_t);
@@ -99,6 +99,11 @@ static int check_device() {
   return 0;
 }
 
+// kernel organisation for one query (maxsim_tc.cu: 0 query-major, 1 M=64, 2 doc-major, 3 auto)
+static int tc_variant(int path) {
+  return path == HRC_PATH_TC_M64 ? 1 : (path == HRC_PATH_TC_DM ? 2 : (path == HRC_PATH_AUTO ? 3 : 0));
+}
+
 // bytes of caller workspace one scoring call needs (only queries longer than 32 tokens on the tensor-core path)
 static size_t maxsim_ws_bytes(int64_t n_items, int n_queries, int lq, int path) {
   if (path == HRC_PATH_SIMT) return 0;
@@ -116,10 +121,11 @@ static int maxsim_dispatch(const void* d_tokens, const int64_t* d_offsets, int64
   // AUTO: the tensor-core path whenever it applies (lq <= 256).  Measured on B200 (profiles/r02_summary.md, "TC / SIMT
   // crossover"): the tcgen05 kernel is faster than the CUDA-core kernel down to a single query token and a 50-document
   // rerank, because the SIMT kernel is FMA-bound and both pay the same launch latency.
+  int variant = tc_variant(path);
   if (path == HRC_PATH_AUTO) path = (lq <= HRC_TC_MAX_LQ * HRC_TC_MAX_SLOTS && total_tokens > 0) ? HRC_PATH_TC : HRC_PATH_SIMT;
-  if (path == HRC_PATH_TC || path == HRC_PATH_TC_M64)
+  if (path == HRC_PATH_TC || path == HRC_PATH_TC_M64 || path == HRC_PATH_TC_DM)
     return launch_maxsim_tc(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_items, d_queries, n_queries, lq,
-                            d_scores, path == HRC_PATH_TC_M64, d_workspace, workspace_bytes, stream);
+                            d_scores, variant, d_workspace, workspace_bytes, stream);
   HRC_REQUIRE(path == HRC_PATH_SIMT, "maxsim: unknown path %d", path);
   return launch_maxsim_simt(d_tokens, d_offsets, n_docs, d_cand_ids, n_items, d_queries, n_queries, lq, d_scores,
                             stream);
@@ -144,7 +150,7 @@ __global__ void shift_ids_kernel(int32_t* ids, int64_t n, int32_t delta) {
 // score matrix is never written) for a SINGLE query of <= 32 tokens with k <= 128 on the tensor-core path — the
 // HBM-bound kernel, whose epilogue has slack.  Otherwise: score matrix -> streaming / radix top-k.
 static bool search_is_fused(int64_t total_tokens, int nq, int lq, int k, int path) {
-  return (path == HRC_PATH_AUTO || path == HRC_PATH_TC) && tc_topk_supported(total_tokens, nq, lq, k);
+  return (path == HRC_PATH_AUTO || path == HRC_PATH_TC || path == HRC_PATH_TC_DM) && tc_topk_supported(total_tokens, nq, lq, k);
 }
 
 struct SearchLayout {      // fused: candidate keys.  staged: score matrix, slot partials (lq > 32), top-k scratch
@@ -337,9 +343,10 @@ int hrc_search(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, i
     HRC_REQUIRE(n_queries <= 65535, "search: too many queries (%d)", n_queries);
     uint64_t* cand = reinterpret_cast<uint64_t*>(ws + L.cand);
     if (int rc = launch_maxsim_tc_topk(d_tokens, d_offsets, n_docs, total_tokens, d_queries, n_queries, lq, k, id_base,
-                                       nullptr, cand, st))
+                                       nullptr, cand, tc_variant(path), st))
       return rc;
-    return launch_topk_merge(cand, L.n_seg * tc_topk_list_len(), n_queries, k, d_keys_out, st, d_ids_out, d_scores_out);
+    return launch_topk_merge(cand, L.n_seg * tc_topk_list_len(), n_queries, k, d_keys_out, st, d_ids_out, d_scores_out,
+                             tc_topk_list_len());
   }
   float* scores = reinterpret_cast<float*>(ws + L.scores);
   if (int rc = maxsim_dispatch(d_tokens, d_offsets, n_docs, total_tokens, nullptr, n_docs, d_queries, n_queries, lq,

@@ -231,6 +231,15 @@ int hrc_comm_init(const void* unique_id, int world, int rank, hrc_comm_t** out) 
     delete c;
     return 1;
   }
+  // warm the communicator up (NCCL sets up its channels lazily on the first collectives): three tiny all-gathers now,
+  // not inside somebody's first searches
+  uint64_t* d_tmp = nullptr;
+  if (cudaMalloc(reinterpret_cast<void**>(&d_tmp), sizeof(uint64_t) * 128 * (world + 1)) == cudaSuccess) {
+    cudaMemset(d_tmp, 0, sizeof(uint64_t) * 128 * (world + 1));
+    for (int i = 0; i < 3; ++i) g_nccl.AllGather(d_tmp + 128 * world, d_tmp, 128, ncclUint64, c->nccl, nullptr);
+    cudaDeviceSynchronize();
+    cudaFree(d_tmp);
+  }
   *out = reinterpret_cast<hrc_comm_t*>(c);
   return 0;
 }

@@ -181,7 +181,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   static_assert(kTileBytes % 2048 == 0, "tile slabs must stay 1024-byte aligned for the 128B swizzle");
   static_assert((MT == 1 && (ZP == 1 || ZP == 2) && CG == 1) || (MT == 2 && ZP == 0 && (CG == 1 || CG == 2)),
                 "instantiations: <1,1,1> <1,2,1> <2,0,1> <2,0,2>");
-  static_assert(!(TK && ZP == 2), "fused top-k: not for the M=64 variant (its scores are combined with atomicAdd)");
+  static_assert(!TK || (MT == 1 && ZP == 1), "fused top-k: the single-query kernel only (see tc_topk_supported)");
   // A tile's accumulators (all M-tiles) are ONE unit: one tfull / tempty pair per stage.  The warps of a lane group
   // alternate DOCUMENTS and each reads all M-tiles of a tile in one walk.
   // HBM-bound kernels (MT == 1): ONE tcgen05.commit per tile (tfull); the shared-memory slot is released by the
@@ -202,7 +202,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   uint64_t* qfull = bars + 28;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
   int64_t* seg = reinterpret_cast<int64_t*>(bars + 30);  // [0]=doc_begin [1]=doc_end [2]=tok_begin [3]=tok_end
-  uint64_t* lists = bars + 64;                           // TK: [kEpiWarps][MT][kListCap] keys
+  uint64_t* lists = bars + 64;                           // TK: [kEpiWarps][kListCap] keys
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -425,38 +425,29 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
 #pragma unroll
     for (int j = 0; j < MT; ++j) pend_m[j] = 0.f;
 
-    // TK: this warp's key lists (one per M-tile).  The emitting lanes — lane 0 for M-tile 0, lane 16 for M-tile 1 —
-    // own their list's fill count and threshold (the k-th best key so far; 0 = accept everything).
+    // TK (single-query kernel only): this warp's key list.  After warp_sum EVERY lane holds the document's score, and
+    // every lane keeps the list's fill count, threshold key and threshold score, so "does this score enter the list?" is
+    // one float compare and a warp-uniform branch — no vote, no shuffle.  Only then is the 64-bit key formed (by every
+    // lane, identically), stored by lane 0, and a full list compacted with a bitonic sort.
     const int lidx = slot * rep + sub;                       // 0 .. kEpiWarps-1
-    uint64_t* my_lists = lists + size_t(lidx) * MT * kListCap;
-    uint64_t* lst = my_lists + ((MT == 2 && lane >= 16) ? kListCap : 0);
-    // The epilogue is instruction-bound in the batched kernels, so the common case must cost next to nothing: after
-    // the butterfly EVERY lane of a half-warp holds its M-tile's score, and every lane keeps a copy of its list's
-    // threshold score (thr_f: the k-th best so far), so "does this score enter the list?" is one float compare and one
-    // vote for the whole warp.  Only when some score passes does the warp take the slow path (form the key, append,
-    // compact a full list with a bitonic sort).
-    uint32_t cnt = 0;
-    uint64_t thr = 0;
+    uint64_t* lst = lists + size_t(lidx) * kListCap;
+    uint32_t cnt = 0;                                        // warp-uniform
+    uint64_t thr = 0;                                        // warp-uniform: the k-th best key so far (0: accept everything)
     float thr_f = -INFINITY;
     if constexpr (TK) {
-      for (int i = lane; i < MT * kListCap; i += 32) my_lists[i] = 0;
+      for (int i = lane; i < kListCap; i += 32) lst[i] = 0;
       __syncwarp();
     }
-    auto append_slow = [&](bool pass, float score, int64_t doc) {     // whole warp; `pass` per half-warp
-      if (pass && (lane & 15) == 0 && (MT == 2 || lane == 0)) {
-        const uint64_t key = make_key(score, int32_t(p.id_base + int32_t(doc)));
-        if (key > thr) lst[cnt++] = key;
-      }
-      if (!__any_sync(0xffffffffu, cnt >= uint32_t(kListCap))) return;
-#pragma unroll
-      for (int j = 0; j < MT; ++j) {                                   // sort the full list(s), keep the best k
-        if (__shfl_sync(0xffffffffu, cnt, j * 16) >= uint32_t(kListCap)) {
-          warp_sort256_desc(my_lists + j * kListCap, lane);
-          float tf = 0.f;
-          if (lane == j * 16) { cnt = uint32_t(p.k); thr = lst[p.k - 1]; tf = key_score(thr); }
-          tf = __shfl_sync(0xffffffffu, tf, j * 16);
-          if (MT == 1 || (lane >> 4) == j) thr_f = tf;
-        }
+    auto offer = [&](float score, int64_t doc) {             // whole warp, uniform arguments
+      if (score < thr_f) return;                             // (false for NaN, which make_key orders as -inf)
+      const uint64_t key = make_key(score, int32_t(p.id_base + int32_t(doc)));
+      if (key <= thr) return;
+      if (lane == 0) lst[cnt] = key;
+      if (++cnt == uint32_t(kListCap)) {
+        warp_sort256_desc(lst, lane);
+        cnt = uint32_t(p.k);
+        thr = lst[p.k - 1];
+        thr_f = key_score(thr);
       }
     };
 
@@ -472,11 +463,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
         for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         const bool act = lo_half ? active[0] : active[1];
         const int64_t row = lo_half ? out_row[0] : out_row[1];
-        if ((lane & 15) == 0 && act && (!TK || p.scores != nullptr)) p.scores[row + pend_col] = a;
-        if constexpr (TK) {
-          const bool pass = act && !(a < thr_f);           // (also true for NaN, which make_key orders as -inf)
-          if (!HRC_DBG(p, 8) && __any_sync(0xffffffffu, pass)) append_slow(pass, a, pend_col);
-        }
+        if ((lane & 15) == 0 && act) p.scores[row + pend_col] = a;
       } else {
         // M=64: only lanes 0-15 of a lane group hold accumulator rows (16 query tokens)
         const float sc = warp_sum((ZP == 2 && lane >= 16) ? 0.f : pend_m[0]);
@@ -489,9 +476,8 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
           }
         }
       }
-      if constexpr (TK && MT == 1) {
-        const bool pass = active[0] && !(sc_all < thr_f);
-        if (__any_sync(0xffffffffu, pass)) append_slow(pass, sc_all, pend_col);
+      if constexpr (TK) {
+        if (active[0]) offer(sc_all, pend_col);
       }
       pending = false;
     };
@@ -591,31 +577,20 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     if (pending) emit_pending();
 
     if constexpr (TK) {
-      // every list sorted, best first
-#pragma unroll
-      for (int j = 0; j < MT; ++j) warp_sort256_desc(my_lists + j * kListCap, lane);
-      // the `rep` warps of a lane group scored disjoint documents for the same queries: tree-merge their lists
+      warp_sort256_desc(lst, lane);         // sorted, best first
+      // the `rep` warps of a lane group scored disjoint documents for the same query: tree-merge their lists
       // (partner's best kListOut into the upper half, sort).  All epilogue warps meet at the named barrier.
       for (int st = 1; st < rep; st <<= 1) {
         asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
         if ((sub & (2 * st - 1)) == 0 && sub + st < rep) {
-          const uint64_t* other = lists + size_t(lidx + st) * MT * kListCap;
-#pragma unroll
-          for (int j = 0; j < MT; ++j) {
-            for (int i = lane; i < kListOut; i += 32) my_lists[j * kListCap + kListOut + i] = other[j * kListCap + i];
-            warp_sort256_desc(my_lists + j * kListCap, lane);
-          }
+          const uint64_t* other = lists + size_t(lidx + st) * kListCap;
+          for (int i = lane; i < kListOut; i += 32) lst[kListOut + i] = other[i];
+          warp_sort256_desc(lst, lane);
         }
       }
-      if (sub == 0) {
-#pragma unroll
-        for (int j = 0; j < MT; ++j) {
-          if (active[j]) {
-            const int q = q_base + 4 * j + slot;
-            uint64_t* out = p.cand_keys + (int64_t(q) * p.n_segments + item) * kListOut;
-            for (int i = lane; i < kListOut; i += 32) out[i] = my_lists[j * kListCap + i];
-          }
-        }
+      if (sub == 0 && active[0]) {
+        uint64_t* out = p.cand_keys + (int64_t(q_base + slot) * p.n_segments + item) * kListOut;
+        for (int i = lane; i < kListOut; i += 32) out[i] = lst[i];
       }
     }
   }
@@ -665,6 +640,300 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
       }
     }
   }
+}
+
+// =====================================================================================================================
+// maxsim_dm_kernel — the DOC-MAJOR orientation for ONE query: A = document tokens (M = 128), B = the query (N = 32).
+//
+// The query-major kernel above puts the query on the M axis, so a single 32-token query occupies 32 of the 128 rows of
+// every MMA: three quarters of the issued tensor work multiplies zeros.  That costs nothing at burst clocks, but the
+// single-query search is what runs for seconds on end, at the GPU's power cap, where every watt spent on the tensor
+// pipe is a watt the memory system does not get.  Here D[row = document token][col = query token] = 128 lanes x 32
+// columns: exactly the useful work (2 * 32 * 128 flop per token), a quarter of the tensor-pipe time and of the B-operand
+// traffic, 16 accumulator stages of 32 TMEM columns instead of 4 of 128.
+//
+// The price is the epilogue: the max over a document's tokens now runs ACROSS LANES.  To keep it warp-local, a tile is
+// not 128 consecutive tokens but 4 x 32: the CTA's segment is cut into FOUR token streams of whole documents, one per
+// epilogue warp / TMEM lane quadrant, and tile t holds tokens [32t, 32t + 32) of each stream (4 TMA boxes of 32 rows).
+// A warp therefore sees ITS stream chunk by chunk on its own 32 lanes — lane i = token 32t + i of the stream, register
+// j = query token j — and reduces a document's piece with a 5-level max butterfly (31 shuffles) that leaves lane j
+// holding max_t <q_j, d_t>; the running maximum stays in that lane across chunks, and a finished document is one
+// warp_sum.  No cross-warp combine, no atomics, documents never split between warps.
+// =====================================================================================================================
+constexpr int kDmQBytes = 32 * HRC_DIM * 2;         // the query as the B operand: 32 rows, 8 KB
+constexpr int kDmTileBytes = 128 * HRC_DIM * 2;      // 4 streams x 32 tokens, 32 KB
+constexpr int kDmStages = 5;
+constexpr int kDmAcc = 16;                          // accumulator stages: 512 TMEM columns / 32
+constexpr int kDmThreads = 6 * 32;                  // TMA warp, MMA warp, 4 epilogue warps
+
+// one level of the max reduce-scatter: N live values per lane -> N/2, exchanging with lane ^ OFF
+template <int N, int OFF>
+__device__ __forceinline__ void max_halve(float (&a)[32], bool upper) {
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) {
+    const float keep = upper ? a[i + N / 2] : a[i];
+    const float send = upper ? a[i] : a[i + N / 2];
+    a[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, OFF));
+  }
+}
+// lane j <- max over the 32 lanes of a[j]   (a is destroyed)
+__device__ __forceinline__ float lanes_max_transpose(float (&a)[32], int lane) {
+  max_halve<32, 16>(a, (lane & 16) != 0);
+  max_halve<16, 8>(a, (lane & 8) != 0);
+  max_halve<8, 4>(a, (lane & 4) != 0);
+  max_halve<4, 2>(a, (lane & 2) != 0);
+  max_halve<2, 1>(a, (lane & 1) != 0);
+  return a[0];
+}
+
+template <bool TK>
+__global__ void __launch_bounds__(kDmThreads, 1)
+maxsim_dm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
+  constexpr uint32_t kIdesc = make_idesc_bf16_f32(128, 32);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                        // 8 KB (1024-aligned)
+  uint8_t* sD = smem + kDmQBytes;                            // kDmStages x 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + kDmStages * kDmTileBytes);
+  uint64_t* full = bars;                           // [kDmStages] TMA -> MMA
+  uint64_t* empty = bars + 8;                      // [kDmStages] epilogue (forwarding the MMA's completion) -> TMA
+  uint64_t* tfull = bars + 16;                     // [kDmAcc]    MMA -> epilogue
+  uint64_t* tempty = bars + 32;                    // [kDmAcc]    epilogue -> MMA
+  uint64_t* qfull = bars + 48;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 49);
+  int64_t* sdoc = reinterpret_cast<int64_t*>(bars + 50);     // [5] first document of each stream (+ end)
+  int64_t* stok = reinterpret_cast<int64_t*>(bars + 55);     // [5] first token of each stream (+ end)
+  uint64_t* lists = bars + 64;                               // TK: [4][kListCap] keys
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint64_t wd = p.watchdog_ns;
+  const int64_t item = blockIdx.x;
+
+  if (threadIdx.x < 5) {       // stream boundaries: the segment's token range cut in four at document starts
+    const int64_t b0 = (p.total_tokens * item) / p.n_segments;
+    const int64_t b1 = (p.total_tokens * (item + 1)) / p.n_segments;
+    const int64_t d0 = item == 0 ? 0 : lower_bound_doc(p.offsets, p.n_docs, b0);
+    const int64_t d1 = (item + 1 == p.n_segments) ? p.n_docs : lower_bound_doc(p.offsets, p.n_docs, b1);
+    const int64_t t0 = p.offsets[d0], t1 = p.offsets[d1];
+    int64_t d;
+    if (threadIdx.x == 0) d = d0;
+    else if (threadIdx.x == 4) d = d1;
+    else {
+      d = lower_bound_doc(p.offsets, p.n_docs, t0 + ((t1 - t0) * int64_t(threadIdx.x)) / 4);
+      d = d < d0 ? d0 : (d > d1 ? d1 : d);
+    }
+    sdoc[threadIdx.x] = d;
+    stok[threadIdx.x] = p.offsets[d];
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_d);
+    tma_prefetch_desc(&tmap_q);
+    for (int i = 0; i < kDmStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kDmAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    mbar_init(qfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+
+  const uint32_t acc_base = *tmem_slot;
+  int64_t longest = 0;
+#pragma unroll
+  for (int s4 = 0; s4 < 4; ++s4) longest = max(longest, stok[s4 + 1] - stok[s4]);
+  const int n_tiles = int((longest + 31) / 32);
+
+  if (warp == 0) {
+    // =============================== TMA producer =============================================
+    if (n_tiles > 0 && elect_one()) {
+      mbar_arrive_expect_tx(qfull, kDmQBytes);
+      tma_load_3d(sQ, &tmap_q, qfull, 0, 0, p.vq_base, kEvictLast);                  // rows >= lq arrive as zeros
+      tma_load_3d(sQ + kDmQBytes / 2, &tmap_q, qfull, 64, 0, p.vq_base, kEvictLast);
+      int64_t row0[4];
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) row0[s4] = stok[s4];
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait_wd(&empty[stage], phase ^ 1, wd);
+        uint8_t* dst = sD + stage * kDmTileBytes;
+        if (HRC_DBG(p, 2)) {
+          mbar_arrive(&full[stage]);
+        } else {
+          mbar_arrive_expect_tx(&full[stage], kDmTileBytes);
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) {
+            // a stream that has ended keeps loading (its neighbour's tokens, or zeros beyond the store): harmless, no
+            // document of this warp owns those lanes, and the byte count of a tile stays constant
+            const int row = int(row0[s4] + int64_t(t) * 32);
+            tma_load_2d(dst + s4 * 4096, &tmap_d, &full[stage], 0, row, p.doc_policy);
+            tma_load_2d(dst + kDmTileBytes / 2 + s4 * 4096, &tmap_d, &full[stage], 64, row, p.doc_policy);
+          }
+        }
+        if (++stage == kDmStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================================
+    if (n_tiles > 0) {
+      mbar_wait_wd(qfull, 0, wd);
+      tc_fence_after_sync();
+      const uint32_t sQ_addr = smem_u32(sQ);
+      const uint32_t sD_addr = smem_u32(sD);
+      int stage = 0; uint32_t phase = 0;
+      int ts = 0; uint32_t tphase = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait_wd(&full[stage], phase, wd);
+        mbar_wait_wd(&tempty[ts], tphase ^ 1, wd);
+        tc_fence_after_sync();
+        if (elect_one()) {
+          const uint32_t a_tile = sD_addr + stage * kDmTileBytes;
+          const uint32_t d_tmem = acc_base + uint32_t(ts * 32);
+#pragma unroll
+          for (int k = 0; k < HRC_DIM / 16; ++k) {
+            if (HRC_DBG(p, 4)) break;
+            const uint64_t a_desc = make_kmajor_sw128_desc(a_tile + (k >> 2) * (kDmTileBytes / 2) + (k & 3) * 32);   // documents
+            const uint64_t b_desc = make_kmajor_sw128_desc(sQ_addr + (k >> 2) * (kDmQBytes / 2) + (k & 3) * 32);     // query
+            umma_bf16_ss(d_tmem, a_desc, b_desc, kIdesc, k > 0 ? 1u : 0u);
+          }
+          umma_commit(&tfull[ts]);          // the first epilogue warp forwards it to empty[stage]
+        }
+        __syncwarp();
+        if (++stage == kDmStages) { stage = 0; phase ^= 1; }
+        if (++ts == kDmAcc) { ts = 0; tphase ^= 1; }
+      }
+    }
+  } else {
+    // =============================== epilogue: one stream per warp ============================
+    const int quad = warp & 3;                           // TMEM lanes 32*quad.. = rows 32*quad.. of the tile = stream `quad`
+    const uint32_t lane_base = uint32_t(quad * 32) << 16;
+    const int64_t doc_begin = sdoc[quad], doc_end = sdoc[quad + 1], tok_begin = stok[quad];
+    const int n_docs_seg = int(doc_end - doc_begin);
+    const int my_chunks = int((stok[quad + 1] - tok_begin + 31) / 32);
+    const bool q_active = p.vq_base < p.n_queries;
+    const int64_t out_row = int64_t(p.vq_base) * p.n_items;
+
+    const uint32_t tok_begin_lo = uint32_t(tok_begin);
+    const uint32_t raw_none = tok_begin_lo + uint32_t(INT_MAX);
+    int batch = 0;
+    uint32_t ends = raw_none, ends_next = raw_none;
+    auto load_ends = [&](int b) -> uint32_t {
+      const int d = b * 32 + lane;
+      uint32_t r = raw_none;
+      if (d < n_docs_seg) r = uint32_t(p.offsets[doc_begin + d + 1]);
+      return r;
+    };
+    auto end_of = [&](int d) -> int {   // d non-decreasing over calls, -1 <= d < n_docs_seg
+      if (d < 0) return 0;
+#pragma unroll 1
+      while ((d >> 5) > batch) {
+        ends = ends_next;
+        ++batch;
+        ends_next = load_ends(batch + 1);
+      }
+      return int(__shfl_sync(0xffffffffu, ends, d & 31) - tok_begin_lo);
+    };
+    ends = load_ends(0);
+    ends_next = load_ends(1);
+
+    int my = 0;                              // local index of the document being accumulated
+    bool have_doc = q_active && n_docs_seg > 0;
+    int s_tok = 0, e_tok = 0;
+    if (have_doc) e_tok = end_of(0);
+    float m = -INFINITY;                    // lane j: running max_t <q_j, d_t> of the current document
+
+    // fused top-k state (see the query-major kernel)
+    uint64_t* lst = lists + size_t(quad) * kListCap;
+    uint32_t cnt = 0;                        // warp-uniform, like thr and thr_f: every lane holds the score after warp_sum
+    uint64_t thr = 0;
+    float thr_f = -INFINITY;
+    if constexpr (TK) {
+      for (int i = lane; i < kListCap; i += 32) lst[i] = 0;
+      __syncwarp();
+    }
+    auto finish_doc = [&]() {
+      const float sc = warp_sum(m);
+      const int64_t col = doc_begin + my;
+      if (lane == 0 && (!TK || p.scores != nullptr)) p.scores[out_row + col] = sc;
+      if constexpr (TK) {
+        if (!HRC_DBG(p, 8) && !(sc < thr_f)) {   // one compare per document; warp-uniform (also taken for NaN)
+          const uint64_t key = make_key(sc, int32_t(p.id_base + int32_t(col)));
+          if (key > thr) {
+            if (lane == 0) lst[cnt] = key;
+            if (++cnt == uint32_t(kListCap)) {
+              warp_sort256_desc(lst, lane);
+              cnt = uint32_t(p.k);
+              thr = lst[p.k - 1];
+              thr_f = key_score(thr);
+            }
+          }
+        }
+      }
+      m = -INFINITY;
+      ++my;
+      have_doc = my < n_docs_seg;
+      s_tok = e_tok;
+      if (have_doc) e_tok = end_of(my);
+    };
+
+    int ts = 0; uint32_t tphase = 0;
+    int stage_e = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      mbar_wait_wd(&tfull[ts], tphase, wd);
+      if (quad == 0 && lane == 0) mbar_arrive(&empty[stage_e]);   // the tile's MMAs are done: its smem slot may be refilled
+      if (++stage_e == kDmStages) stage_e = 0;
+      tc_fence_after_sync();
+      if (t < my_chunks && have_doc && !HRC_DBG(p, 1)) {
+        uint32_t v[32];
+        tmem_ld_32x32(acc_base + lane_base + uint32_t(ts * 32), v);
+        tmem_ld_wait();
+        const int c0 = t * 32, c1 = c0 + 32;
+        while (have_doc && s_tok < c1) {
+          const int lo = max(s_tok, c0), hi = min(e_tok, c1);     // this document's tokens inside this chunk: lanes [lo-c0, hi-c0)
+          if (hi > lo) {
+            float w[32];
+            if (hi - lo == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) w[j] = __uint_as_float(v[j]);
+            } else {
+              const bool mine = lane >= lo - c0 && lane < hi - c0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) w[j] = mine ? __uint_as_float(v[j]) : -INFINITY;
+            }
+            m = fmaxf(m, lanes_max_transpose(w, lane));
+          }
+          if (e_tok > c1) break;              // the document continues in the next chunk
+          finish_doc();
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[ts]);
+      if (++ts == kDmAcc) { ts = 0; tphase ^= 1; }
+    }
+    while (have_doc) finish_doc();            // trailing empty documents: -inf
+
+    if constexpr (TK) {
+      if (!HRC_DBG(p, 32)) warp_sort256_desc(lst, lane);
+      for (int st = 1; st < (HRC_DBG(p, 32) ? 1 : 4); st <<= 1) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if ((quad & (2 * st - 1)) == 0) {
+          const uint64_t* other = lists + size_t(quad + st) * kListCap;
+          for (int i = lane; i < kListOut; i += 32) lst[kListOut + i] = other[i];
+          warp_sort256_desc(lst, lane);
+        }
+      }
+      if (quad == 0 && q_active) {
+        uint64_t* out = p.cand_keys + (int64_t(p.vq_base) * p.n_segments + item) * kListOut;
+        for (int i = lane; i < kListOut; i += 32) out[i] = lst[i];
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(acc_base, kTmemCols);
 }
 
 // --- host side -------------------------------------------------------------------------------
@@ -755,7 +1024,7 @@ int sm_count() {
 uint64_t g_watchdog_ns = 20ull * 1000000000ull;   // hrc_set_watchdog_ms
 #ifdef HRC_EXPERIMENTS
 int g_debug = 0;                                  // hrc_exp_set_debug: 1 no epilogue math, 2 no document TMA, 4 no MMA,
-                                                  // 8 fused top-k never appends, 16 non-TK kernels get the TK kernels' smem
+                                                  // 8 doc-major fused top-k never offers, 32 ... skips its final list merge
 int g_stages = 0;                                 // hrc_exp_set_stages: cap of the shared-memory ring depth (0 = default)
 #endif
 
@@ -768,10 +1037,7 @@ int launch_cfg(const void* d_tokens, const void* d_queries, int lq, int n_real_q
   if (int rc = cached_map(d_tokens, uint64_t(p.total_tokens), 0, TN / CG, &tmap_d)) return rc;
   if (int rc = cached_map(d_queries, uint64_t(lq), uint64_t(n_real_queries), 32, &tmap_q)) return rc;
   const int q_bytes = MT * kQBytes;
-  int list_bytes = TK ? epi_warps(MT, ZP) * MT * kListCap * 8 : 0;
-#ifdef HRC_EXPERIMENTS
-  if (!TK && (g_debug & 16)) list_bytes = epi_warps(MT, ZP) * MT * kListCap * 8;
-#endif
+  const int list_bytes = TK ? epi_warps(MT, ZP) * kListCap * 8 : 0;
   int stages = (kMaxSmem - 1024 - 512 - q_bytes - list_bytes) / kTileBytes;
   // Ring depth: 8 x 16 KB for the batched kernels; FIVE x 32 KB for the HBM-bound ones — a sixth stage fits but is
   // slower (libhrc_exp stage sweep, same box: C2 4.67-4.90 ms with 6, 4.69-4.78 with 5, 4.60-4.64 with 4, 5.09 with 3;
@@ -816,6 +1082,27 @@ int launch_cfg(const void* d_tokens, const void* d_queries, int lq, int n_real_q
   return 0;
 }
 
+template <bool TK>
+int launch_dm(const void* d_tokens, const void* d_queries, int lq, int n_real_queries, TcParams p, cudaStream_t stream) {
+  CUtensorMap tmap_d, tmap_q;
+  if (int rc = cached_map(d_tokens, uint64_t(p.total_tokens), 0, 32, &tmap_d)) return rc;     // one stream's 32-token box
+  if (int rc = cached_map(d_queries, uint64_t(lq), uint64_t(n_real_queries), 32, &tmap_q)) return rc;
+  p.n_stages = kDmStages;
+  const int smem_bytes = 1024 + kDmQBytes + kDmStages * kDmTileBytes + 512 + (TK ? 4 * kListCap * 8 : 0);
+  static PerDeviceOnce once;
+  int dev;
+  if (once.pending(&dev)) {
+    HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_dm_kernel<TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    once.mark(dev);
+  }
+  trace_begin(stream);
+  maxsim_dm_kernel<TK><<<dim3((unsigned)p.n_segments), kDmThreads, smem_bytes, stream>>>(tmap_d, tmap_q, p);
+  trace_end(stream);
+  count_launch();
+  HRC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // out[q][i] = sum over the slots of query q, in slot order (deterministic)
 __global__ void sum_slots_kernel(const float* __restrict__ part, int q_slots, int64_t n_items, int64_t total,
                                  float* __restrict__ out) {
@@ -826,6 +1113,11 @@ __global__ void sum_slots_kernel(const float* __restrict__ part, int q_slots, in
   for (int sl = 0; sl < q_slots; ++sl) acc += part[(q * q_slots + sl) * n_items + d];
   out[i] = acc;
 }
+
+// single-query kernel organisations.  Auto (HRC_PATH_AUTO): doc-major for one query of <= 32 tokens over the corpus —
+// same time as the query-major kernel at burst clocks, 5-7 % faster once the GPU sits at its power cap (3 s back to back,
+// same box: 4.77 vs 5.10 ms per C2 search; M=64 4.98) — query-major for everything else.
+constexpr int kVariantDefault = 0, kVariantM64 = 1, kVariantDocMajor = 2, kVariantAuto = 3;
 
 struct TopkOut {            // fused top-k request (corpus mode, lq <= 32, k <= kListOut)
   uint64_t* cand_keys;
@@ -843,8 +1135,10 @@ constexpr int kRerankFusedMax = 1024;
 
 int launch_tc_slots(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
                     const int32_t* d_cand_ids, int64_t n_items, const void* d_queries, int n_real_queries,
-                    int q_slots, int lq, float* d_scores, bool m64, const TopkOut* tk, const RerankOut* rr,
+                    int q_slots, int lq, float* d_scores, int variant, const TopkOut* tk, const RerankOut* rr,
                     cudaStream_t stream) {
+  const bool m64 = variant == kVariantM64;
+  const bool dm = variant == kVariantDocMajor || (variant == kVariantAuto && d_cand_ids == nullptr && q_slots == 1);
   const int n_queries = n_real_queries * q_slots;      // virtual queries from here on
   HRC_REQUIRE(total_tokens > 0 && total_tokens < (1ll << 31), "tc path: total_tokens=%lld out of range",
               (long long)total_tokens);
@@ -887,6 +1181,13 @@ int launch_tc_slots(const void* d_tokens, const int64_t* d_offsets, int64_t n_do
   }
   const int64_t tiles = (total_tokens + TN - 1) / TN;
   p.n_segments = int(tiles < sm_count() ? tiles : sm_count());
+  if (dm && n_queries == 1) {                   // doc-major orientation: exactly the useful tensor work
+    // every stream of a CTA wants at least a chunk or two: 4 streams per segment
+    const int64_t chunks = (total_tokens + 127) / 128;
+    p.n_segments = int(chunks < sm_count() ? chunks : sm_count());
+    return tk ? launch_dm<true>(d_tokens, d_queries, lq, n_real_queries, p, stream)
+              : launch_dm<false>(d_tokens, d_queries, lq, n_real_queries, p, stream);
+  }
   if (n_queries <= 4) {
     p.slots_used = n_queries == 1 ? 1 : (n_queries == 2 ? 2 : 4);
     if (tk) return launch_cfg<1, 1, 1, true>(d_tokens, d_queries, lq, n_real_queries, p, dim3((unsigned)p.n_segments), stream);
@@ -959,14 +1260,14 @@ int tc_topk_list_len() { return kListOut; }
 // d_cand_keys: uint64 [n_queries][tc_topk_segments()][kListOut]; d_scores optional (the full matrix, if wanted)
 int launch_maxsim_tc_topk(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
                           const void* d_queries, int n_queries, int lq, int k, int32_t id_base, float* d_scores,
-                          uint64_t* d_cand_keys, cudaStream_t stream) {
+                          uint64_t* d_cand_keys, int variant, cudaStream_t stream) {
   if (n_docs == 0 || n_queries == 0) return 0;
   HRC_REQUIRE(tc_topk_supported(total_tokens, n_queries, lq, k), "fused top-k: needs <= %d queries, lq <= %d and k <= %d",
               HRC_FUSED_TOPK_MAX_QUERIES, HRC_TC_MAX_LQ, kListOut);
   HRC_REQUIRE(d_cand_keys != nullptr, "fused top-k: null candidate buffer");
   const TopkOut tk{d_cand_keys, k, id_base};
   return launch_tc_slots(d_tokens, d_offsets, n_docs, total_tokens, nullptr, n_docs, d_queries, n_queries, 1, lq, d_scores,
-                         false, &tk, nullptr, stream);
+                         variant, &tk, nullptr, stream);
 }
 
 // ---- fused rerank: candidate MaxSim + sorted top-k in ONE launch (hrc_rerank's default) ----------------------------
@@ -987,7 +1288,7 @@ int launch_maxsim_tc_rerank(const void* d_tokens, const int64_t* d_offsets, int6
   HRC_CHECK_CUDA(cudaMemsetAsync(d_counter, 0, size_t(n_queries) * sizeof(uint32_t), stream));
   const RerankOut rr{d_counter, k, d_pos, d_ids, d_scores_out};
   return launch_tc_slots(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_cand, d_queries, n_queries, 1, lq,
-                         d_scores, false, nullptr, &rr, stream);
+                         d_scores, kVariantDefault, nullptr, &rr, stream);
 }
 
 // bytes of caller workspace the tensor-core path needs: the per-slot partial scores of queries longer than 32 tokens
@@ -999,14 +1300,14 @@ size_t maxsim_tc_workspace_bytes(int64_t n_items, int n_queries, int lq) {
 
 int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
                      const int32_t* d_cand_ids, int64_t n_items, const void* d_queries, int n_queries,
-                     int lq, float* d_scores, bool m64, void* d_workspace, size_t workspace_bytes, cudaStream_t stream) {
+                     int lq, float* d_scores, int variant, void* d_workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (n_items == 0 || n_queries == 0) return 0;
   HRC_REQUIRE(lq >= 1 && lq <= HRC_TC_MAX_LQ * HRC_TC_MAX_SLOTS, "tc path: lq=%d not in [1,%d]", lq,
               HRC_TC_MAX_LQ * HRC_TC_MAX_SLOTS);
   const int q_slots = (lq + HRC_TC_MAX_LQ - 1) / HRC_TC_MAX_LQ;
   if (q_slots == 1)
     return launch_tc_slots(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_items, d_queries, n_queries, 1, lq,
-                           d_scores, m64, nullptr, nullptr, stream);
+                           d_scores, variant, nullptr, nullptr, stream);
   // A query of more than 32 tokens is scored as q_slots virtual queries of <= 32 tokens (rows beyond lq arrive as
   // zeros from TMA and add max_t <0, d_t> = 0); their partial scores (caller workspace) are summed in slot order.
   HRC_REQUIRE(int64_t(n_queries) * q_slots <= 65535, "tc path: too many query slots (%d x %d)", n_queries, q_slots);
@@ -1017,7 +1318,7 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
   float* part = static_cast<float*>(d_workspace);
   const int64_t total = int64_t(n_queries) * n_items;
   if (int rc = launch_tc_slots(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_items, d_queries, n_queries,
-                               q_slots, lq, part, m64, nullptr, nullptr, stream))
+                               q_slots, lq, part, variant, nullptr, nullptr, stream))
     return rc;
   sum_slots_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(part, q_slots, n_items, total, d_scores);
   count_launch();

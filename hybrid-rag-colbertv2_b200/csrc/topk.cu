@@ -27,6 +27,7 @@ constexpr int kMergeMax = 24576;      // keys per stage-2 CTA (192 KB)
 constexpr int kSortMax = HRC_MAX_TOPK;
 
 constexpr int kBins = 2048;           // 11-bit digits: 64-bit keys in at most 6 passes, usually 3
+constexpr int kSmallMerge = 2048;     // merges of up to this many keys sort them outright
 
 struct SelectScratch {
   uint32_t hist[kBins];
@@ -180,11 +181,15 @@ select_scores_kernel(const float* __restrict__ scores, const int32_t* __restrict
   select_topk(keys, cn, k, dst, final_sorted != 0, sort_buf, sc);
 }
 
-// ids_out / scores_out (optional, final level only): the unpacked result, so that no separate unpack launch is needed
+// ids_out / scores_out (optional, final level only): the unpacked result, so that no separate unpack launch is needed.
+// list_len > 0 (final level only): the input is a concatenation of lists of list_len keys, each SORTED best first (what
+// the fused MaxSim epilogue and the streaming top-k hand over).  The k-th key of any one list is a lower bound of the
+// global k-th key, so T = max over the lists of their k-th key cuts the candidates to a few hundred: gather the keys
+// >= T, sort them outright.  (If more than kSmallMerge pass — adversarial ties — fall through to the radix select.)
 __global__ void __launch_bounds__(kSelThreads)
 select_keys_kernel(const uint64_t* __restrict__ keys_in, int n_in, int k, uint64_t* __restrict__ out,
                    int n_groups, int group_len, int final_sorted, int32_t* __restrict__ ids_out,
-                   float* __restrict__ scores_out) {
+                   float* __restrict__ scores_out, int list_len) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem);
   uint64_t* sort_buf = keys + group_len;
@@ -195,6 +200,41 @@ select_keys_kernel(const uint64_t* __restrict__ keys_in, int n_in, int k, uint64
   const int begin = group * group_len;
   const int gn = min(group_len, n_in - begin);
   const uint64_t* src = keys_in + row * n_in + begin;
+  if (list_len > 0 && final_sorted && n_groups == 1 && k <= list_len && gn > kSmallMerge) {
+    __shared__ unsigned long long s_thr;
+    if (threadIdx.x == 0) { s_thr = 0; sc.count = 0; }
+    __syncthreads();
+    unsigned long long t = 0;
+    for (int l = threadIdx.x; l * list_len < gn; l += kSelThreads) t = max(t, (unsigned long long)src[l * list_len + k - 1]);
+    for (int o = 16; o > 0; o >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if ((threadIdx.x & 31) == 0 && t != 0) atomicMax(&s_thr, t);
+    __syncthreads();
+    const uint64_t thr = s_thr;
+    if (thr != 0) {
+      for (int i = threadIdx.x; i < gn; i += kSelThreads) {
+        const uint64_t key = src[i];
+        if (key >= thr) {
+          const int slot = atomicAdd(&sc.count, 1);
+          if (slot < kSmallMerge) keys[slot] = key;
+        }
+      }
+      __syncthreads();
+      const int got = sc.count;
+      if (got <= kSmallMerge) {                       // (got >= k: the list that set T alone holds k keys >= T)
+        const int n_pad = next_pow2(got < k ? k : got);
+        for (int i = got + threadIdx.x; i < n_pad; i += kSelThreads) keys[i] = 0;
+        bitonic_sort_desc(keys, n_pad);
+        for (int i = threadIdx.x; i < k; i += kSelThreads) {
+          const uint64_t key = keys[i];
+          out[row * k + i] = key;
+          if (ids_out) ids_out[row * k + i] = key ? key_id(key) : -1;
+          if (scores_out) scores_out[row * k + i] = key ? key_score(key) : -INFINITY;
+        }
+        return;
+      }
+      __syncthreads();
+    }
+  }
   for (int i = threadIdx.x; i < gn; i += kSelThreads) keys[i] = src[i];
   __syncthreads();
   uint64_t* dst = out + (row * n_groups + group) * k;
@@ -220,10 +260,10 @@ constexpr int kStreamWarps = kStreamThreads / 32;
 constexpr int kStreamMaxChunks = kMergeMax / kKeyListOut;      // chunk lists per row the merge level can take (192)
 
 __host__ __device__ inline int stream_chunks(int64_t n, int n_rows) {
-  int64_t want = (4 * 148 + n_rows - 1) / n_rows;              // ~4 CTAs per SM over all rows
-  const int64_t by_size = (n + 2047) / 2048;                   // at least 2048 scores per CTA
+  int64_t want = (2 * 148 + n_rows - 1) / n_rows;              // ~2 CTAs per SM over all rows ...
+  const int64_t by_size = (n + 2047) / 2048;                   // ... of at least 2048 scores each ...
   if (want > by_size) want = by_size;
-  if (want > kStreamMaxChunks) want = kStreamMaxChunks;
+  if (want > 64) want = 64;                                    // ... and at most 64 lists per row for the merge launch
   return int(want < 1 ? 1 : want);
 }
 
@@ -349,6 +389,26 @@ merge_parts_kernel(const uint64_t* __restrict__ parts, int n_parts, int64_t part
     __syncthreads();
   }
   const int64_t row = blockIdx.x;
+  if (n <= kSmallMerge) {
+    // few keys (2..8 ranks x k = 100: the usual case): one bitonic sort of the padded list, no radix passes
+    const int n_pad = next_pow2(n < k ? k : n);
+    for (int i = threadIdx.x; i < n_pad; i += kSelThreads) {
+      uint64_t key = 0;
+      if (i < n) {
+        const int p = i / k, j = i - p * k;
+        key = __ldcg(parts + int64_t(p) * part_stride + row * k + j);
+      }
+      keys[i] = key;
+    }
+    bitonic_sort_desc(keys, n_pad);
+    for (int i = threadIdx.x; i < k; i += kSelThreads) {
+      const uint64_t key = keys[i];
+      out[row * k + i] = key;
+      if (ids_out) ids_out[row * k + i] = key ? key_id(key) : -1;
+      if (scores_out) scores_out[row * k + i] = key ? key_score(key) : -INFINITY;
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < n; i += kSelThreads) {
     const int p = i / k, j = i - p * k;
     keys[i] = __ldcg(parts + int64_t(p) * part_stride + row * k + j);
@@ -409,7 +469,8 @@ int configure_smem() {
 
 // levels of stage 2 over n_in keys per row; writes sorted top-k to d_out.  tmp holds intermediates.
 int run_key_levels(const uint64_t* d_in, int64_t n_in, int n_rows, int k, uint64_t* d_out, uint64_t* tmp0,
-                   uint64_t* tmp1, cudaStream_t stream, int32_t* d_ids_out = nullptr, float* d_scores_out = nullptr) {
+                   uint64_t* tmp1, cudaStream_t stream, int32_t* d_ids_out = nullptr, float* d_scores_out = nullptr,
+                   int list_len = 0) {
   const uint64_t* cur = d_in;
   int64_t cur_n = n_in;
   int flip = 0;
@@ -422,7 +483,7 @@ int run_key_levels(const uint64_t* d_in, int64_t n_in, int n_rows, int k, uint64
     const size_t smem = size_t(group_len) * 8 + (last ? sort_buf_bytes(k) : 0);
     select_keys_kernel<<<dim3(n_groups, n_rows), kSelThreads, smem, stream>>>(
         cur, int(cur_n), k, dst, n_groups, group_len, last ? 1 : 0, last ? d_ids_out : nullptr,
-        last ? d_scores_out : nullptr);
+        last ? d_scores_out : nullptr, (last && cur == d_in) ? list_len : 0);
     count_launch();
     HRC_CHECK_CUDA(cudaGetLastError());
     if (last) break;
@@ -478,7 +539,7 @@ int launch_topk(const float* d_scores, const int32_t* d_ids, int64_t n, int n_ro
     HRC_CHECK_CUDA(cudaGetLastError());
     if (c == 1) return 0;
     return run_key_levels(cand, int64_t(c) * kKeyListOut, n_rows, k, d_keys_out, nullptr, nullptr, stream, d_ids_out,
-                          d_scores_out);
+                          d_scores_out, kKeyListOut);
   }
   const int64_t n_chunks = (n + kChunk - 1) / kChunk;
   if (n_chunks == 1) {
@@ -507,7 +568,7 @@ int launch_topk(const float* d_scores, const int32_t* d_ids, int64_t n, int n_ro
 }
 
 int launch_topk_merge(const uint64_t* d_keys_in, int n_in, int n_rows, int k, uint64_t* d_keys_out,
-                      cudaStream_t stream, int32_t* d_ids_out, float* d_scores_out) {
+                      cudaStream_t stream, int32_t* d_ids_out, float* d_scores_out, int sorted_list_len) {
   if (n_rows == 0 || k == 0) return 0;
   HRC_REQUIRE(k >= 1 && k <= HRC_MAX_TOPK, "top-k merge: k=%d not in [1,%d]", k, HRC_MAX_TOPK);
   HRC_REQUIRE(n_in >= 0 && n_in <= kMergeMax, "top-k merge: n_in=%d exceeds %d", n_in, kMergeMax);
@@ -517,7 +578,8 @@ int launch_topk_merge(const uint64_t* d_keys_in, int n_in, int n_rows, int k, ui
     HRC_CHECK_CUDA(cudaMemsetAsync(d_keys_out, 0, size_t(n_rows) * k * 8, stream));
     return 0;
   }
-  return run_key_levels(d_keys_in, n_in, n_rows, k, d_keys_out, nullptr, nullptr, stream, d_ids_out, d_scores_out);
+  return run_key_levels(d_keys_in, n_in, n_rows, k, d_keys_out, nullptr, nullptr, stream, d_ids_out, d_scores_out,
+                        sorted_list_len);
 }
 
 uint64_t get_watchdog_ns();
@@ -530,7 +592,9 @@ int launch_topk_merge_parts(const uint64_t* d_parts, int n_parts, int part_strid
   HRC_REQUIRE(n_parts >= 1 && int64_t(n_parts) * k <= kMergeMax, "merge: %d x %d keys exceed %d", n_parts, k, kMergeMax);
   HRC_REQUIRE(n_rows <= 65535 && n_flags <= kSelThreads, "merge: too many rows (%d)", n_rows);
   if (configure_smem()) return 1;
-  const size_t smem = size_t(n_parts) * k * 8 + sort_buf_bytes(k);
+  int n_pad = 1;
+  while (n_pad < n_parts * k || n_pad < k) n_pad <<= 1;
+  const size_t smem = n_parts * k <= kSmallMerge ? size_t(n_pad) * 8 : size_t(n_parts) * k * 8 + sort_buf_bytes(k);
   merge_parts_kernel<<<n_rows, kSelThreads, smem, stream>>>(d_parts, n_parts, part_stride, k, d_keys_out, d_ids_out,
                                                             d_scores_out, d_flags, seq, n_flags, get_watchdog_ns());
   count_launch();

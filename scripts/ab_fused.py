@@ -46,9 +46,13 @@ def ab(name, store, q, steps, rounds=3):
         L.maxsim_scores(store.tokens, store.offsets, q, out=scores)
         L.keys_unpack(L.topk(scores, K, workspace=tws))
 
-    res = {"fused": [], "staged": []}
+    def fused_dm():
+        L.search(store.tokens, store.offsets, q, K, workspace=ws, unpack=True, path=L.PATH_TC_DM)
+
+    routes = [("fused", fused), ("staged", staged)] + ([("fused_doc_major", fused_dm)] if q.shape[0] == 1 else [])
+    res = {name: [] for name, _ in routes}
     for _ in range(rounds):
-        for route, fn in (("fused", fused), ("staged", staged)):
+        for route, fn in routes:
             res[route].append(run(fn, steps))
     for route, xs in res.items():
         print(json.dumps({"config": name, "route": route, "step_ms": [round(a, 3) for a, _ in xs],

@@ -60,7 +60,7 @@ def _dump_observed_errors():
 
 
 def _path(L, name):
-    return {"tc": L.PATH_TC, "simt": L.PATH_SIMT, "tc_m64": L.PATH_TC_M64, "auto": L.PATH_AUTO}[name]
+    return {"tc": L.PATH_TC, "simt": L.PATH_SIMT, "tc_m64": L.PATH_TC_M64, "tc_dm": L.PATH_TC_DM, "auto": L.PATH_AUTO}[name]
 
 
 SHAPES = [
@@ -79,10 +79,11 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-@pytest.mark.parametrize("path", ["tc", "simt", "tc_m64"])
+@pytest.mark.parametrize("path", ["tc", "simt", "tc_m64", "tc_dm"])
 def test_maxsim_scores_match_oracle(cuda_dev, shape, path):
-    """Every scoring path: tcgen05 (default), CUDA cores, and the M=64 tensor-core variant for 1-2 queries
-    (HRC_PATH_TC_M64; with more queries it is the default kernel)."""
+    """Every scoring path: tcgen05 (default), CUDA cores, the M=64 tensor-core variant for 1-2 queries
+    (HRC_PATH_TC_M64) and the doc-major kernel for one query (HRC_PATH_TC_DM); with more queries the last two are the
+    default kernel."""
     L = _lib()
     q, tok, off = _case(hash(shape) % 10_000, *shape)
     exp = o.maxsim_scores(q.float(), tok.float(), off)
@@ -92,8 +93,9 @@ def test_maxsim_scores_match_oracle(cuda_dev, shape, path):
 
 
 @pytest.mark.parametrize("shape", [(64, 32, 512, 9, 32), (33, 127, 129, 5, 32), (120, 1, 200, 21, 32), (300, 1, 40, 16, 20),
-                                   (3000, 16, 200, 40, 32), (1, 700, 700, 17, 32), (500, 1, 300, 2, 32), (77, 30, 34, 1, 32)])
-@pytest.mark.parametrize("path", ["tc", "tc_m64"])
+                                   (3000, 16, 200, 40, 32), (1, 700, 700, 17, 32), (500, 1, 300, 2, 32), (77, 30, 34, 1, 32),
+                                   (5000, 1, 70, 1, 32), (900, 100, 600, 1, 20), (3, 1, 2, 1, 32)])
+@pytest.mark.parametrize("path", ["tc", "tc_m64", "tc_dm"])
 def test_batched_and_m64_kernels_more_shapes(cuda_dev, shape, path):
     """Batched (MT=2) kernels — CTA pairs (cta_group::2, from two query groups up, with an odd last group on the
     single-CTA kernel) and single CTAs: 40 queries over many segments, 17 queries on one 6-tile document, short
@@ -703,8 +705,8 @@ def _boundary_corpus(nq, lq, seed=5):
     return q, tok, off, planted
 
 
-@pytest.mark.parametrize("nq,path", [(1, "tc"), (2, "tc"), (3, "tc"), (1, "tc_m64"), (2, "tc_m64"), (8, "tc"), (16, "tc"),
-                                     (24, "tc"), (2, "simt")])
+@pytest.mark.parametrize("nq,path", [(1, "tc"), (2, "tc"), (3, "tc"), (1, "tc_m64"), (2, "tc_m64"), (1, "tc_dm"), (8, "tc"),
+                                     (16, "tc"), (24, "tc"), (2, "simt")])
 def test_decisive_token_at_every_chunk_and_tile_boundary(cuda_dev, nq, path):
     L = _lib()
     q, tok, off, planted = _boundary_corpus(nq, 32)
@@ -732,7 +734,7 @@ def test_decisive_token_at_every_chunk_and_tile_boundary(cuda_dev, nq, path):
         _assert_scores(gotc, exp.flip(1), f"boundary candidates nq={nq}", bucket="boundary")
 
 
-@pytest.mark.parametrize("path", ["tc", "simt", "tc_m64"])
+@pytest.mark.parametrize("path", ["tc", "simt", "tc_m64", "tc_dm"])
 def test_maxsim_kernels_reproduce_the_reference_where_it_computes_maxsim(cuda_dev, golden_dir, path):
     """REFERENCE PIN for the MaxSim kernels: tests/golden/maxsim_pin.npz holds outputs of the UNMODIFIED reference
     `_maxsim_score` (local_rag_complete.py:821-829) on inputs where its mean-pool cosine equals MaxSim (identical
@@ -763,7 +765,7 @@ def test_maxsim_kernels_reproduce_the_reference_where_it_computes_maxsim(cuda_de
     assert ids[0, 0].item() == 0 and sc[0, 0].item() == 1.0                                # the query's own copy
 
 
-@pytest.mark.parametrize("path", ["tc", "simt", "tc_m64"])
+@pytest.mark.parametrize("path", ["tc", "simt", "tc_m64", "tc_dm"])
 def test_maxsim_kernels_match_float64_known_answers(cuda_dev, golden_dir, path):
     L = _lib()
     z = np.load(os.path.join(golden_dir, "maxsim_kat_f64.npz"))
@@ -935,6 +937,10 @@ def test_fused_topk_equals_score_matrix_topk(cuda_dev, nq, corpus):
         assert torch.equal(keys, ref), f"{corpus} nq={nq} k={k}"
         ri, rs = L.keys_unpack(ref)
         assert torch.equal(ids, ri) and torch.equal(sc, rs)
+    if nq == 1:                                                          # the doc-major kernel's fused top-k
+        dm_scores = L.maxsim_scores(tok_d, off_d, q_d, path=L.PATH_TC_DM)
+        for k, base in ((100, 0), (128, 7), (1, 3)):
+            assert torch.equal(L.search(tok_d, off_d, q_d, k, id_base=base, path=L.PATH_TC_DM)[0], L.topk(dm_scores, k, id_base=base))
     keys129 = L.search(tok_d, off_d, q_d, 129)[0]                       # k > 128: the staged route
     assert torch.equal(keys129, L.topk(scores, 129))
     if nq == 1:                                                          # oracle on the adversarial corpora
@@ -962,6 +968,9 @@ def test_fused_topk_with_empty_and_tiny_inputs(cuda_dev):
         scores = L.maxsim_scores(tok_d, off_d, q_d)
         for k in (40, 100, 128):
             assert torch.equal(L.search(tok_d, off_d, q_d, k)[0], L.topk(scores, k)), f"empty runs nq={nq} k={k}"
+            if nq == 1:
+                dm = L.maxsim_scores(tok_d, off_d, q_d, path=L.PATH_TC_DM)
+                assert torch.equal(L.search(tok_d, off_d, q_d, k, path=L.PATH_TC_DM)[0], L.topk(dm, k)), f"dm empty runs k={k}"
 
 
 @pytest.mark.parametrize("n_cand,lq,nq", [(50, 32, 1), (50, 32, 5), (1024, 32, 2), (1025, 32, 2), (7, 40, 3), (1, 32, 1), (300, 9, 4)])
@@ -1005,7 +1014,8 @@ def test_results_are_bitwise_repeatable(cuda_dev):
             res = [L.maxsim_scores(tok_d, off_d, q_d), L.maxsim_scores_ids(tok_d, off_d, cand, q_d)]
             res += list(L.rerank(tok_d, off_d, cand, q_d, 10)[:3])
             if lq <= 32:
-                res += [L.search(tok_d, off_d, q_d, 100)[0], L.maxsim_scores(tok_d, off_d, q_d, path=L.PATH_TC_M64)]
+                res += [L.search(tok_d, off_d, q_d, 100)[0], L.maxsim_scores(tok_d, off_d, q_d, path=L.PATH_TC_M64),
+                        L.maxsim_scores(tok_d, off_d, q_d, path=L.PATH_TC_DM), L.search(tok_d, off_d, q_d, 100, path=L.PATH_TC_DM)[0]]
             if first is None:
                 first = [r.clone() for r in res]
             else:

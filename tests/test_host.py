@@ -33,7 +33,8 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert _lib.maxsim_workspace_bytes(1000, 2, 32) == 0 and _lib.maxsim_workspace_bytes(1000, 2, 33) == 2 * 2 * 1000 * 4
     assert lib.hrc_last_error() == b""
     assert _lib.topk_workspace_bytes(1000, 4, 10) == 0
-    assert _lib.topk_workspace_bytes(1_000_000, 1, 100) > 123 * 100 * 8
+    assert _lib.topk_workspace_bytes(1_000_000, 1, 100) == 64 * 128 * 8 + 256      # streaming top-k: 64 lists of 128 keys
+    assert _lib.topk_workspace_bytes(1_000_000, 1, 1000) > 123 * 1000 * 8          # radix select (k > 128)
 
 
 def test_no_cpu_fallback():
