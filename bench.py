@@ -334,10 +334,12 @@ def run_ours(args):
         stream, one per step boundary; the scoring kernels inside are traced.  -> dict (ms are max over ranks)."""
         for i in range(warmup):
             fn(i)
-        barrier()
+        # everything that only one rank does (NVML init of the clock sampler: ~10 ms) happens BEFORE the barrier: a rank
+        # that enters the timed region late makes every other rank wait for it in its first all-gather
         sampler = ClockSampler(local_rank).start() if (sample_clocks and rank == 0) else None
         _lib.trace_enable(8 * steps + 8)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        barrier()
         launches0 = _lib.launch_count()
         t0 = time.perf_counter()
         ev[0].record()
