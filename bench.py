@@ -368,6 +368,10 @@ def run_ours(args):
     kernel_ms = head["kernel_ms_mean"]              # mean over the SAME timed steps (max over ranks)
 
     # ---- end to end through the public API with host buffers ----------------------------------------------------
+    # (one second of idle first: the headline loop has warmed the GPU towards its power cap, and the two loops should
+    #  start from the same state — the pause is outside every timed region)
+    barrier()
+    time.sleep(1.0)
     e2e = timed_loop(step_e2e, args.steps, args.warmup)
 
     secondary = {}

@@ -28,7 +28,7 @@ def main():
         cfg = hrc.RAGConfig(colbert_index_path=os.path.join(tmp, "colbert"), colbert_top_k=50, bm25_top_k=50,
                             rerank_candidates=20, final_top_k=5)
         indexer = hrc.DualIndexer(cfg)
-        indexer.build_colbert_index(corpus)                       # JinaColBERTRetriever.index -> packed bf16 store + index.pt
+        indexer.build_colbert_index(corpus)                       # JinaColBERTRetriever.index -> packed bf16 store + index.hrc.pt
         retriever = indexer.colbert_retriever
         print(f"store: {retriever.store.n_docs} documents, {retriever.store.total_tokens} tokens, "
               f"{retriever.store.nbytes() / 1e6:.2f} MB on {retriever.store.device}")

@@ -355,6 +355,9 @@ def hybrid_retrieve(tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.
     return ids, scores
 
 
+_RERANK_WS: dict = {}      # (n_cand, n_queries, lq, k) -> workspace bytes: the rerank is latency-bound, every ctypes call counts
+
+
 def rerank(tokens: torch.Tensor, offsets: torch.Tensor, cand_ids: torch.Tensor, queries: torch.Tensor, k: int, *,
            path: int = PATH_AUTO, workspace: Optional[Workspace] = None, want_cand_scores: bool = False):
     """Fused candidate MaxSim + sorted top-k in one C call.
@@ -366,7 +369,11 @@ def rerank(tokens: torch.Tensor, offsets: torch.Tensor, cand_ids: torch.Tensor, 
     n_docs = offsets.numel() - 1
     nq, lq = int(queries.shape[0]), int(queries.shape[1])
     n_cand = int(cand_ids.shape[1])
-    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, int(load().hrc_rerank_workspace_bytes(n_cand, nq, lq, k)))
+    shape = (n_cand, nq, lq, k)
+    need = _RERANK_WS.get(shape)
+    if need is None:
+        need = _RERANK_WS[shape] = int(load().hrc_rerank_workspace_bytes(n_cand, nq, lq, k))
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, need)
     cand_scores = torch.empty((nq, n_cand), dtype=torch.float32, device=dev) if want_cand_scores else None
     out = torch.empty((3, nq, k), dtype=torch.int32, device=dev)      # one allocation: pos | ids | scores (fp32 view)
     pos, ids, scores = out[0], out[1], out[2].view(torch.float32)

@@ -656,9 +656,10 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
 // not 128 consecutive tokens but 4 x 32: the CTA's segment is cut into FOUR token streams of whole documents, one per
 // epilogue warp / TMEM lane quadrant, and tile t holds tokens [32t, 32t + 32) of each stream (4 TMA boxes of 32 rows).
 // A warp therefore sees ITS stream chunk by chunk on its own 32 lanes — lane i = token 32t + i of the stream, register
-// j = query token j — and reduces a document's piece with a 5-level max butterfly (31 shuffles) that leaves lane j
-// holding max_t <q_j, d_t>; the running maximum stays in that lane across chunks, and a finished document is one
-// warp_sum.  No cross-warp combine, no atomics, documents never split between warps.
+// j = query token j — and reduces a document's piece with ONE warp-wide max instruction per query token
+// (redux.sync.max.f32, sm_100a); the 32 running maxima max_t <q_j, d_t> live replicated in every lane across chunks, and
+// a finished document is 31 adds in the order of the query-major kernels' butterfly (bit-identical scores).  No
+// cross-warp combine, no atomics, documents never split between warps.
 // =====================================================================================================================
 constexpr int kDmQBytes = 32 * HRC_DIM * 2;         // the query as the B operand: 32 rows, 8 KB
 constexpr int kDmTileBytes = 128 * HRC_DIM * 2;      // 4 streams x 32 tokens, 32 KB
@@ -666,24 +667,25 @@ constexpr int kDmStages = 5;
 constexpr int kDmAcc = 16;                          // accumulator stages: 512 TMEM columns / 32
 constexpr int kDmThreads = 6 * 32;                  // TMA warp, MMA warp, 4 epilogue warps
 
-// one level of the max reduce-scatter: N live values per lane -> N/2, exchanging with lane ^ OFF
-template <int N, int OFF>
-__device__ __forceinline__ void max_halve(float (&a)[32], bool upper) {
-#pragma unroll
-  for (int i = 0; i < N / 2; ++i) {
-    const float keep = upper ? a[i + N / 2] : a[i];
-    const float send = upper ? a[i] : a[i + N / 2];
-    a[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, OFF));
-  }
+// max over the 32 lanes of v, returned to every lane: ONE instruction on sm_100a (CREDUX.MAX.F32, result in a uniform
+// register).  scripts/micro/redux_bench.cu: 32 of these + 32 FMNMX take 174 cycles per 32 x 32 block and warp, the 5-level
+// shuffle reduce-scatter (31 SHFL + 62 SEL + 31 FMNMX) 346.
+__device__ __forceinline__ float lanes_max(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
 }
-// lane j <- max over the 32 lanes of a[j]   (a is destroyed)
-__device__ __forceinline__ float lanes_max_transpose(float (&a)[32], int lane) {
-  max_halve<32, 16>(a, (lane & 16) != 0);
-  max_halve<16, 8>(a, (lane & 8) != 0);
-  max_halve<8, 4>(a, (lane & 4) != 0);
-  max_halve<4, 2>(a, (lane & 2) != 0);
-  max_halve<2, 1>(a, (lane & 1) != 0);
-  return a[0];
+// x[0] + ... + x[31] in exactly the association order of warp_sum's xor butterfly over 32 lanes (16, 8, 4, 2, 1), so that
+// a score summed in one thread is bit-identical to the query-major kernels' score summed across lanes
+__device__ __forceinline__ float sum32_butterfly_order(const float (&x)[32]) {
+  float a[16], b[8], c[4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = x[i] + x[i + 16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = a[i] + a[i + 8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = b[i] + b[i + 4];
+  return (c[0] + c[2]) + (c[1] + c[3]);
 }
 
 template <bool TK>
@@ -841,7 +843,9 @@ maxsim_dm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     bool have_doc = q_active && n_docs_seg > 0;
     int s_tok = 0, e_tok = 0;
     if (have_doc) e_tok = end_of(0);
-    float m = -INFINITY;                    // lane j: running max_t <q_j, d_t> of the current document
+    float mr[32];                           // mr[j]: running max_t <q_j, d_t> of the current document, in every lane
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mr[j] = -INFINITY;
 
     // fused top-k state (see the query-major kernel)
     uint64_t* lst = lists + size_t(quad) * kListCap;
@@ -853,7 +857,7 @@ maxsim_dm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
       __syncwarp();
     }
     auto finish_doc = [&]() {
-      const float sc = warp_sum(m);
+      const float sc = sum32_butterfly_order(mr);
       const int64_t col = doc_begin + my;
       if (lane == 0 && (!TK || p.scores != nullptr)) p.scores[out_row + col] = sc;
       if constexpr (TK) {
@@ -870,7 +874,8 @@ maxsim_dm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
           }
         }
       }
-      m = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mr[j] = -INFINITY;
       ++my;
       have_doc = my < n_docs_seg;
       s_tok = e_tok;
@@ -891,17 +896,13 @@ maxsim_dm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
         const int c0 = t * 32, c1 = c0 + 32;
         while (have_doc && s_tok < c1) {
           const int lo = max(s_tok, c0), hi = min(e_tok, c1);     // this document's tokens inside this chunk: lanes [lo-c0, hi-c0)
-          if (hi > lo) {
-            float w[32];
-            if (hi - lo == 32) {
+          if (hi - lo == 32) {                  // the chunk lies inside the document
 #pragma unroll
-              for (int j = 0; j < 32; ++j) w[j] = __uint_as_float(v[j]);
-            } else {
-              const bool mine = lane >= lo - c0 && lane < hi - c0;
+            for (int j = 0; j < 32; ++j) mr[j] = fmaxf(mr[j], lanes_max(__uint_as_float(v[j])));
+          } else if (hi > lo) {                 // a boundary inside the chunk: the other documents' lanes read as -inf
+            const bool mine = lane >= lo - c0 && lane < hi - c0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) w[j] = mine ? __uint_as_float(v[j]) : -INFINITY;
-            }
-            m = fmaxf(m, lanes_max_transpose(w, lane));
+            for (int j = 0; j < 32; ++j) mr[j] = fmaxf(mr[j], lanes_max(mine ? __uint_as_float(v[j]) : -INFINITY));
           }
           if (e_tok > c1) break;              // the document continues in the next chunk
           finish_doc();

@@ -182,10 +182,12 @@ select_scores_kernel(const float* __restrict__ scores, const int32_t* __restrict
 }
 
 // ids_out / scores_out (optional, final level only): the unpacked result, so that no separate unpack launch is needed.
-// list_len > 0 (final level only): the input is a concatenation of lists of list_len keys, each SORTED best first (what
-// the fused MaxSim epilogue and the streaming top-k hand over).  The k-th key of any one list is a lower bound of the
-// global k-th key, so T = max over the lists of their k-th key cuts the candidates to a few hundred: gather the keys
-// >= T, sort them outright.  (If more than kSmallMerge pass — adversarial ties — fall through to the radix select.)
+// list_len > 0 (final level only): the input is a concatenation of n_lists lists of list_len keys, each SORTED best
+// first (what the fused MaxSim epilogue and the streaming top-k hand over).  Let j = ceil(k / n_lists) - 1 and
+// m = ceil(k / (j + 1)): the m-th largest of the lists' j-th keys, T, has at least m * (j + 1) >= k keys at or above it
+// (j + 1 in each of m lists), so it is a lower bound of the global k-th key — and a tight one: for 148 lists and
+// k = 100 it is the 100th best list HEAD, which leaves a few hundred of the 18,944 candidates.  Gather the keys >= T,
+// sort them outright.  (If more than kSmallMerge pass — adversarial ties — fall through to the radix select.)
 __global__ void __launch_bounds__(kSelThreads)
 select_keys_kernel(const uint64_t* __restrict__ keys_in, int n_in, int k, uint64_t* __restrict__ out,
                    int n_groups, int group_len, int final_sorted, int32_t* __restrict__ ids_out,
@@ -200,14 +202,33 @@ select_keys_kernel(const uint64_t* __restrict__ keys_in, int n_in, int k, uint64
   const int begin = group * group_len;
   const int gn = min(group_len, n_in - begin);
   const uint64_t* src = keys_in + row * n_in + begin;
+  if (final_sorted && n_groups == 1 && gn <= kSmallMerge) {      // few keys: sort them outright
+    const int n_pad = next_pow2(gn < k ? k : gn);
+    for (int i = threadIdx.x; i < n_pad; i += kSelThreads) keys[i] = i < gn ? src[i] : 0;
+    bitonic_sort_desc(keys, n_pad);
+    for (int i = threadIdx.x; i < k; i += kSelThreads) {
+      const uint64_t key = keys[i];
+      out[row * k + i] = key;
+      if (ids_out) ids_out[row * k + i] = key ? key_id(key) : -1;
+      if (scores_out) scores_out[row * k + i] = key ? key_score(key) : -INFINITY;
+    }
+    return;
+  }
   if (list_len > 0 && final_sorted && n_groups == 1 && k <= list_len && gn > kSmallMerge) {
     __shared__ unsigned long long s_thr;
+    const int n_lists = (gn + list_len - 1) / list_len;          // <= kMergeMax / 128 = 192 < kSelThreads
+    const int j = (k + n_lists - 1) / n_lists - 1;
+    const int m = (k + j) / (j + 1);
+    uint64_t* heads = reinterpret_cast<uint64_t*>(sc.hist);       // 192 x 8 B of the 8 KB histogram
     if (threadIdx.x == 0) { s_thr = 0; sc.count = 0; }
+    if (int(threadIdx.x) < n_lists) heads[threadIdx.x] = (threadIdx.x * list_len + j < unsigned(gn)) ? src[threadIdx.x * list_len + j] : 0;
     __syncthreads();
-    unsigned long long t = 0;
-    for (int l = threadIdx.x; l * list_len < gn; l += kSelThreads) t = max(t, (unsigned long long)src[l * list_len + k - 1]);
-    for (int o = 16; o > 0; o >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, o));
-    if ((threadIdx.x & 31) == 0 && t != 0) atomicMax(&s_thr, t);
+    if (int(threadIdx.x) < n_lists) {
+      const uint64_t mine = heads[threadIdx.x];
+      int rank = 0;
+      for (int l = 0; l < n_lists; ++l) rank += (heads[l] > mine || (heads[l] == mine && l < int(threadIdx.x))) ? 1 : 0;
+      if (rank == m - 1) s_thr = mine;
+    }
     __syncthreads();
     const uint64_t thr = s_thr;
     if (thr != 0) {
@@ -480,7 +501,12 @@ int run_key_levels(const uint64_t* d_in, int64_t n_in, int n_rows, int k, uint64
     const int n_groups = int((cur_n + group_len - 1) / group_len);
     uint64_t* dst = last ? d_out : (flip ? tmp1 : tmp0);
     HRC_REQUIRE(dst != nullptr, "top-k: %lld candidate keys per row need workspace", (long long)cur_n);
-    const size_t smem = size_t(group_len) * 8 + (last ? sort_buf_bytes(k) : 0);
+    size_t smem = size_t(group_len) * 8 + (last ? sort_buf_bytes(k) : 0);
+    if (last && group_len <= kSmallMerge) {                  // the direct-sort path pads the keys to a power of two
+      size_t n_pad = 1;
+      while (n_pad < size_t(group_len) || n_pad < size_t(k)) n_pad <<= 1;
+      if (n_pad * 8 > smem) smem = n_pad * 8;
+    }
     select_keys_kernel<<<dim3(n_groups, n_rows), kSelThreads, smem, stream>>>(
         cur, int(cur_n), k, dst, n_groups, group_len, last ? 1 : 0, last ? d_ids_out : nullptr,
         last ? d_scores_out : nullptr, (last && cur == d_in) ? list_len : 0);

@@ -1,18 +1,20 @@
 #!/usr/bin/env python
 """Counts of the SASS mnemonics that prove TMA / tcgen05 / TMEM use, per kernel of maxsim_tc.cu.
-    cuobjdump -sass hybrid-rag-colbertv2_b200/csrc/build/maxsim_tc.o | python scripts/sass_mnemonics.py > profiles/r01_sass_mnemonics.txt"""
+    cuobjdump -sass hybrid-rag-colbertv2_b200/csrc/build/maxsim_tc.o | python scripts/sass_mnemonics.py > profiles/r02_sass_mnemonics.txt"""
 import collections
 import re
 import sys
 
-KEYS = ['UTMALDG', 'UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'UTCATOMSWS', 'SYNCS', 'UCGABAR', 'FMNMX3', 'FMNMX', 'FSEL', 'SHFL', 'STG',
-        'LDG', 'ATOMG', 'RED']
+KEYS = ['UTMALDG', 'UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'UTCATOMSWS', 'SYNCS', 'UCGABAR', 'FMNMX3', 'FMNMX', 'FSEL', 'SHFL', 'CREDUX',
+        'STG', 'LDG', 'ATOMG', 'RED', 'VOTE', 'BAR']
 cur, counts = None, collections.OrderedDict()
 for line in sys.stdin:
     m = re.search(r'Function : (\S+)', line)
     if m:
-        t = re.search(r'maxsim_tc_kernelILi(\d)ELi(\d+)ELb(\d)ELi(\d)ELi(\d)ELi(\d)E', m.group(1))
-        cur = ('maxsim_tc_kernel<MT=%s,TN=%s,TS=%s,ZP=%s,CG=%s,EPI=%s>' % t.groups()) if t else m.group(1)[:60]
+        t = re.search(r'maxsim_tc_kernelILi(\d)ELi(\d)ELi(\d)ELb(\d)E', m.group(1))
+        u = re.search(r'maxsim_dm_kernelILb(\d)E', m.group(1))
+        cur = (('maxsim_tc_kernel<MT=%s,ZP=%s,CG=%s,TK=%s>' % t.groups()) if t else
+               (('maxsim_dm_kernel<TK=%s>' % u.groups()) if u else m.group(1)[:60]))
         counts[cur] = collections.Counter()
         continue
     if cur is None:
