@@ -163,7 +163,7 @@ __device__ __forceinline__ float max32_masked_acc(const uint32_t (&v)[32], uint3
   return max32_acc(t, m);
 }
 
-template <int MT, int ZP, int CG, bool TK>
+template <int MT, int ZP, int CG, bool TK, bool RR>
 __global__ void __launch_bounds__(cta_threads(MT, ZP), 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_q,
                  const TcParams p) {
@@ -182,6 +182,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   static_assert((MT == 1 && (ZP == 1 || ZP == 2) && CG == 1) || (MT == 2 && ZP == 0 && (CG == 1 || CG == 2)),
                 "instantiations: <1,1,1> <1,2,1> <2,0,1> <2,0,2>");
   static_assert(!TK || (MT == 1 && ZP == 1), "fused top-k: the single-query kernel only (see tc_topk_supported)");
+  static_assert(!RR || (MT == 1 && ZP == 1 && !TK), "fused rerank: the candidate-mode instantiation only");
   // A tile's accumulators (all M-tiles) are ONE unit: one tfull / tempty pair per stage.  The warps of a lane group
   // alternate DOCUMENTS and each reads all M-tiles of a tile in one walk.
   // HBM-bound kernels (MT == 1): ONE tcgen05.commit per tile (tfull); the shared-memory slot is released by the
@@ -471,9 +472,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
         if (lane == 0 && active[0]) {
           if constexpr (ZP == 2) atomicAdd(&p.scores[out_row[0] + pend_col], sc);   // the other token half adds its part
           else if (!TK || p.scores != nullptr) p.scores[out_row[0] + pend_col] = sc;
-          if constexpr (ZP == 1 && !TK) {
-            if (p.rr_counter != nullptr) __threadfence();   // fused rerank: the score must be visible to the last CTA
-          }
+          if constexpr (RR) __threadfence();                // fused rerank: the score must be visible to the last CTA
         }
       }
       if constexpr (TK) {
@@ -604,12 +603,12 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     if (warp == 1) tmem_dealloc(acc_base, kTmemCols);
   }
 
-  if constexpr (MT == 1 && ZP == 1 && !TK) {
+  if constexpr (RR) {
     // Fused rerank (candidate mode): every CTA scored ONE candidate; the last CTA of a query to get here ranks the
     // query's n_items scores (rank by counting over 64-bit (score, position) keys: n_items <= 1024) and writes the
     // sorted top rr_k — what torch.argsort(descending)[:k] does at local_rag_complete.py:789-792 — so that a rerank
     // is ONE launch.  The tile ring is idle by now and holds the keys.
-    if (p.rr_counter != nullptr) {
+    {
       volatile int* s_last = reinterpret_cast<volatile int*>(bars + 40);   // (no static shared memory: the dynamic
                                                                             //  allocation already takes the whole 227 KB)
       const int q = q_base;                               // candidate mode: one (virtual = real) query per blockIdx.y
@@ -1029,7 +1028,7 @@ int g_debug = 0;                                  // hrc_exp_set_debug: 1 no epi
 int g_stages = 0;                                 // hrc_exp_set_stages: cap of the shared-memory ring depth (0 = default)
 #endif
 
-template <int MT, int ZP, int CG, bool TK = false>
+template <int MT, int ZP, int CG, bool TK = false, bool RR = false>
 int launch_cfg(const void* d_tokens, const void* d_queries, int lq, int n_real_queries, TcParams p, dim3 grid,
                cudaStream_t stream) {
   constexpr int kTileBytes = (TN / CG) * HRC_DIM * 2;   // what ONE CTA stages per tile
@@ -1053,7 +1052,7 @@ int launch_cfg(const void* d_tokens, const void* d_queries, int lq, int n_real_q
   static PerDeviceOnce once;
   int dev;
   if (once.pending(&dev)) {
-    HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT, ZP, CG, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HRC_CHECK_CUDA(cudaFuncSetAttribute(maxsim_tc_kernel<MT, ZP, CG, TK, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kMaxSmem));
     once.mark(dev);
   }
@@ -1073,9 +1072,9 @@ int launch_cfg(const void* d_tokens, const void* d_queries, int lq, int n_real_q
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    HRC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, maxsim_tc_kernel<MT, ZP, CG, TK>, tmap_d, tmap_q, p));
+    HRC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, maxsim_tc_kernel<MT, ZP, CG, TK, RR>, tmap_d, tmap_q, p));
   } else {
-    maxsim_tc_kernel<MT, ZP, CG, TK><<<grid, cta_threads(MT, ZP), smem_bytes, stream>>>(tmap_d, tmap_q, p);
+    maxsim_tc_kernel<MT, ZP, CG, TK, RR><<<grid, cta_threads(MT, ZP), smem_bytes, stream>>>(tmap_d, tmap_q, p);
   }
   trace_end(stream);
   count_launch();
@@ -1177,8 +1176,9 @@ int launch_tc_slots(const void* d_tokens, const int64_t* d_offsets, int64_t n_do
 
   if (d_cand_ids != nullptr) {
     HRC_REQUIRE(n_queries <= 65535, "tc path: too many queries for a candidate launch (%d)", n_queries);
-    return launch_cfg<1, 1, 1>(d_tokens, d_queries, lq, n_real_queries, p, dim3((unsigned)n_items, (unsigned)n_queries),
-                               stream);
+    const dim3 cgrid((unsigned)n_items, (unsigned)n_queries);
+    return rr ? launch_cfg<1, 1, 1, false, true>(d_tokens, d_queries, lq, n_real_queries, p, cgrid, stream)
+              : launch_cfg<1, 1, 1>(d_tokens, d_queries, lq, n_real_queries, p, cgrid, stream);
   }
   const int64_t tiles = (total_tokens + TN - 1) / TN;
   p.n_segments = int(tiles < sm_count() ? tiles : sm_count());

@@ -42,6 +42,18 @@ def all_gather_keys(keys: torch.Tensor, k: int, group=None) -> torch.Tensor:
     return out.permute(1, 0, 2).reshape(bq, world * k).contiguous()
 
 
+class PendingKeys:
+    """The result of ShardedSearcher.search_keys_async: merged keys that become valid on the exchange stream."""
+
+    def __init__(self, keys: torch.Tensor, done: torch.cuda.Event):
+        self._keys, self._done = keys, done
+
+    def result(self) -> torch.Tensor:
+        """The merged keys, ordered after the exchange on the CURRENT stream (no host synchronisation)."""
+        torch.cuda.current_stream(self._keys.device).wait_event(self._done)
+        return self._keys
+
+
 class ShardedSearcher:
     """search / hybrid retrieve over a corpus sharded across the ranks of a torch.distributed group (one rank per GPU)."""
 
@@ -56,6 +68,8 @@ class ShardedSearcher:
         self._host: Optional[_lib.ShardedHostSearch] = None
         self._pinned = None
         self._n_global: Optional[int] = None
+        self._side: Optional[torch.cuda.Stream] = None       # exchange stream of search_keys_async
+        self._side_ws = _lib.Workspace()
         if transport != "torch":
             self.comm = _lib.Comm(retriever.device, group, p2p_max_keys=p2p_max_keys if transport == "p2p" else 0)
             self._host = _lib.ShardedHostSearch(self.comm)
@@ -88,6 +102,40 @@ class ShardedSearcher:
         s = r.store
         return _lib.sharded_search(self.comm, s.tokens, s.offsets, q, int(k), id_base=s.doc_id_base, path=self._path(),
                                    transport=_TRANSPORTS[self.transport], workspace=self._ws, unpack=False)[0]
+
+    def search_keys_async(self, query_embeddings: torch.Tensor, k: int) -> PendingKeys:
+        """Pipelined form of search_keys for a stream of independent queries: the local MaxSim + top-k runs on the
+        current stream, the exchange + merge on a dedicated stream, so the next query's scan of the shard does not wait
+        for this query's collective (nor for the slowest rank of this step).  Every rank must issue the same sequence of
+        calls.  `.result()` orders the merged keys after the exchange on the current stream."""
+        if self.transport == "torch":
+            raise ValueError("search_keys_async needs a library transport ('nccl' or 'p2p')")
+        r = self.retriever
+        dev = r.device
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        q = r._prep_queries(query_embeddings)
+        s = r.store
+        k_local = min(int(k), s.n_docs)
+        local = torch.zeros((q.shape[0], int(k)), dtype=torch.int64, device=dev) if k_local < k else None
+        if k_local > 0:
+            got = _lib.search(s.tokens, s.offsets, q, k_local, id_base=s.doc_id_base, path=self._path(),
+                              workspace=self._ws, unpack=False)[0]
+            if local is None:
+                local = got
+            else:
+                local[:, :k_local] = got
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        local.record_stream(self._side)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ready)
+            merged = _lib.allgather_merge_topk(self.comm, local, int(k), transport=_TRANSPORTS[self.transport],
+                                               workspace=self._side_ws)[0]
+            done = torch.cuda.Event()
+            done.record(self._side)
+        merged.record_stream(torch.cuda.current_stream(dev))
+        return PendingKeys(merged, done)
 
     def search_embeddings(self, query_embeddings: torch.Tensor, k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
         r = self.retriever

@@ -84,6 +84,10 @@ def main():
             qq = q[step % 19: step % 19 + 1]
             same = same and torch.equal(s.search_keys(qq, 100), one.search_keys(qq, 100))
         check(same, f"[{transport}] 40 back-to-back steps")
+        if transport != "torch":                                # pipelined form: exchange on a side stream
+            pend = [s.search_keys_async(q[i % 19: i % 19 + 1], 100) for i in range(30)]
+            same = all(torch.equal(p.result(), one.search_keys(q[i % 19: i % 19 + 1], 100)) for i, p in enumerate(pend))
+            check(same, f"[{transport}] 30 pipelined steps (search_keys_async)")
         a_ids, a_sc = s.retrieve_batch(q, bm25)
         check(torch.equal(a_ids, hy_ids) and torch.equal(a_sc, hy_sc), f"[{transport}] sharded hybrid retrieve, 19 queries")
         b_ids, b_sc = s.retrieve_batch(q[:1], bm25[:1])

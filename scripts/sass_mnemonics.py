@@ -11,9 +11,9 @@ cur, counts = None, collections.OrderedDict()
 for line in sys.stdin:
     m = re.search(r'Function : (\S+)', line)
     if m:
-        t = re.search(r'maxsim_tc_kernelILi(\d)ELi(\d)ELi(\d)ELb(\d)E', m.group(1))
+        t = re.search(r'maxsim_tc_kernelILi(\d)ELi(\d)ELi(\d)ELb(\d)ELb(\d)E', m.group(1))
         u = re.search(r'maxsim_dm_kernelILb(\d)E', m.group(1))
-        cur = (('maxsim_tc_kernel<MT=%s,ZP=%s,CG=%s,TK=%s>' % t.groups()) if t else
+        cur = (('maxsim_tc_kernel<MT=%s,ZP=%s,CG=%s,TK=%s,RR=%s>' % t.groups()) if t else
                (('maxsim_dm_kernel<TK=%s>' % u.groups()) if u else m.group(1)[:60]))
         counts[cur] = collections.Counter()
         continue

@@ -94,7 +94,8 @@ def test_maxsim_scores_match_oracle(cuda_dev, shape, path):
 
 @pytest.mark.parametrize("shape", [(64, 32, 512, 9, 32), (33, 127, 129, 5, 32), (120, 1, 200, 21, 32), (300, 1, 40, 16, 20),
                                    (3000, 16, 200, 40, 32), (1, 700, 700, 17, 32), (500, 1, 300, 2, 32), (77, 30, 34, 1, 32),
-                                   (5000, 1, 70, 1, 32), (900, 100, 600, 1, 20), (3, 1, 2, 1, 32)])
+                                   (5000, 1, 70, 1, 32), (900, 100, 600, 1, 20), (3, 1, 2, 1, 32), (4, 3000, 9000, 1, 32),
+                                   (2, 40_000, 60_000, 1, 7)])
 @pytest.mark.parametrize("path", ["tc", "tc_m64", "tc_dm"])
 def test_batched_and_m64_kernels_more_shapes(cuda_dev, shape, path):
     """Batched (MT=2) kernels — CTA pairs (cta_group::2, from two query groups up, with an odd last group on the
