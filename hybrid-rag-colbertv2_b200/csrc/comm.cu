@@ -12,7 +12,15 @@
 //         no collective launch, no host involvement.  Receive slots are double-buffered by sequence parity: a rank
 //         can be at most one step ahead of a peer, because its own merge needs that peer's keys of the same step.
 #include <dlfcn.h>
-#include <nccl.h>
+
+// The handful of NCCL declarations this file needs, restated from nccl.h (stable since NCCL 2.0) so that neither
+// building nor loading libhrc.so depends on an NCCL installation: the library is dlopen'ed in hrc_comm_init.
+extern "C" {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclInt8 = 0, ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5 } ncclDataType_t;
+}
 
 #include <cstring>
 

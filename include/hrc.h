@@ -88,8 +88,10 @@ void hrc_store_release(const void* d_tokens);
  * Replaces: JinaColBERTRetriever._maxsim_score, local_rag_complete.py:802-831 (as its docstring
  * :807-812 and BASELINE.json's north_star define it), called from search :764.
  *   d_queries : bf16 [n_queries][lq][128]
- *   path      : HRC_PATH_*; AUTO picks TC when lq <= HRC_TC_MAX_LQ * HRC_TC_MAX_SLOTS (a query longer than 32
- *               tokens is scored as ceil(lq / 32) slots whose partial scores are summed in slot order).
+ *   path      : HRC_PATH_*; AUTO picks the tensor cores when lq <= HRC_TC_MAX_LQ * HRC_TC_MAX_SLOTS — the doc-major
+ *               kernel for ONE query of <= 32 tokens, the query-major kernels otherwise (a query longer than 32 tokens
+ *               is scored as ceil(lq / 32) slots whose partial scores are summed in slot order) — and the CUDA cores
+ *               beyond.  All tensor-core organisations return bit-identical scores.
  *   d_workspace : hrc_maxsim_workspace_bytes(n_docs, n_queries, lq) bytes of scratch (0 bytes, and NULL allowed, when
  *               lq <= 32): the per-slot partial scores of long queries.  No call allocates device memory.
  * An empty document (length 0) scores -inf.
