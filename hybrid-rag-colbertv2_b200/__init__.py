@@ -4,7 +4,7 @@ JinaColBERTRetriever / DualIndexer / HybridRetriever API of techmum21p/hybrid-ra
 Import as `hybrid_rag_colbertv2_b200` (the repo-root shim makes the hyphenated directory importable).
 """
 from . import _lib
-from ._lib import HrcError, PATH_AUTO, PATH_SIMT, PATH_TC, PATH_TC_DM, PATH_TC_M64
+from ._lib import HrcError, PATH_AUTO, PATH_SIMT, PATH_TC, PATH_TC_DM
 from .chunks import ChunkIdMap, SqliteChunkFetcher
 from .encoder import ColBERTEncoder, SyntheticEncoder
 from .retriever import DualIndexer, HybridRetriever, JinaColBERTRetriever, RAGConfig, install
@@ -14,6 +14,6 @@ from .store import PackedStore, lengths_to_offsets, shard_doc_ranges
 __all__ = [
     "DualIndexer", "HybridRetriever", "JinaColBERTRetriever", "RAGConfig", "PackedStore", "SyntheticEncoder", "ColBERTEncoder", "ChunkIdMap", "SqliteChunkFetcher",
     "ShardedSearcher", "all_gather_keys", "lengths_to_offsets", "shard_doc_ranges", "HrcError",
-    "PATH_AUTO", "PATH_SIMT", "PATH_TC", "PATH_TC_M64", "PATH_TC_DM", "install",
+    "PATH_AUTO", "PATH_SIMT", "PATH_TC", "PATH_TC_DM", "install",
 ]
 __version__ = "0.2.0"

@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HRC_LIB_PATH") or os.path.join(_HERE, "libhrc.so")   # override: A/B of library builds
 
-PATH_AUTO, PATH_SIMT, PATH_TC, PATH_TC_M64, PATH_TC_DM = 0, 1, 2, 3, 4
+PATH_AUTO, PATH_SIMT, PATH_TC, PATH_TC_DM = 0, 1, 2, 3
 DIM = 128
 MAX_TOPK = 2048
 TC_MAX_LQ = 32          # query tokens per slot on the tensor-core path; up to 8 slots (lq <= 256)

@@ -99,10 +99,8 @@ static int check_device() {
   return 0;
 }
 
-// kernel organisation for one query (maxsim_tc.cu: 0 query-major, 1 M=64, 2 doc-major, 3 auto)
-static int tc_variant(int path) {
-  return path == HRC_PATH_TC_M64 ? 1 : (path == HRC_PATH_TC_DM ? 2 : (path == HRC_PATH_AUTO ? 3 : 0));
-}
+// kernel organisation for one query (maxsim_tc.cu: 0 query-major, 2 doc-major, 3 auto)
+static int tc_variant(int path) { return path == HRC_PATH_TC_DM ? 2 : (path == HRC_PATH_AUTO ? 3 : 0); }
 
 // bytes of caller workspace one scoring call needs (only queries longer than 32 tokens on the tensor-core path)
 static size_t maxsim_ws_bytes(int64_t n_items, int n_queries, int lq, int path) {
@@ -123,7 +121,7 @@ static int maxsim_dispatch(const void* d_tokens, const int64_t* d_offsets, int64
   // rerank, because the SIMT kernel is FMA-bound and both pay the same launch latency.
   int variant = tc_variant(path);
   if (path == HRC_PATH_AUTO) path = (lq <= HRC_TC_MAX_LQ * HRC_TC_MAX_SLOTS && total_tokens > 0) ? HRC_PATH_TC : HRC_PATH_SIMT;
-  if (path == HRC_PATH_TC || path == HRC_PATH_TC_M64 || path == HRC_PATH_TC_DM)
+  if (path == HRC_PATH_TC || path == HRC_PATH_TC_DM)
     return launch_maxsim_tc(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_items, d_queries, n_queries, lq,
                             d_scores, variant, d_workspace, workspace_bytes, stream);
   HRC_REQUIRE(path == HRC_PATH_SIMT, "maxsim: unknown path %d", path);

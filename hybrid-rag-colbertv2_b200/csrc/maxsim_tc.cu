@@ -26,7 +26,6 @@
 //   <1,ZP=1>       HBM-bound (<= 4 queries) and candidate (rerank) mode: the unused rows of the A tile are
 //                  zero, the 4 epilogue warps are stacked on the used lane groups, 6-stage smem ring,
 //                  4 accumulator stages, one tcgen05.commit per tile.                   [default]
-//   <1,ZP=2>       M=64 MMA for <= 2 queries (explicit path HRC_PATH_TC_M64)
 //   <2,ZP=0,CG=2>  tensor-bound, batched: CTA PAIR (cta_group::2, cluster of 2), one M=256 MMA per K slice,
 //                  each CTA stages half of every document tile; 8 epilogue warps per CTA (two per lane
 //                  group, alternating documents), 2 x 2 accumulators.                   [default from 9 queries]
@@ -68,19 +67,18 @@ constexpr int kListOut = kKeyListOut;             // keys per (query, segment) h
 #define HRC_DBG(p, bit) false
 #endif
 
-__host__ __device__ constexpr int epi_warps(int mt, int zp) { return (mt == 2 || zp == 2) ? 8 : 4; }
+__host__ __device__ constexpr int epi_warps(int mt) { return mt == 2 ? 8 : 4; }
 // ZP ("zero padded") variants for <= 4 queries: with slots_used = 1, 2 or 4 queries the other rows of the A tile
 // stay ZERO (measured: replicating the query instead costs ~10 % under sustained load, because the extra
 // tensor-core switching power pushes the GPU into its 1 kW cap), and the 4 epilogue warps are stacked on the
 // USED TMEM lane groups: a warp can only read lanes 32*(warp%4).., so with one query they are warps 4, 8, 12, 16
 // (all on lane group 0, splitting the documents 4 ways), with two queries warps 4, 5, 8, 9, with four 4..7.
 // The warps in between have no role and exit.
-// ZP == 2 additionally uses an M=64 MMA for <= 2 queries (half the tensor work and A-operand traffic).  Its
-// accumulator layout puts rows 0-15 / 16-31 / 32-47 / 48-63 in lanes 0-15 of lane groups 0 / 1 / 2 / 3, so a
-// query's tokens 0-15 and 16-31 are summed by two different warps, which each atomicAdd their half into the
-// (zero-initialised) score: two commutative additions, hence still deterministic.  8 epilogue warps.
+// (An M=64 variant — half the tensor work, a query's token halves in two lane groups combined with atomicAdd — was
+// measured between the two at the power cap, C2 4.51-4.99 ms against 4.41-4.89 for the doc-major kernel, and removed:
+// profiles/experiments/r02_removed_m64_variant.diff.)
 __host__ __device__ constexpr int cta_threads(int mt, int zp) {
-  return zp == 2 ? 18 * 32 : (zp == 1 ? 17 * 32 : (2 + epi_warps(mt, zp)) * 32);
+  return zp == 1 ? 17 * 32 : (2 + epi_warps(mt)) * 32;
 }
 
 struct TcParams {
@@ -167,8 +165,8 @@ template <int MT, int ZP, int CG, bool TK, bool RR>
 __global__ void __launch_bounds__(cta_threads(MT, ZP), 1)
 maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_q,
                  const TcParams p) {
-  constexpr int kEpiWarps = epi_warps(MT, ZP);
-  constexpr int kM = ZP == 2 ? 64 : 128;               // MMA M (rows of the A tile)
+  constexpr int kEpiWarps = epi_warps(MT);
+  constexpr int kM = 128;                              // MMA M (rows of the A tile)
   constexpr int kQBytes = kM * HRC_DIM * 2;            // one A tile in shared memory
   constexpr int kSplit = kEpiWarps / 4;                 // warps sharing one TMEM lane group split the documents
   // CG == 2 (CTA pair, cta_group::2): the pair issues one M=256 MMA per K slice; this CTA stages TN/2 tokens
@@ -179,8 +177,8 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   constexpr int kTileStages = kTmemCols / (MT * TN);    // tiles in flight between MMA and epilogue (4 or 2)
   constexpr uint32_t kIdesc = make_idesc_bf16_f32(kM * CG, TN);
   static_assert(kTileBytes % 2048 == 0, "tile slabs must stay 1024-byte aligned for the 128B swizzle");
-  static_assert((MT == 1 && (ZP == 1 || ZP == 2) && CG == 1) || (MT == 2 && ZP == 0 && (CG == 1 || CG == 2)),
-                "instantiations: <1,1,1> <1,2,1> <2,0,1> <2,0,2>");
+  static_assert((MT == 1 && ZP == 1 && CG == 1) || (MT == 2 && ZP == 0 && (CG == 1 || CG == 2)),
+                "instantiations: <1,1,1> <2,0,1> <2,0,2>");
   static_assert(!TK || (MT == 1 && ZP == 1), "fused top-k: the single-query kernel only (see tc_topk_supported)");
   static_assert(!RR || (MT == 1 && ZP == 1 && !TK), "fused rerank: the candidate-mode instantiation only");
   // A tile's accumulators (all M-tiles) are ONE unit: one tfull / tempty pair per stage.  The warps of a lane group
@@ -352,7 +350,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
         if (++ts == kTileStages) { ts = 0; tphase ^= 1; }
       }
     }
-  } else if (ZP == 0 || (warp >= 4 && (warp & 3) < (ZP == 2 ? 2 : 1) * p.slots_used && (warp >> 2) - 1 < 4 / p.slots_used)) {
+  } else if (ZP == 0 || (warp >= 4 && (warp & 3) < p.slots_used && (warp >> 2) - 1 < 4 / p.slots_used)) {
     // =============================== epilogue ==================================================
     // The warp of (slot g, share `sub`) scores the query in slot g for the documents whose local index is
     // congruent to `residue` modulo `rep`.
@@ -366,7 +364,7 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     bool any_active = false;
 #pragma unroll
     for (int j = 0; j < MT; ++j) {
-      const int q = ZP == 2 ? q_base + (slot >> 1) : q_base + 4 * j + slot;
+      const int q = q_base + 4 * j + slot;
       active[j] = q < p.n_queries;
       out_row[j] = int64_t(q) * p.n_items;
       any_active |= active[j];
@@ -466,12 +464,10 @@ maxsim_tc_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
         const int64_t row = lo_half ? out_row[0] : out_row[1];
         if ((lane & 15) == 0 && act) p.scores[row + pend_col] = a;
       } else {
-        // M=64: only lanes 0-15 of a lane group hold accumulator rows (16 query tokens)
-        const float sc = warp_sum((ZP == 2 && lane >= 16) ? 0.f : pend_m[0]);
+        const float sc = warp_sum(pend_m[0]);
         sc_all = sc;
         if (lane == 0 && active[0]) {
-          if constexpr (ZP == 2) atomicAdd(&p.scores[out_row[0] + pend_col], sc);   // the other token half adds its part
-          else if (!TK || p.scores != nullptr) p.scores[out_row[0] + pend_col] = sc;
+          if (!TK || p.scores != nullptr) p.scores[out_row[0] + pend_col] = sc;
           if constexpr (RR) __threadfence();                // fused rerank: the score must be visible to the last CTA
         }
       }
@@ -1032,12 +1028,12 @@ template <int MT, int ZP, int CG, bool TK = false, bool RR = false>
 int launch_cfg(const void* d_tokens, const void* d_queries, int lq, int n_real_queries, TcParams p, dim3 grid,
                cudaStream_t stream) {
   constexpr int kTileBytes = (TN / CG) * HRC_DIM * 2;   // what ONE CTA stages per tile
-  constexpr int kQBytes = (ZP == 2 ? 64 : 128) * HRC_DIM * 2;
+  constexpr int kQBytes = 128 * HRC_DIM * 2;
   CUtensorMap tmap_d, tmap_q;
   if (int rc = cached_map(d_tokens, uint64_t(p.total_tokens), 0, TN / CG, &tmap_d)) return rc;
   if (int rc = cached_map(d_queries, uint64_t(lq), uint64_t(n_real_queries), 32, &tmap_q)) return rc;
   const int q_bytes = MT * kQBytes;
-  const int list_bytes = TK ? epi_warps(MT, ZP) * kListCap * 8 : 0;
+  const int list_bytes = TK ? epi_warps(MT) * kListCap * 8 : 0;
   int stages = (kMaxSmem - 1024 - 512 - q_bytes - list_bytes) / kTileBytes;
   // Ring depth: 8 x 16 KB for the batched kernels; FIVE x 32 KB for the HBM-bound ones — a sixth stage fits but is
   // slower (libhrc_exp stage sweep, same box: C2 4.67-4.90 ms with 6, 4.69-4.78 with 5, 4.60-4.64 with 4, 5.09 with 3;
@@ -1056,8 +1052,6 @@ int launch_cfg(const void* d_tokens, const void* d_queries, int lq, int n_real_q
                                         kMaxSmem));
     once.mark(dev);
   }
-  if (ZP == 2)   // both token halves of a query accumulate into the score
-    HRC_CHECK_CUDA(cudaMemsetAsync(p.scores, 0, size_t(p.n_queries) * size_t(p.n_items) * sizeof(float), stream));
   trace_begin(stream);
   if constexpr (CG == 2) {
     cudaLaunchConfig_t cfg = {};
@@ -1115,9 +1109,9 @@ __global__ void sum_slots_kernel(const float* __restrict__ part, int q_slots, in
 }
 
 // single-query kernel organisations.  Auto (HRC_PATH_AUTO): doc-major for one query of <= 32 tokens over the corpus —
-// same time as the query-major kernel at burst clocks, 5-7 % faster once the GPU sits at its power cap (3 s back to back,
-// same box: 4.77 vs 5.10 ms per C2 search; M=64 4.98) — query-major for everything else.
-constexpr int kVariantDefault = 0, kVariantM64 = 1, kVariantDocMajor = 2, kVariantAuto = 3;
+// same time as the query-major kernel at burst clocks, 4-7 % faster than round 1's organisation once the GPU sits at its
+// power cap (3 s back to back, same box: 4.41-4.77 vs 4.59-5.10 ms per C2 scan) — query-major for everything else.
+constexpr int kVariantDefault = 0, kVariantDocMajor = 2, kVariantAuto = 3;
 
 struct TopkOut {            // fused top-k request (corpus mode, lq <= 32, k <= kListOut)
   uint64_t* cand_keys;
@@ -1137,7 +1131,6 @@ int launch_tc_slots(const void* d_tokens, const int64_t* d_offsets, int64_t n_do
                     const int32_t* d_cand_ids, int64_t n_items, const void* d_queries, int n_real_queries,
                     int q_slots, int lq, float* d_scores, int variant, const TopkOut* tk, const RerankOut* rr,
                     cudaStream_t stream) {
-  const bool m64 = variant == kVariantM64;
   const bool dm = variant == kVariantDocMajor || (variant == kVariantAuto && d_cand_ids == nullptr && q_slots == 1);
   const int n_queries = n_real_queries * q_slots;      // virtual queries from here on
   HRC_REQUIRE(total_tokens > 0 && total_tokens < (1ll << 31), "tc path: total_tokens=%lld out of range",
@@ -1192,8 +1185,6 @@ int launch_tc_slots(const void* d_tokens, const int64_t* d_offsets, int64_t n_do
   if (n_queries <= 4) {
     p.slots_used = n_queries == 1 ? 1 : (n_queries == 2 ? 2 : 4);
     if (tk) return launch_cfg<1, 1, 1, true>(d_tokens, d_queries, lq, n_real_queries, p, dim3((unsigned)p.n_segments), stream);
-    if (m64 && n_queries <= 2)
-      return launch_cfg<1, 2, 1>(d_tokens, d_queries, lq, n_real_queries, p, dim3((unsigned)p.n_segments), stream);
     return launch_cfg<1, 1, 1>(d_tokens, d_queries, lq, n_real_queries, p, dim3((unsigned)p.n_segments), stream);
   }
   p.n_qgroups = (n_queries + 7) / 8;

@@ -41,8 +41,7 @@ extern "C" {
 #define HRC_PATH_AUTO 0
 #define HRC_PATH_SIMT 1        /* coalesced 16-byte loads + warp-shuffle reduction (CUDA cores) */
 #define HRC_PATH_TC   2        /* TMA + tcgen05.mma + TMEM, fused segmented max/sum epilogue     */
-#define HRC_PATH_TC_M64 3      /* as TC, but 1-2 queries run an M=64 MMA (half the tensor work)  */
-#define HRC_PATH_TC_DM  4      /* as TC, but ONE query runs doc-major (documents on M, query on N = 32): exactly the useful tensor work */
+#define HRC_PATH_TC_DM 3       /* as TC, but ONE query runs doc-major (documents on M, query on N = 32): exactly the useful tensor work */
 
 /* Library / ABI version (major*10000 + minor*100 + patch). */
 int hrc_version(void);

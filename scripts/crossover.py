@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Where does the tensor-core path stop paying?  (HRC_PATH_AUTO's rule must come from data.)
-TC vs SIMT (and the M=64 TC variant) for query lengths 1..32 on (a) the 50-candidate rerank (launch-latency-bound)
+TC vs SIMT (and the doc-major TC kernel) for query lengths 1..32 on (a) the 50-candidate rerank (launch-latency-bound)
 and (b) a full-corpus single-query scan of 200k ragged passages (bandwidth-bound).  One JSON line per point."""
 import json
 import os
@@ -33,7 +33,7 @@ store = synth_store(200_000, 32, 512, seed=12, device=dev)
 g = torch.Generator().manual_seed(0)
 cand = torch.randint(0, store.n_docs, (1, 50), generator=g, dtype=torch.int32).to(dev)
 out = torch.empty((1, store.n_docs), dtype=torch.float32, device=dev)
-paths = (("tc", L.PATH_TC), ("tc_m64", L.PATH_TC_M64), ("simt", L.PATH_SIMT))
+paths = (("tc", L.PATH_TC), ("tc_dm", L.PATH_TC_DM), ("simt", L.PATH_SIMT))
 for lq in (1, 2, 4, 8, 16, 32):
     q = synth_queries(1, lq, device=dev)
     row = {"lq": lq}
@@ -41,8 +41,8 @@ for lq in (1, 2, 4, 8, 16, 32):
         row[f"rerank50_{name}_us"] = round(timed(lambda: L.maxsim_scores_ids(store.tokens, store.offsets, cand, q, path=path), 200), 2)
         row[f"scan200k_{name}_us"] = round(timed(lambda: L.maxsim_scores(store.tokens, store.offsets, q, path=path, out=out), 5), 1)
     print(json.dumps(row), flush=True)
-for nq in (1, 2, 3, 4):                       # few-query scans: TC single-CTA kernel vs its M=64 variant
+for nq in (1, 2, 3, 4):                       # few-query scans: explicit query-major vs what AUTO picks
     q = synth_queries(nq, 32, device=dev)
     o2 = torch.empty((nq, store.n_docs), dtype=torch.float32, device=dev)
     print(json.dumps({"nq": nq, "scan200k_tc_us": round(timed(lambda: L.maxsim_scores(store.tokens, store.offsets, q, path=L.PATH_TC, out=o2), 10), 1),
-                      "scan200k_tc_m64_us": round(timed(lambda: L.maxsim_scores(store.tokens, store.offsets, q, path=L.PATH_TC_M64, out=o2), 10), 1)}), flush=True)
+                      "scan200k_auto_us": round(timed(lambda: L.maxsim_scores(store.tokens, store.offsets, q, path=L.PATH_AUTO, out=o2), 10), 1)}), flush=True)

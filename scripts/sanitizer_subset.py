@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A <= 60 s subset of the parity suite for compute-sanitizer (memcheck / racecheck / synccheck / initcheck):
-one small case per kernel organisation — single-CTA tensor-core kernel with 1, 2 and 4 queries, the M=64 variant,
+one small case per kernel organisation — single-CTA tensor-core kernel with 1, 2 and 4 queries, the doc-major single-query kernel,
 the single-CTA batched kernel, CTA pairs (cta_group::2) with and without an odd query group, candidate (rerank)
 mode, queries longer than 32 tokens (slot partials in the caller's workspace), the CUDA-core kernel, mean-pool
 cosine, radix top-k (one and several chunks), merge, RRF and the fused search / rerank / hybrid calls.
@@ -47,7 +47,7 @@ def close(got, exp, what):
 rng = np.random.default_rng(3)
 lens = np.concatenate([rng.integers(1, 200, 300), [0, 1, 31, 32, 33, 127, 128, 129, 400]]).tolist()   # ~31k tokens: every SM
 for bq, lq, path, name in [(1, 32, L.PATH_TC, "tc 1 query"), (2, 32, L.PATH_TC, "tc 2 queries"), (4, 17, L.PATH_TC, "tc 4 queries lq=17"),
-                           (1, 32, L.PATH_TC_M64, "m64 1 query"), (2, 32, L.PATH_TC_M64, "m64 2 queries"),
+                           (1, 32, L.PATH_TC_DM, "doc-major 1 query"), (1, 9, L.PATH_TC_DM, "doc-major lq=9"),
                            (7, 32, L.PATH_TC, "single-CTA batched, 7 queries"), (16, 32, L.PATH_TC, "CTA pairs, 16 queries"),
                            (24, 32, L.PATH_TC, "CTA pairs + odd group, 24 queries"), (2, 70, L.PATH_TC, "lq=70 (3 slots)"),
                            (9, 40, L.PATH_TC, "lq=40 x 9 queries (pairs of slots)"), (2, 32, L.PATH_SIMT, "simt")]:

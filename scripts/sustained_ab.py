@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Sustained (power-capped) A/B of the single-query search routes on ONE box: each route runs back to back for ~3 s,
 alternating twice; kernel time from hrc_trace, SM clock / power from NVML.  Routes: query-major fused (default),
-doc-major fused (HRC_PATH_TC_DM), M=64 staged (HRC_PATH_TC_M64)."""
+doc-major fused (HRC_PATH_TC_DM), each also writing scores only, and the pure read probe.  (The M=64 variant measured
+here in round 2 — between the two — has been removed: profiles/r02_logs/r02_sustained_ab_*.log keep its numbers.)"""
 import json
 import os
 import statistics
@@ -50,7 +51,7 @@ def sustained(fn, seconds=3.0):
     stop.set()
     th.join()
     half = k[len(k) // 2:]
-    return {"step_ms": round(el / n * 1e3, 3), "kernel_ms_second_half": round(sum(half) / max(len(half), 1), 3),
+    return {"step_ms": round(el / n * 1e3, 3), "kernel_ms_second_half": round(sum(half) / max(len(half), 1), 3) if half else None,
             "sm_mhz": statistics.median([s[0] for s in samples[len(samples) // 2:]]),
             "power_w": round(statistics.median([s[1] for s in samples[len(samples) // 2:]]), 1)}
 
@@ -62,9 +63,10 @@ ws = L.Workspace()
 scores = torch.empty((1, store.n_docs), dtype=torch.float32, device=dev)
 routes = {"query_major_fused": lambda: L.search(store.tokens, store.offsets, q, K, workspace=ws),
           "doc_major_fused": lambda: L.search(store.tokens, store.offsets, q, K, workspace=ws, path=L.PATH_TC_DM),
-          "m64_scores_only": lambda: L.maxsim_scores(store.tokens, store.offsets, q, out=scores, path=L.PATH_TC_M64),
           "query_major_scores_only": lambda: L.maxsim_scores(store.tokens, store.offsets, q, out=scores, path=L.PATH_TC),
           "doc_major_scores_only": lambda: L.maxsim_scores(store.tokens, store.offsets, q, out=scores, path=L.PATH_TC_DM)}
+probe_out = torch.zeros(1, dtype=torch.int32, device=dev)
+routes["read_probe_16B_loads"] = lambda: L.read_probe(store.tokens, probe_out)      # the memory system alone, same bytes
 for rnd in range(2):
     for name, fn in routes.items():
         print(json.dumps({"corpus": which, "route": name, "round": rnd, **sustained(fn)}), flush=True)

@@ -72,7 +72,7 @@ def _close(got, exp, what):
     assert err <= 4e-6, f"{what}: {err}"
 
 
-@pytest.mark.parametrize("nq,lq,path", [(1, 32, "tc"), (2, 32, "tc"), (4, 17, "tc"), (1, 32, "m64"), (2, 32, "m64"), (7, 32, "tc"),
+@pytest.mark.parametrize("nq,lq,path", [(1, 32, "tc"), (2, 32, "tc"), (4, 17, "tc"), (1, 32, "dm"), (1, 20, "dm"), (7, 32, "tc"),
                                         (16, 32, "tc"), (24, 32, "tc"), (2, 70, "tc"), (9, 40, "tc"), (2, 32, "simt")])
 def test_scoring_entry_points_stay_inside_their_buffers(cuda_dev, nq, lq, path):
     from hybrid_rag_colbertv2_b200 import _lib as L
@@ -82,7 +82,7 @@ def test_scoring_entry_points_stay_inside_their_buffers(cuda_dev, nq, lq, path):
     q, tok, off = _case(5, lens, nq, lq)
     n_docs, T = len(lens), int(off[-1])
     exp = o.maxsim_scores(q.float(), tok.float(), off)
-    P = {"tc": L.PATH_TC, "m64": L.PATH_TC_M64, "simt": L.PATH_SIMT}[path]
+    P = {"tc": L.PATH_TC, "dm": L.PATH_TC_DM, "simt": L.PATH_SIMT}[path]
     st = torch.cuda.current_stream(cuda_dev).cuda_stream
     A = Arena(cuda_dev)
     p_tok, _ = A.alloc(T * 256, src=tok)

@@ -60,7 +60,7 @@ def _dump_observed_errors():
 
 
 def _path(L, name):
-    return {"tc": L.PATH_TC, "simt": L.PATH_SIMT, "tc_m64": L.PATH_TC_M64, "tc_dm": L.PATH_TC_DM, "auto": L.PATH_AUTO}[name]
+    return {"tc": L.PATH_TC, "simt": L.PATH_SIMT, "tc_dm": L.PATH_TC_DM, "auto": L.PATH_AUTO}[name]
 
 
 SHAPES = [
@@ -79,11 +79,10 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-@pytest.mark.parametrize("path", ["tc", "simt", "tc_m64", "tc_dm"])
+@pytest.mark.parametrize("path", ["tc", "simt", "tc_dm", "auto"])
 def test_maxsim_scores_match_oracle(cuda_dev, shape, path):
-    """Every scoring path: tcgen05 (default), CUDA cores, the M=64 tensor-core variant for 1-2 queries
-    (HRC_PATH_TC_M64) and the doc-major kernel for one query (HRC_PATH_TC_DM); with more queries the last two are the
-    default kernel."""
+    """Every scoring path: tcgen05 query-major (HRC_PATH_TC), CUDA cores, the doc-major kernel for one query
+    (HRC_PATH_TC_DM; with more queries it is the query-major kernel) and what HRC_PATH_AUTO picks."""
     L = _lib()
     q, tok, off = _case(hash(shape) % 10_000, *shape)
     exp = o.maxsim_scores(q.float(), tok.float(), off)
@@ -96,11 +95,12 @@ def test_maxsim_scores_match_oracle(cuda_dev, shape, path):
                                    (3000, 16, 200, 40, 32), (1, 700, 700, 17, 32), (500, 1, 300, 2, 32), (77, 30, 34, 1, 32),
                                    (5000, 1, 70, 1, 32), (900, 100, 600, 1, 20), (3, 1, 2, 1, 32), (4, 3000, 9000, 1, 32),
                                    (2, 40_000, 60_000, 1, 7)])
-@pytest.mark.parametrize("path", ["tc", "tc_m64", "tc_dm"])
-def test_batched_and_m64_kernels_more_shapes(cuda_dev, shape, path):
+@pytest.mark.parametrize("path", ["tc", "tc_dm"])
+def test_batched_and_single_query_kernels_more_shapes(cuda_dev, shape, path):
     """Batched (MT=2) kernels — CTA pairs (cta_group::2, from two query groups up, with an odd last group on the
     single-CTA kernel) and single CTAs: 40 queries over many segments, 17 queries on one 6-tile document, short
-    documents, partial query groups — and the 1-2 query shapes on both single-query kernels (M=128 / M=64)."""
+    documents, partial query groups — and the one-query shapes (very long documents, thousands of short ones, fewer
+    documents than token streams) on both single-query kernels (query-major / doc-major)."""
     L = _lib()
     q, tok, off = _case(78, *shape)
     exp = o.maxsim_scores(q.float(), tok.float(), off)
@@ -706,7 +706,7 @@ def _boundary_corpus(nq, lq, seed=5):
     return q, tok, off, planted
 
 
-@pytest.mark.parametrize("nq,path", [(1, "tc"), (2, "tc"), (3, "tc"), (1, "tc_m64"), (2, "tc_m64"), (1, "tc_dm"), (8, "tc"),
+@pytest.mark.parametrize("nq,path", [(1, "tc"), (2, "tc"), (3, "tc"), (1, "tc_dm"), (1, "auto"), (8, "tc"),
                                      (16, "tc"), (24, "tc"), (2, "simt")])
 def test_decisive_token_at_every_chunk_and_tile_boundary(cuda_dev, nq, path):
     L = _lib()
@@ -735,7 +735,7 @@ def test_decisive_token_at_every_chunk_and_tile_boundary(cuda_dev, nq, path):
         _assert_scores(gotc, exp.flip(1), f"boundary candidates nq={nq}", bucket="boundary")
 
 
-@pytest.mark.parametrize("path", ["tc", "simt", "tc_m64", "tc_dm"])
+@pytest.mark.parametrize("path", ["tc", "simt", "tc_dm"])
 def test_maxsim_kernels_reproduce_the_reference_where_it_computes_maxsim(cuda_dev, golden_dir, path):
     """REFERENCE PIN for the MaxSim kernels: tests/golden/maxsim_pin.npz holds outputs of the UNMODIFIED reference
     `_maxsim_score` (local_rag_complete.py:821-829) on inputs where its mean-pool cosine equals MaxSim (identical
@@ -766,7 +766,7 @@ def test_maxsim_kernels_reproduce_the_reference_where_it_computes_maxsim(cuda_de
     assert ids[0, 0].item() == 0 and sc[0, 0].item() == 1.0                                # the query's own copy
 
 
-@pytest.mark.parametrize("path", ["tc", "simt", "tc_m64", "tc_dm"])
+@pytest.mark.parametrize("path", ["tc", "simt", "tc_dm"])
 def test_maxsim_kernels_match_float64_known_answers(cuda_dev, golden_dir, path):
     L = _lib()
     z = np.load(os.path.join(golden_dir, "maxsim_kat_f64.npz"))
@@ -1015,7 +1015,7 @@ def test_results_are_bitwise_repeatable(cuda_dev):
             res = [L.maxsim_scores(tok_d, off_d, q_d), L.maxsim_scores_ids(tok_d, off_d, cand, q_d)]
             res += list(L.rerank(tok_d, off_d, cand, q_d, 10)[:3])
             if lq <= 32:
-                res += [L.search(tok_d, off_d, q_d, 100)[0], L.maxsim_scores(tok_d, off_d, q_d, path=L.PATH_TC_M64),
+                res += [L.search(tok_d, off_d, q_d, 100)[0], L.maxsim_scores(tok_d, off_d, q_d, path=L.PATH_TC),
                         L.maxsim_scores(tok_d, off_d, q_d, path=L.PATH_TC_DM), L.search(tok_d, off_d, q_d, 100, path=L.PATH_TC_DM)[0]]
             if first is None:
                 first = [r.clone() for r in res]
