@@ -1,13 +1,22 @@
 // maxsim_tc.cu — tensor-core MaxSim: TMA -> tcgen05.mma (TMEM accumulators) -> fused segmented
-// row-max / query-token-sum epilogue.  The [Lq x Ld] similarity matrix never leaves the SM.
+// max / query-token-sum epilogue.  The [Lq x Ld] similarity matrix never leaves the SM.
 //
 // Data layout in HBM
 //   tokens  : bf16 [total_tokens][128], packed, padding-free           (TMA map: 2-D, 128B swizzle)
 //   offsets : int64 [n_docs + 1] CSR document boundaries
-//   queries : bf16 [n_queries][lq][128]; 32 query tokens per A-tile slot, a longer query (lq <= 256) is scored as
+//   queries : bf16 [n_queries][lq][128]; 32 query tokens per tile slot, a longer query (lq <= 256) is scored as
 //             ceil(lq / 32) "virtual queries" whose partial scores are summed in slot order (sum_slots_kernel)
 //
-// One CTA = one contiguous run of whole documents ("segment") x one group of 4*MT (virtual) queries.
+// Two kernels (DESIGN.md §4 has the measurements behind every choice):
+//
+// maxsim_dm_kernel<TK> — ONE query, DOC-MAJOR: A = document tokens (M = 128), B = the query (N = 32), so exactly the
+//   useful tensor work is issued; a tile is 4 streams x 32 tokens, one stream of whole documents per epilogue warp;
+//   the max over a document's tokens is one redux.sync.max.f32 per query token.  HRC_PATH_AUTO's choice for a single
+//   query; TK fuses the per-segment top-k into the epilogue (hrc_search = 2 launches).  See the comment above it.
+//
+// maxsim_tc_kernel<MT, ZP, CG, TK, RR> — QUERY-MAJOR: A = queries (M = 4 slots x 32 tokens), B = document tokens
+//   (N = 128): D[row = query token][col = doc token].  One CTA = one contiguous run of whole documents ("segment") x
+//   one group of 4*MT (virtual) queries.
 //   warp 0      : TMA producer  — streams 128-token x 128-dim tiles through a shared-memory ring
 //   warp 1      : MMA issuer    — per tile and M-tile: 8 x tcgen05.mma (M=128 [256 over a CTA pair], N=128, K=16),
 //                                 accumulator = 128 TMEM columns; owns TMEM alloc/dealloc
@@ -17,22 +26,21 @@
 //                                 >= 32-token pieces), document boundaries are warp-uniform, and a document's
 //                                 score is one shuffle butterfly, emitted after the tile has been released.
 //                                 Every warp owns WHOLE documents (no cross-warp combine).
-// MMA orientation: A = queries (M = 4 slots x 32 tokens), B = document tokens (N):
-// D[row = query token][col = doc token].
+//   <1,ZP=1>          2-4 queries (HBM-bound) and candidate mode: the unused rows of the A tile are zero, the 4
+//                     epilogue warps are stacked on the used lane groups, 5-stage smem ring, 4 accumulator stages,
+//                     one tcgen05.commit per tile.  TK: fused top-k (one query, explicit HRC_PATH_TC).
+//                     RR: candidate (rerank) mode with the sorted top-k written by the last CTA of a query to finish
+//                     (hrc_rerank = one launch).
+//   <2,ZP=0,CG=2>     tensor-bound, batched: CTA PAIR (cta_group::2, cluster of 2), one M=256 MMA per K slice,
+//                     each CTA stages half of every document tile; 8 epilogue warps per CTA (two per lane
+//                     group, alternating documents), 2 x 2 accumulators.            [from 9 queries]
+//   <2,ZP=0,CG=1>     single-CTA batched kernel (5..8 queries, or an odd last query group)
+//   The organisations measured slower — query replicated over the A tile, A operand in TMEM, per-M-tile accumulator
+//   units (round 1), the M=64 variant (round 2) — are no longer in the source: profiles/experiments/ keeps their diffs.
 //
-// Instantiations <MT, ZP, CG> (DESIGN.md §4.1 has the measurements behind each choice; the organisations that were
-// measured slower in round 1 — query replicated over the A tile, A operand in TMEM, per-M-tile accumulator units —
-// are no longer in the source: profiles/experiments/ keeps their diffs):
-//   <1,ZP=1>       HBM-bound (<= 4 queries) and candidate (rerank) mode: the unused rows of the A tile are
-//                  zero, the 4 epilogue warps are stacked on the used lane groups, 6-stage smem ring,
-//                  4 accumulator stages, one tcgen05.commit per tile.                   [default]
-//   <2,ZP=0,CG=2>  tensor-bound, batched: CTA PAIR (cta_group::2, cluster of 2), one M=256 MMA per K slice,
-//                  each CTA stages half of every document tile; 8 epilogue warps per CTA (two per lane
-//                  group, alternating documents), 2 x 2 accumulators.                   [default from 9 queries]
-//   <2,ZP=0,CG=1>  single-CTA batched kernel (5..8 queries, or an odd last query group)
 // The product library reads no environment variables.  Building with -DHRC_EXPERIMENTS (make exp -> libhrc_exp.so)
-// adds hrc_exp_set_debug(): bit 0 skips the epilogue math, bit 1 the document TMA, bit 2 the MMAs — the
-// kernel-skeleton measurements behind DESIGN.md §4.1 and the TMA-ring read peak of scripts/read_peak.py.
+// adds hrc_exp_set_debug() / hrc_exp_set_stages(): kernel skeletons (no epilogue math / no document TMA / no MMA) and
+// the shared-memory-ring cap behind the measurements in DESIGN.md §4 (scripts/exp_sweep.py, scripts/exp_dm_tk.py).
 //
 // Reference semantics: local_rag_complete.py:807-812 (docstring), :813-817 (shapes), summed over
 // query tokens per BASELINE.json north_star.  Algorithmic traffic: 256 B per document token.
