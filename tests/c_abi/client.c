@@ -90,7 +90,37 @@ int main(void) {
       if (top[b * K + j] != tc[b * N_DOCS + ids[b * K + j]]) { printf("key score != score row\n"); return 1; }
     }
   }
-  /* 4. errors are reported, not swallowed */
+  /* 4. the one-call entry points with caller-owned workspaces: hrc_search (one query: 2 launches, the top-k fused
+   *    into the doc-major MaxSim epilogue) must return the keys of step 3, and hrc_rerank (ONE launch) must rank the
+   *    first 40 of them in the same order */
+  {
+    enum { NC = 40, RK = 10 };
+    size_t sws = hrc_search_workspace_bytes(N_DOCS, T, 1, LQ, K, HRC_PATH_AUTO);
+    size_t rws = hrc_rerank_workspace_bytes(NC, 1, LQ, RK);
+    void *d_sws, *d_rws; uint64_t* d_k1; int32_t *d_i1, *d_pos, *d_rid; float *d_s1, *d_rs;
+    CK(cudaMalloc(&d_sws, sws)); CK(cudaMalloc(&d_rws, rws));
+    CK(cudaMalloc((void**)&d_k1, sizeof(uint64_t) * K)); CK(cudaMalloc((void**)&d_i1, sizeof(int32_t) * K));
+    CK(cudaMalloc((void**)&d_s1, sizeof(float) * K)); CK(cudaMalloc((void**)&d_pos, sizeof(int32_t) * RK));
+    CK(cudaMalloc((void**)&d_rid, sizeof(int32_t) * RK)); CK(cudaMalloc((void**)&d_rs, sizeof(float) * RK));
+    const unsigned long long before = (unsigned long long)hrc_launch_count();
+    HK(hrc_search(d_tok, d_off, N_DOCS, T, d_q, 1, LQ, K, 0, d_sws, sws, d_k1, d_i1, d_s1, HRC_PATH_AUTO, NULL));
+    if ((unsigned long long)hrc_launch_count() - before != 2) { printf("hrc_search for one query should be 2 launches\n"); return 1; }
+    HK(hrc_rerank(d_tok, d_off, N_DOCS, T, d_i1, NC, d_q, 1, LQ, RK, d_rws, rws, d_pos, d_rid, d_rs, NULL, HRC_PATH_AUTO, NULL));
+    if ((unsigned long long)hrc_launch_count() - before != 3) { printf("hrc_rerank should be 1 launch\n"); return 1; }
+    CK(cudaDeviceSynchronize());
+    int32_t i1[K], pos[RK], rid[RK]; float s1[K], rs[RK];
+    CK(cudaMemcpy(i1, d_i1, sizeof(i1), cudaMemcpyDeviceToHost)); CK(cudaMemcpy(s1, d_s1, sizeof(s1), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(pos, d_pos, sizeof(pos), cudaMemcpyDeviceToHost)); CK(cudaMemcpy(rid, d_rid, sizeof(rid), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rs, d_rs, sizeof(rs), cudaMemcpyDeviceToHost));
+    for (int j = 0; j < K; ++j)
+      if (i1[j] != ids[j] || fabsf(s1[j] - top[j]) > 4e-6f * fabsf(top[j])) { printf("hrc_search differs from scores + top-k at rank %d\n", j); return 1; }
+    for (int j = 0; j < RK; ++j)      /* candidates were handed over best first: the rerank keeps that order */
+      if (pos[j] != j || rid[j] != ids[j] || rs[j] != s1[j]) { printf("hrc_rerank: rank %d is position %d\n", j, pos[j]); return 1; }
+    if (hrc_search(d_tok, d_off, N_DOCS, T, d_q, 1, LQ, K, 0, d_sws, sws - 1, d_k1, d_i1, d_s1, HRC_PATH_AUTO, NULL) == 0) {
+      printf("a workspace one byte short was accepted\n"); return 1;
+    }
+  }
+  /* 5. errors are reported, not swallowed */
   if (hrc_topk(d_tc, NULL, N_DOCS, NQ, HRC_MAX_TOPK + 1, 0, d_keys, d_ws, ws_bytes, NULL) == 0 || hrc_last_error()[0] == 0) {
     printf("k > HRC_MAX_TOPK was accepted\n"); return 1;
   }
