@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from typing import Optional
 
 import torch
@@ -32,6 +33,7 @@ SYMBOLS = {
     "hrc_trace_collect": (_I, [_P, _I]),
     "hrc_store_register": (_I, [_P, _I64]),
     "hrc_store_release": (None, [_P]),
+    "hrc_store_validate": (_I, [_P, _P, _I64, _I64, _I, _P, _SZ, _P, _P]),
     "hrc_maxsim_workspace_bytes": (_SZ, [_I64, _I, _I]),
     "hrc_maxsim_scores": (_I, [_P, _P, _I64, _I64, _P, _I, _I, _P, _I, _P, _SZ, _P]),
     "hrc_maxsim_scores_ids": (_I, [_P, _P, _I64, _I64, _P, _I, _P, _I, _I, _P, _I, _P, _SZ, _P]),
@@ -170,23 +172,50 @@ def store_release(tokens: torch.Tensor) -> None:
         _lib.hrc_store_release(_ptr(tokens))
 
 
+def store_validate(tokens: torch.Tensor, offsets: torch.Tensor, *, check_values: bool = True) -> dict:
+    """Integrity check of a packed store (hrc_store_validate), run once at load / build time: raises ValueError when the
+    CSR offsets are malformed or (check_values) a token value is NaN / infinite.  Returns
+    {'longest_doc_tokens': ...} for a sound store.  Synchronises the current stream."""
+    dev = _require_cuda(tokens, offsets)
+    _check_store(tokens, offsets)
+    ws = torch.empty(4, dtype=torch.int64, device=dev)
+    rep = (ctypes.c_int64 * 4)()
+    with torch.cuda.device(dev):
+        rc = load().hrc_store_validate(_ptr(tokens), _ptr(offsets), offsets.numel() - 1, int(tokens.shape[0]),
+                                       1 if check_values else 0, _ptr(ws), 32, rep, _stream(dev))
+    if rc in (3, 4):
+        raise ValueError(load().hrc_last_error().decode())
+    _check(rc, "hrc_store_validate")
+    return {"longest_doc_tokens": int(rep[3])}
+
+
 class Workspace:
-    """A reusable 256-byte-aligned device scratch buffer that only ever grows: no per-call allocation once warm."""
+    """Reusable 256-byte-aligned device scratch that only ever grows: no per-call allocation once warm.  One buffer PER
+    STREAM (keyed by the stream handle the call is issued on): two threads driving the same retriever on different
+    streams never share scratch, and a buffer is only ever replaced from the stream whose kernels use it, which is
+    what makes handing the old one back to torch's stream-ordered caching allocator safe."""
 
     def __init__(self):
-        self.buf: Optional[torch.Tensor] = None
+        self.bufs: dict = {}
 
-    def get(self, dev, nbytes: int) -> torch.Tensor:
-        if self.buf is None or self.buf.device != dev or self.buf.numel() < nbytes:
-            self.buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)   # caching allocator: 512-B aligned
-        return self.buf
+    @property
+    def buf(self) -> Optional[torch.Tensor]:
+        """The largest buffer held (diagnostics / tests)."""
+        return max(self.bufs.values(), key=lambda b: b.numel(), default=None)
+
+    def get(self, dev, nbytes: int, stream: int = 0) -> torch.Tensor:
+        buf = self.bufs.get(stream)
+        if buf is None or buf.device != dev or buf.numel() < nbytes:
+            buf = self.bufs[stream] = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)   # 512-B aligned
+        return buf
 
 
-def _ws(workspace: Optional[Workspace], dev, nbytes: int):
-    """(pointer, bytes) of a scratch buffer of at least nbytes; (None, 0) when none is needed."""
+def _ws(workspace: Optional[Workspace], dev, nbytes: int, stream: int = 0):
+    """(pointer, bytes, keep-alive) of a scratch buffer of at least nbytes for calls issued on `stream`;
+    (None, 0, None) when none is needed."""
     if nbytes == 0:
         return None, 0, None
-    buf = (workspace or Workspace()).get(dev, nbytes)
+    buf = (workspace or Workspace()).get(dev, nbytes, stream)
     return buf.data_ptr(), buf.numel(), buf
 
 
@@ -216,10 +245,11 @@ def maxsim_scores(tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.Te
         out = torch.empty((nq, n_docs), dtype=torch.float32, device=dev)
     else:
         assert out.shape == (nq, n_docs) and out.dtype == torch.float32 and out.is_contiguous()
-    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, 0 if path == PATH_SIMT else maxsim_workspace_bytes(n_docs, nq, lq))
+    st = _stream(dev)
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, 0 if path == PATH_SIMT else maxsim_workspace_bytes(n_docs, nq, lq), st)
     with torch.cuda.device(dev):
         rc = load().hrc_maxsim_scores(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), _ptr(queries),
-                                      nq, lq, _ptr(out), path, ws_ptr, ws_bytes, _stream(dev))
+                                      nq, lq, _ptr(out), path, ws_ptr, ws_bytes, st)
     _check(rc, "hrc_maxsim_scores")
     return out
 
@@ -256,10 +286,11 @@ def maxsim_scores_ids(tokens: torch.Tensor, offsets: torch.Tensor, cand_ids: tor
     nq, lq = int(queries.shape[0]), int(queries.shape[1])
     n_cand = int(cand_ids.shape[1])
     out = torch.empty((nq, n_cand), dtype=torch.float32, device=dev)
-    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, 0 if path == PATH_SIMT else maxsim_workspace_bytes(n_cand, nq, lq))
+    st = _stream(dev)
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, 0 if path == PATH_SIMT else maxsim_workspace_bytes(n_cand, nq, lq), st)
     with torch.cuda.device(dev):
         rc = load().hrc_maxsim_scores_ids(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), _ptr(cand_ids),
-                                          n_cand, _ptr(queries), nq, lq, _ptr(out), path, ws_ptr, ws_bytes, _stream(dev))
+                                          n_cand, _ptr(queries), nq, lq, _ptr(out), path, ws_ptr, ws_bytes, st)
     _check(rc, "hrc_maxsim_scores_ids")
     return out
 
@@ -272,14 +303,15 @@ def search(tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.Tensor, k
     _check_queries(queries)
     n_docs = offsets.numel() - 1
     nq, lq = int(queries.shape[0]), int(queries.shape[1])
+    st = _stream(dev)
     ws_ptr, ws_bytes, _keep = _ws(workspace, dev, int(load().hrc_search_workspace_bytes(n_docs, int(tokens.shape[0]), nq,
-                                                                                        lq, k, path)))
+                                                                                        lq, k, path)), st)
     keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
     ids = torch.empty((nq, k), dtype=torch.int32, device=dev) if unpack else None
     scores = torch.empty((nq, k), dtype=torch.float32, device=dev) if unpack else None
     with torch.cuda.device(dev):
         rc = load().hrc_search(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), _ptr(queries), nq, lq, k,
-                               id_base, ws_ptr, ws_bytes, _ptr(keys), _ptr(ids), _ptr(scores), path, _stream(dev))
+                               id_base, ws_ptr, ws_bytes, _ptr(keys), _ptr(ids), _ptr(scores), path, st)
     _check(rc, "hrc_search")
     return keys, ids, scores
 
@@ -290,6 +322,11 @@ class HostSearch:
 
     def __init__(self):
         self.key = None
+        self._lock = threading.Lock()      # the staging buffers are this object's: one search at a time per object
+
+    def __call__(self, *args, **kwargs):
+        with self._lock:
+            return self._call(*args, **kwargs)
 
     def _ensure(self, dev, nq: int, lq: int, n_docs: int, total_tokens: int, k: int, path: int):
         key = (str(dev), nq, lq, n_docs, total_tokens, k, path)
@@ -302,8 +339,8 @@ class HostSearch:
             self.scores = torch.empty((nq, k), dtype=torch.float32).pin_memory()
             self.key = key
 
-    def __call__(self, tokens: torch.Tensor, offsets: torch.Tensor, queries_host: torch.Tensor, k: int, *,
-                 id_base: int = 0, path: int = PATH_AUTO, copy: bool = True):
+    def _call(self, tokens: torch.Tensor, offsets: torch.Tensor, queries_host: torch.Tensor, k: int, *,
+              id_base: int = 0, path: int = PATH_AUTO, copy: bool = True):
         """queries_host: fp32 CPU tensor [nq, lq, 128] (pinned: used in place; pageable: staged through a pinned
         buffer).  Returns (ids int32 [nq, k], scores fp32 [nq, k]) CPU tensors.  With copy=True (default) they are
         fresh tensors the caller owns; copy=False returns this object's PINNED staging buffers, which the next call
@@ -344,13 +381,14 @@ def hybrid_retrieve(tokens: torch.Tensor, offsets: torch.Tensor, queries: torch.
     nq, lq = int(queries.shape[0]), int(queries.shape[1])
     need = int(load().hrc_hybrid_retrieve_workspace_bytes(n_docs, int(tokens.shape[0]), nq, lq, colbert_k, n_candidates,
                                                           final_k, path))
-    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, need)
+    st = _stream(dev)
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, need, st)
     ids = torch.empty((nq, final_k), dtype=torch.int32, device=dev)
     scores = torch.empty((nq, final_k), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         rc = load().hrc_hybrid_retrieve(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), _ptr(queries), nq, lq,
                                         _ptr(bm25_ids), int(bm25_ids.shape[1]), colbert_k, rrf_k, n_candidates, final_k,
-                                        id_base, ws_ptr, ws_bytes, _ptr(ids), _ptr(scores), path, _stream(dev))
+                                        id_base, ws_ptr, ws_bytes, _ptr(ids), _ptr(scores), path, st)
     _check(rc, "hrc_hybrid_retrieve")
     return ids, scores
 
@@ -373,14 +411,15 @@ def rerank(tokens: torch.Tensor, offsets: torch.Tensor, cand_ids: torch.Tensor, 
     need = _RERANK_WS.get(shape)
     if need is None:
         need = _RERANK_WS[shape] = int(load().hrc_rerank_workspace_bytes(n_cand, nq, lq, k))
-    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, need)
+    st = _stream(dev)
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, need, st)
     cand_scores = torch.empty((nq, n_cand), dtype=torch.float32, device=dev) if want_cand_scores else None
     out = torch.empty((3, nq, k), dtype=torch.int32, device=dev)      # one allocation: pos | ids | scores (fp32 view)
     pos, ids, scores = out[0], out[1], out[2].view(torch.float32)
     with torch.cuda.device(dev):
         rc = load().hrc_rerank(_ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]), _ptr(cand_ids), n_cand,
                                _ptr(queries), nq, lq, k, ws_ptr, ws_bytes, pos.data_ptr(), ids.data_ptr(),
-                               scores.data_ptr(), _ptr(cand_scores), path, _stream(dev))
+                               scores.data_ptr(), _ptr(cand_scores), path, st)
     _check(rc, "hrc_rerank")
     return pos, ids, scores, cand_scores
 
@@ -521,13 +560,14 @@ def allgather_merge_topk(comm: Comm, local_keys: torch.Tensor, k: int, *, transp
     dev = _require_cuda(local_keys)
     assert local_keys.dtype == torch.int64 and local_keys.dim() == 2 and local_keys.shape[1] == k
     n_rows = int(local_keys.shape[0])
-    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, int(load().hrc_allgather_merge_workspace_bytes(comm.world, n_rows, k)))
+    st = _stream(dev)
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, int(load().hrc_allgather_merge_workspace_bytes(comm.world, n_rows, k)), st)
     keys = torch.empty((n_rows, k), dtype=torch.int64, device=dev)
     ids = torch.empty((n_rows, k), dtype=torch.int32, device=dev) if unpack else None
     scores = torch.empty((n_rows, k), dtype=torch.float32, device=dev) if unpack else None
     with torch.cuda.device(dev):
         rc = load().hrc_allgather_merge_topk(comm.handle, _ptr(local_keys), n_rows, k, transport, ws_ptr, ws_bytes,
-                                             _ptr(keys), _ptr(ids), _ptr(scores), _stream(dev))
+                                             _ptr(keys), _ptr(ids), _ptr(scores), st)
     _check(rc, "hrc_allgather_merge_topk")
     return keys, ids, scores
 
@@ -542,14 +582,15 @@ def sharded_search(comm: Comm, tokens: torch.Tensor, offsets: torch.Tensor, quer
     n_docs = offsets.numel() - 1
     nq, lq = int(queries.shape[0]), int(queries.shape[1])
     need = int(load().hrc_sharded_search_workspace_bytes(comm.world, n_docs, int(tokens.shape[0]), nq, lq, k, path))
-    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, need)
+    st = _stream(dev)
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, need, st)
     keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
     ids = torch.empty((nq, k), dtype=torch.int32, device=dev) if unpack else None
     scores = torch.empty((nq, k), dtype=torch.float32, device=dev) if unpack else None
     with torch.cuda.device(dev):
         rc = load().hrc_sharded_search(comm.handle, transport, _ptr(tokens), _ptr(offsets), n_docs, int(tokens.shape[0]),
                                        _ptr(queries), nq, lq, k, id_base, ws_ptr, ws_bytes, _ptr(keys), _ptr(ids),
-                                       _ptr(scores), path, _stream(dev))
+                                       _ptr(scores), path, st)
     _check(rc, "hrc_sharded_search")
     return keys, ids, scores
 
@@ -560,8 +601,13 @@ class ShardedHostSearch:
     def __init__(self, comm: Comm):
         self.comm = comm
         self.key = None
+        self._lock = threading.Lock()
 
-    def __call__(self, tokens, offsets, queries_host, k, *, id_base=0, path=PATH_AUTO, transport=TRANSPORT_NCCL, copy=True):
+    def __call__(self, *args, **kwargs):
+        with self._lock:
+            return self._call(*args, **kwargs)
+
+    def _call(self, tokens, offsets, queries_host, k, *, id_base=0, path=PATH_AUTO, transport=TRANSPORT_NCCL, copy=True):
         dev = _require_cuda(tokens, offsets)
         _check_store(tokens, offsets)
         assert not queries_host.is_cuda and queries_host.dtype == torch.float32 and queries_host.dim() == 3
@@ -602,14 +648,15 @@ def sharded_hybrid_retrieve(comm: Comm, tokens: torch.Tensor, offsets: torch.Ten
     n_docs, total = offsets.numel() - 1, int(tokens.shape[0])
     nq, lq = int(queries.shape[0]), int(queries.shape[1])
     need = int(load().hrc_sharded_hybrid_workspace_bytes(comm.world, n_docs, total, nq, lq, colbert_k, n_candidates, final_k, path))
-    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, need)
+    st = _stream(dev)
+    ws_ptr, ws_bytes, _keep = _ws(workspace, dev, need, st)
     ids = torch.empty((nq, final_k), dtype=torch.int32, device=dev)
     scores = torch.empty((nq, final_k), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         rc = load().hrc_sharded_hybrid_retrieve(comm.handle, transport, _ptr(tokens), _ptr(offsets), n_docs, total,
                                                 int(n_docs_global), _ptr(queries), nq, lq, _ptr(bm25_ids),
                                                 int(bm25_ids.shape[1]), colbert_k, rrf_k, n_candidates, final_k, id_base,
-                                                ws_ptr, ws_bytes, _ptr(ids), _ptr(scores), path, _stream(dev))
+                                                ws_ptr, ws_bytes, _ptr(ids), _ptr(scores), path, st)
     _check(rc, "hrc_sharded_hybrid_retrieve")
     return ids, scores
 

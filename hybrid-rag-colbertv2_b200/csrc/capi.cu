@@ -76,6 +76,7 @@ int launch_rerank_unpack(const uint64_t*, int, int, const int32_t*, int, int32_t
 int launch_rrf(const int32_t*, int, const int32_t*, int, int, int, int, int32_t*, double*, int32_t*, cudaStream_t);
 int launch_synth(void*, int64_t, int64_t, uint64_t, cudaStream_t);
 int launch_read_probe(const void*, size_t, uint32_t*, cudaStream_t);
+int launch_store_validate(const void*, const int64_t*, int64_t, int64_t, int, unsigned long long*, cudaStream_t);
 int launch_meanpool_cosine(const void*, const int64_t*, int64_t, const void*, int, int, float*, cudaStream_t);
 
 static int check_device() {
@@ -515,6 +516,38 @@ int hrc_rrf_fuse(const int32_t* d_ids_a, int n_a, const int32_t* d_ids_b, int n_
 int hrc_synth_tokens(void* d_tokens_out, int64_t token_begin, int64_t n_tokens, uint64_t seed, void* stream) {
   if (int rc = check_device()) return rc;
   return launch_synth(d_tokens_out, token_begin, n_tokens, seed, static_cast<cudaStream_t>(stream));
+}
+
+int hrc_store_validate(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                       int check_values, void* d_workspace, size_t workspace_bytes, int64_t* report_out, void* stream) {
+  if (int rc = check_device()) return rc;
+  HRC_REQUIRE(d_offsets != nullptr && n_docs >= 0 && total_tokens >= 0 && (total_tokens == 0 || d_tokens != nullptr),
+              "store_validate: null store");
+  HRC_REQUIRE(d_workspace != nullptr && workspace_bytes >= 32 && (reinterpret_cast<uintptr_t>(d_workspace) & 7) == 0,
+              "store_validate: workspace of 32 bytes, 8-byte aligned, required");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto* d_report = static_cast<unsigned long long*>(d_workspace);
+  if (int rc = launch_store_validate(d_tokens, d_offsets, n_docs, total_tokens, check_values, d_report, s)) return rc;
+  unsigned long long rep[4];
+  HRC_CHECK_CUDA(cudaMemcpyAsync(rep, d_report, sizeof(rep), cudaMemcpyDeviceToHost, s));
+  HRC_CHECK_CUDA(cudaStreamSynchronize(s));
+  const int64_t first_bad = rep[1] ? n_docs + 1 - int64_t(rep[1]) : -1;
+  if (report_out) {
+    report_out[0] = int64_t(rep[0]);
+    report_out[1] = first_bad;
+    report_out[2] = int64_t(rep[2]);
+    report_out[3] = int64_t(rep[3]);
+  }
+  if (rep[0]) {
+    set_error("store_validate: %llu offsets entries break the CSR contract (offsets[0] = 0, non-decreasing, "
+              "offsets[n_docs] = total_tokens = %lld); first at entry %lld", rep[0], (long long)total_tokens, (long long)first_bad);
+    return 3;
+  }
+  if (rep[2]) {
+    set_error("store_validate: %llu token values are NaN or infinite", rep[2]);
+    return 4;
+  }
+  return 0;
 }
 
 int hrc_read_probe(const void* d_buf, size_t bytes, uint32_t* d_out, void* stream) {

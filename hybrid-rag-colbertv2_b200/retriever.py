@@ -185,6 +185,7 @@ class JinaColBERTRetriever:
             self.store = PackedStore.from_packed(data['tokens'], data['offsets'], device=self.device,
                                                  doc_id_base=int(data.get('doc_id_base', 0)))
             self.corpus = data['corpus']
+            self._validate_loaded()
             return
         index_file = os.path.join(self.config.colbert_index_path, 'index.pt')
         data = torch.load(index_file, map_location="cpu")
@@ -194,6 +195,12 @@ class JinaColBERTRetriever:
         else:  # reference layout: dense fp32 [N, Ld, D], no mask
             self.store = PackedStore.from_dense(emb, data.get('lengths'), device=self.device)
         self.corpus = data['corpus']
+        self._validate_loaded()
+
+    def _validate_loaded(self) -> None:
+        """Index files come from outside the process: check them on the device once (offsets, no NaN / inf values)."""
+        if self.store.tokens.is_cuda:
+            self.store.validate()
 
     # ------------------------------------------------------------------------------------------
     # tensor-level API (additive): everything stays on the device

@@ -87,6 +87,13 @@ class PackedStore:
     def nbytes(self) -> int:
         return self.tokens.numel() * 2 + self.offsets.numel() * 8
 
+    def validate(self, check_values: bool = True) -> dict:
+        """On-device integrity check (hrc_store_validate): CSR offsets well-formed and, with check_values, no NaN /
+        infinite token value (one such row poisons the max of its document).  Raises ValueError; a CUDA store only.
+        Run once after loading a file — the reference's `load` (:748-753) trusts the file."""
+        from . import _lib
+        return _lib.store_validate(self.tokens, self.offsets, check_values=check_values)
+
     # ---- construction ------------------------------------------------------------------------
     @staticmethod
     def _validate(offsets_cpu: torch.Tensor, total: int, allow_empty: bool) -> None:
@@ -192,6 +199,7 @@ class PackedStore:
             secs = _lib.store_read_file(tok_file, t0 * DIM * 2, tokens, chunk_bytes) if t1 > t0 else 0.0
             store = cls(tokens, (off[d0:d1 + 1] - off[d0]).to(dev), meta.get("doc_id_base", 0) + d0)
             store.last_io_seconds = secs
+            store.validate()          # a truncated or corrupted token file must not be searched
             return store
         raw = np.fromfile(tok_file, dtype=np.int16, count=(t1 - t0) * DIM, offset=t0 * DIM * 2)
         tokens = torch.from_numpy(raw).view(torch.bfloat16).reshape(t1 - t0, DIM)

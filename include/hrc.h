@@ -82,6 +82,19 @@ int hrc_store_register(const void* d_tokens, int64_t total_tokens);
 void hrc_store_release(const void* d_tokens);
 
 /*
+ * Integrity check of a packed store, meant to run ONCE when an index is loaded or built (not on the search path): the
+ * scoring kernels trust the CSR offsets and the finiteness of the token rows.  Checks offsets[0] = 0, offsets
+ * non-decreasing, offsets[n_docs] = total_tokens, and (check_values != 0) streams the tokens once looking for NaN /
+ * infinite values.  d_workspace: >= 32 bytes of device memory, 8-byte aligned.  Synchronises the stream.
+ * report_out (host, optional, 4 x int64): [0] offending offsets entries, [1] index of the first one (-1 = none),
+ * [2] non-finite token values, [3] longest document in tokens.  Returns 0 = sound, 3 = offsets broken, 4 = non-finite
+ * values (hrc_last_error says which); the reference has no counterpart — torch.load at local_rag_complete.py:751-753
+ * trusts the file.
+ */
+int hrc_store_validate(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                       int check_values, void* d_workspace, size_t workspace_bytes, int64_t* report_out, void* stream);
+
+/*
  * MaxSim scores of every query against every document of the packed store.
  *   d_scores[q * n_docs + d] = sum_{i < lq} max_{t in doc d} <Q[q][i], tokens[t]>      (fp32 accumulate)
  * Replaces: JinaColBERTRetriever._maxsim_score, local_rag_complete.py:802-831 (as its docstring

@@ -1024,6 +1024,59 @@ def test_results_are_bitwise_repeatable(cuda_dev):
                     assert torch.equal(a, b), f"nq={nq} lq={lq}: results differ between runs"
 
 
+def test_two_host_threads_on_two_streams_share_one_retriever(cuda_dev):
+    """SURVEY §8(b) 'thread-safe per (device, stream)': two host threads drive ONE retriever on their own CUDA streams at
+    the same time (search, rerank, hybrid pipeline); each must get exactly what a single-threaded run returns.  Scratch is
+    per stream (_lib.Workspace), the TMA-descriptor cache is locked, the one-launch rerank's counter lives in the
+    caller's workspace."""
+    import threading
+
+    import hybrid_rag_colbertv2_b200 as hrc
+    q, tok, off = _case(77, 60_000, 8, 200, 6, 32)
+    cfg = hrc.RAGConfig(device=str(cuda_dev), colbert_top_k=100, rerank_candidates=50, final_top_k=10)
+    r = hrc.JinaColBERTRetriever(cfg)
+    r.store = hrc.PackedStore(tok.to(cuda_dev), off.to(cuda_dev))
+    idx = hrc.DualIndexer(cfg)
+    idx.colbert_retriever = r
+    h = hrc.HybridRetriever(cfg, idx, None, verbose=False)
+    q_d = q.to(cuda_dev)
+    g = torch.Generator().manual_seed(1)
+    cand = torch.randint(0, 60_000, (6, 50), generator=g, dtype=torch.int32).to(cuda_dev)
+    bm25 = torch.randint(0, 60_000, (6, 100), generator=g, dtype=torch.int32).to(cuda_dev)
+
+    def work(i):
+        qq = q_d[i:i + 1] if i % 2 == 0 else q_d[i:i + 3]          # fused doc-major search / batched kernel + streaming top-k
+        n = qq.shape[0]
+        return [r.search_keys(qq, 100), *r.rerank_ids(qq, cand[i:i + n], 10), *h.retrieve_batch(qq, bm25[i:i + n])]
+
+    expect = [[t.clone() for t in work(i)] for i in range(4)]
+    torch.cuda.synchronize()
+    errors = []
+
+    def run(tid):
+        try:
+            torch.cuda.set_device(cuda_dev)
+            with torch.cuda.stream(torch.cuda.Stream(cuda_dev)):
+                for it in range(60):
+                    i = (it + 2 * tid) % 4
+                    got = work(i)
+                    torch.cuda.current_stream().synchronize()
+                    for a, b in zip(got, expect[i]):
+                        if not torch.equal(a, b):
+                            errors.append(f"thread {tid}, iteration {it}, case {i}: result differs")
+                            return
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"thread {tid}: {e!r}")
+
+    threads = [threading.Thread(target=run, args=(t,)) for t in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert len(r._workspace.bufs) >= 3, "expected one scratch buffer per stream"
+
+
 # ======================================================================================================
 # SURVEY §8(f) rows 2 and 3 on the device: streamed native store, encoder hook on CUDA
 # ======================================================================================================
@@ -1062,6 +1115,50 @@ def test_native_store_streams_to_disk_and_back_by_shard(cuda_dev, tmp_path):
         with open(os.path.join(path, "tokens.bf16.bin"), "r+b") as f:
             f.truncate(store.total_tokens * 256 - 4096)
         hrc.PackedStore.load(path, device=cuda_dev)
+
+
+def test_store_validate_catches_broken_offsets_and_non_finite_values(cuda_dev, tmp_path):
+    """hrc_store_validate (run by PackedStore.load / JinaColBERTRetriever.load on every file they read): the CSR contract
+    and the finiteness of the token values are checked on the device against a host restatement."""
+    import hybrid_rag_colbertv2_b200 as hrc
+    L = _lib()
+    q, tok, off = _case(91, 5000, 0, 300, 1, 32)
+    tok_d, off_d = tok.to(cuda_dev), off.to(cuda_dev)
+    rep = L.store_validate(tok_d, off_d)
+    assert rep["longest_doc_tokens"] == int((off[1:] - off[:-1]).max())
+    assert L.store_validate(torch.zeros((0, 128), dtype=torch.bfloat16, device=cuda_dev),
+                            torch.zeros(1, dtype=torch.int64, device=cuda_dev))["longest_doc_tokens"] == 0
+    def first_bad(o, total):                                          # host restatement of the CSR contract
+        n = o.numel() - 1
+        for i in range(n + 1):
+            v = int(o[i])
+            ok = 0 <= v <= total and (i != 0 or v == 0) and (i != n or v == total) and (i == n or int(o[i + 1]) >= v)
+            if not ok:
+                return i
+        return -1
+
+    assert first_bad(off, int(off[-1])) == -1
+    for entry, value in ((0, 1), (5000, int(off[-1]) - 1), (1234, int(off[1235]) + 1), (77, -3), (4000, int(off[-1]) + 5)):
+        bad = off.clone()
+        bad[entry] = value
+        first = first_bad(bad, int(off[-1]))
+        assert first >= 0
+        with pytest.raises(ValueError, match=f"first at entry {first}\\b"):
+            L.store_validate(tok_d, bad.to(cuda_dev), check_values=False)
+    for row, col, v in ((0, 0, float("nan")), (int(off[-1]) - 1, 127, float("inf")), (31_337, 64, float("-inf"))):
+        poisoned = tok_d.clone()
+        poisoned[row, col] = v
+        with pytest.raises(ValueError, match="1 token values are NaN or infinite"):
+            L.store_validate(poisoned, off_d)
+        L.store_validate(poisoned, off_d, check_values=False)          # offsets alone are sound
+    # a native store whose token file was damaged after it was written is refused at load time
+    st = hrc.PackedStore(tok_d, off_d)
+    st.save(str(tmp_path / "store"))
+    with open(tmp_path / "store" / "tokens.bf16.bin", "r+b") as f:
+        f.seek(256 * 4321 + 10)
+        f.write(b"\x80\x7f")                                          # bf16 +inf
+    with pytest.raises(ValueError, match="NaN or infinite"):
+        hrc.PackedStore.load(str(tmp_path / "store"), device=cuda_dev, allow_empty=True)
 
 
 class _WordTokenizer:
