@@ -481,6 +481,9 @@ def run_ours(args):
                                "ms_per_step": r5["ms_per_step"], "docs_per_s": args.c5_global_docs / (r5["ms_per_step"] * 1e-3),
                                "kernel_ms": r5["kernel_ms"], "per_gpu_GBps": gbs, "frac_hbm_copy_peak": gbs / hbm_peak,
                                "frac_of_nominal_7.7TBps": gbs / 7700.0, "clocks": r5.get("clocks"), "parity_check": pc5}
+            if "c4" in want:
+                secondary["c4_sharded"] = bench_c4_sharded(torch, hrc, _lib, retr, searcher, dev, synth_queries, timed_loop,
+                                                           args.c5_global_docs, world)
         else:
             secondary["c5"] = {"skipped": f"{per_rank_gb:.0f} GB per GPU does not fit at N={world}"}
 
@@ -577,6 +580,31 @@ def bench_c4(torch, hrc, _lib, retr, dev, synth_queries):
     return out
 
 
+def bench_c4_sharded(torch, hrc, _lib, retr, searcher, dev, synth_queries, timed_loop, n_global, world):
+    """C4 over the C5 corpus (N > 1): the hybrid pipeline with the corpus sharded by documents — global ColBERT top-100
+    (local search + exchange + merge) -> RRF with the given BM25 lists (global ids) -> every rank scores the candidates
+    it owns -> exchange + merge of the rerank keys; one C call per rank and query (hrc_sharded_hybrid_retrieve).
+    parity_check: the library's result equals the same stages done with torch.distributed collectives, on every rank."""
+    n_queries = 100
+    queries = synth_queries(n_queries, LQ, seed=SEED + 12, device=dev)
+    g = torch.Generator().manual_seed(5)                          # same lists on every rank
+    bm25 = torch.randint(0, n_global, (n_queries, 100), generator=g, dtype=torch.int32).to(dev)
+    r = timed_loop(lambda i: searcher.retrieve_batch(queries[i:i + 1], bm25[i:i + 1], top_k_final=10), n_queries - 3, 3)
+    cross = hrc.ShardedSearcher(retr, transport="torch")
+    same = True
+    for i in (0, 7, 50):
+        a_ids, a_sc = searcher.retrieve_batch(queries[i:i + 2], bm25[i:i + 2], top_k_final=10)
+        b_ids, b_sc = cross.retrieve_batch(queries[i:i + 2], bm25[i:i + 2], top_k_final=10)
+        same = same and bool(torch.equal(a_ids, b_ids)) and bool(torch.equal(a_sc, b_sc))
+    flag = torch.tensor([1 if same else 0], device=dev)
+    torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+    return {"what": f"C4 hybrid pipeline over the C5 corpus ({n_global} passages x {DOC_LEN} tokens on {world} GPUs), "
+                    f"{n_queries - 3} queries one at a time: hrc_sharded_hybrid_retrieve (transport {searcher.transport})",
+            "ms_per_query": r["ms_per_step"], "queries_per_s": 1e3 / r["ms_per_step"], "kernel_ms": r["kernel_ms"],
+            "launches_per_query": r["launches"] / max(1, n_queries - 3),
+            "parity_check": "ok" if bool(flag[0]) else "library result differs from the torch.distributed cross-check"}
+
+
 def bench_c3(torch, _lib, retr, rag, dev, synth_queries, tf_sus, tf_burst, timed_loop):
     """C3: 256 queries x 32 tokens over 1M passages of 32..512 tokens — the tensor-bound config."""
     nq = 256
@@ -613,6 +641,16 @@ def bench_c1(torch, _lib, retr, rag, dev, queries):
     us_api = cuda_time(torch, lambda: retr.rerank_ids(q, cand, k=10), 200) * 1e3
     out["rerank_ids_us"] = us_api
     out["docs_per_s"] = 50 / (us_api * 1e-6)
+    # the same launch replayed from a CUDA graph (GraphedRerank: inputs written in place, no Python / ctypes per call)
+    import hybrid_rag_colbertv2_b200 as hrc
+    plan = hrc.GraphedRerank(retr, 1, 50, k=10)
+    plan.queries.copy_(q)
+    plan.candidates.copy_(cand)
+    want = [t.clone() for t in retr.rerank_ids(q, cand, k=10)]
+    got = plan.run()
+    torch.cuda.synchronize()
+    out["graph_replay_us"] = cuda_time(torch, plan.run, 200) * 1e3
+    out["graph_replay_equals_direct_call"] = all(bool(torch.equal(a, b)) for a, b in zip(got, want))
     return out
 
 

@@ -296,11 +296,12 @@ class JinaColBERTRetriever:
                                     path=_knob(self.config, "maxsim_path"), copy=copy)
         return ids, self._finish_scores(sc, q.shape[1])
 
-    def rerank_ids(self, query_embeddings: torch.Tensor, candidate_ids: torch.Tensor, k: int = 10
-                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    def rerank_ids(self, query_embeddings: torch.Tensor, candidate_ids: torch.Tensor, k: int = 10,
+                   workspace: Optional["_lib.Workspace"] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """Rerank stored documents by id without re-encoding them.
 
-        candidate_ids: int [Bq, C] (local ids of this store; negative = absent).
+        candidate_ids: int [Bq, C] (local ids of this store; negative = absent).  `workspace`: device scratch to use
+        instead of the retriever's own (per stream).
         Returns (result_index int32 [Bq, k'], doc ids int32 [Bq, k'], scores fp32 [Bq, k']).
         """
         self._require_store()
@@ -325,7 +326,8 @@ class JinaColBERTRetriever:
             pos, top_scores = self._sort_large(cs, k_eff)
             return pos, torch.gather(cand, 1, pos.long()), self._finish_scores(top_scores, q.shape[1])
         pos, doc_ids, top_scores, _ = _lib.rerank(self.store.tokens, self.store.offsets, cand, q, k_eff,
-                                                  path=_knob(self.config, "maxsim_path"), workspace=self._workspace)
+                                                  path=_knob(self.config, "maxsim_path"),
+                                                  workspace=self._workspace if workspace is None else workspace)
         return pos, doc_ids, self._finish_scores(top_scores, q.shape[1])
 
     def _require_store(self) -> None:
@@ -416,6 +418,47 @@ def install(module, classes: Sequence[str] = ("JinaColBERTRetriever",), score_mo
         if not hasattr(module, name):
             raise AttributeError(f"install: {module.__name__} has no {name}")
         setattr(module, name, mine[name])
+
+
+class GraphedRerank:
+    """`rerank_ids` for a FIXED shape, captured once in a CUDA graph and replayed (additive API).
+
+    A rerank of 50 candidates is 12 us of device work behind ~22 us of Python + ctypes + launch set-up; a graph replay
+    removes the host side.  The caller writes its inputs IN PLACE into `queries` (bf16 [Bq, Lq, 128]) and
+    `candidates` (int32 [Bq, C] local doc ids, negative = absent) — e.g. the encoder's output buffer and the RRF
+    kernel's id buffer — then calls `run()`; `result_index`, `doc_ids` and `scores` ([Bq, k]) are this object's
+    buffers, overwritten by the next `run()` (stream-ordered on the stream `run()` is called on).  The graph holds
+    the store's addresses: it refuses to run once the retriever's store has been replaced.
+
+        plan = hrc.GraphedRerank(retriever, n_queries=1, n_candidates=50, k=10)
+        plan.queries.copy_(q); plan.candidates.copy_(ids); pos, doc_ids, scores = plan.run()
+    """
+
+    def __init__(self, retriever: "JinaColBERTRetriever", n_queries: int, n_candidates: int, k: int = 10, lq: int = 32):
+        retriever._require_store()
+        if retriever._literal():
+            raise ValueError("GraphedRerank scores with MaxSim; score_mode='reference_literal' is a characterisation mode")
+        dev = retriever.device
+        self.retriever, self._store = retriever, retriever.store
+        self.queries = torch.zeros((n_queries, lq, DIM), dtype=torch.bfloat16, device=dev)
+        self.candidates = torch.full((n_queries, n_candidates), -1, dtype=torch.int32, device=dev)
+        self._scratch = _lib.Workspace()        # the graph's own: its address is baked into the captured launch
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            retriever.rerank_ids(self.queries, self.candidates, k, workspace=self._scratch)     # warm-up: descriptors, scratch
+            side.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self.result_index, self.doc_ids, self.scores = retriever.rerank_ids(self.queries, self.candidates, k,
+                                                                                    workspace=self._scratch)
+        torch.cuda.current_stream(dev).wait_stream(side)
+
+    def run(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        if self.retriever.store is not self._store:
+            raise RuntimeError("GraphedRerank: the retriever's store was replaced after capture; build a new plan")
+        self.graph.replay()
+        return self.result_index, self.doc_ids, self.scores
 
 
 class DualIndexer:

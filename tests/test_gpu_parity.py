@@ -1024,6 +1024,75 @@ def test_results_are_bitwise_repeatable(cuda_dev):
                     assert torch.equal(a, b), f"nq={nq} lq={lq}: results differ between runs"
 
 
+def test_entry_points_are_cuda_graph_capturable(cuda_dev):
+    """The device-pointer entry points neither allocate nor synchronise, so a caller can capture them in a CUDA graph
+     and replay it on new query contents written in place: search, one-launch rerank and the
+    whole hybrid pipeline, replayed 3 times each, must equal the direct calls bit for bit."""
+    L = _lib()
+    q, tok, off = _case(55, 30_000, 8, 200, 5, 32)
+    tok_d, off_d = tok.to(cuda_dev), off.to(cuda_dev)
+    g = torch.Generator().manual_seed(2)
+    cands = torch.randint(0, 30_000, (5, 50), generator=g, dtype=torch.int32).to(cuda_dev)
+    bm25s = torch.randint(0, 30_000, (5, 100), generator=g, dtype=torch.int32).to(cuda_dev)
+    q_all = q.to(cuda_dev)
+    for nq in (1, 2):
+        q_in = q_all[:nq].clone()                                   # static inputs of the graph
+        cand_in, bm_in = cands[:nq].clone(), bm25s[:nq].clone()
+        ws = [L.Workspace() for _ in range(3)]
+
+        def calls():
+            keys, ids, sc = L.search(tok_d, off_d, q_in, 100, workspace=ws[0])
+            pos, rid, rsc, _ = L.rerank(tok_d, off_d, cand_in, q_in, 10, workspace=ws[1])
+            hid, hsc = L.hybrid_retrieve(tok_d, off_d, q_in, bm_in, colbert_k=100, rrf_k=60, n_candidates=50, final_k=10,
+                                         workspace=ws[2])
+            return [keys, ids, sc, pos, rid, rsc, hid, hsc]
+
+        side = torch.cuda.Stream(cuda_dev)
+        with torch.cuda.stream(side):
+            calls()                                                  # warm-up: descriptors encoded, scratch grown
+            side.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                outs = calls()
+        torch.cuda.synchronize()
+        for shift in (0, 1, 3):
+            q_in.copy_(q_all[shift:shift + nq])
+            cand_in.copy_(cands[shift:shift + nq])
+            bm_in.copy_(bm25s[shift:shift + nq])
+            torch.cuda.synchronize()
+            graph.replay()
+            torch.cuda.synchronize()
+            got = [t.clone() for t in outs]
+            want = calls()
+            torch.cuda.synchronize()
+            for a, b in zip(got, want):
+                assert torch.equal(a, b), f"nq={nq} shift={shift}: graph replay differs from the direct call"
+
+
+def test_graphed_rerank_equals_rerank_ids(cuda_dev):
+    """hrc.GraphedRerank: the fixed-shape, CUDA-graph form of rerank_ids returns what rerank_ids returns for every new
+    input written in place, and refuses to run against a replaced store."""
+    import hybrid_rag_colbertv2_b200 as hrc
+    q, tok, off = _case(56, 20_000, 8, 300, 6, 32)
+    r = hrc.JinaColBERTRetriever(hrc.RAGConfig(device=str(cuda_dev)))
+    r.store = hrc.PackedStore(tok.to(cuda_dev), off.to(cuda_dev))
+    g = torch.Generator().manual_seed(8)
+    cands = torch.randint(-1, 20_000, (6, 50), generator=g, dtype=torch.int32).to(cuda_dev)
+    q_d = q.to(cuda_dev)
+    for nq in (1, 3):
+        plan = hrc.GraphedRerank(r, nq, 50, k=10)
+        for shift in range(3):
+            plan.queries.copy_(q_d[shift:shift + nq])
+            plan.candidates.copy_(cands[shift:shift + nq])
+            got = [t.clone() for t in plan.run()]
+            want = r.rerank_ids(q_d[shift:shift + nq], cands[shift:shift + nq], 10)
+            for a, b in zip(got, want):
+                assert torch.equal(a, b), f"nq={nq} shift={shift}"
+    r.store = hrc.PackedStore(tok.to(cuda_dev), off.to(cuda_dev))
+    with pytest.raises(RuntimeError, match="store was replaced"):
+        plan.run()
+
+
 def test_two_host_threads_on_two_streams_share_one_retriever(cuda_dev):
     """SURVEY §8(b) 'thread-safe per (device, stream)': two host threads drive ONE retriever on their own CUDA streams at
     the same time (search, rerank, hybrid pipeline); each must get exactly what a single-threaded run returns.  Scratch is
