@@ -9,7 +9,8 @@
  *                          PARITY ONLY PARTLY PINNED BY THE REFERENCE (its body :819-829 is a mean-pool cosine; it
  *                          ships no tests): bit-equal to the unmodified reference where that cosine IS MaxSim
  *                          (tests/golden/maxsim_pin.npz), within 2e-6 of float64 known answers
- *                          (maxsim_kat_f64.npz), cross-checked against the Python oracle.
+ *                          (maxsim_kat_f64.npz) and of scores vLLM 0.22.0's own MaxSim functions produced
+ *                          (maxsim_vllm_pin.npz, tests/golden/make_vllm_pin.py), cross-checked against the Python oracle.
  *   oracle_literal_scores  the BODY of _maxsim_score as coded, :821-829: cosine of the mean-pooled token vectors
  *                          (fp32 accumulation in index order; torch reduces in a different order, so this agrees
  *                          with the reference's vectors to ~1e-6, not bit for bit).  PINNED on

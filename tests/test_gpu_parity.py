@@ -777,6 +777,27 @@ def test_maxsim_kernels_match_float64_known_answers(cuda_dev, golden_dir, path):
         _assert_scores(got, torch.from_numpy(z[f"{name}_scores_f64"]).float(), f"kat {name} {path}", bucket="kat_f64")
 
 
+@pytest.mark.parametrize("path", ["tc", "simt", "tc_dm", "auto"])
+def test_maxsim_kernels_match_vllm_outputs(cuda_dev, golden_dir, path):
+    """The CUDA kernels against scores vLLM 0.22.0's MaxSim functions produced (tests/golden/make_vllm_pin.py): an
+    implementation neither this repo's oracle nor its kernels had a hand in.  Also through the one-call search: the
+    top-10 it returns are vLLM's top-10 in vLLM's order (gaps permitting)."""
+    from golden.make_vllm_pin import load_pin
+    L = _lib()
+    z = load_pin(os.path.join(golden_dir, "maxsim_vllm_pin.npz"))
+    tok_d = torch.from_numpy(z["tok"]).to(torch.bfloat16).to(cuda_dev)
+    off_d = torch.from_numpy(z["off"]).to(cuda_dev)
+    for name in ("q32", "q7", "q1"):
+        q, pair, _ = z[name]
+        q_d = torch.from_numpy(q).to(torch.bfloat16).to(cuda_dev)
+        got = L.maxsim_scores(tok_d, off_d, q_d, path=_path(L, path))
+        _assert_scores(got, torch.from_numpy(pair), f"vllm pin {name} {path}", bucket="vllm_pin")
+        _, ids, sc = L.search(tok_d, off_d, q_d, 10, path=_path(L, path))
+        for b in range(q.shape[0]):
+            err = o.check_ranking(ids[b].tolist(), sc[b].tolist(), torch.from_numpy(pair[b]), 10, TIGHT)
+            assert err is None, f"{name} {path} query {b}: {err}"
+
+
 def test_search_host_results_belong_to_the_caller(cuda_dev):
     """two consecutive search_host results held at once must not alias (pinned staging is reused)."""
     import hybrid_rag_colbertv2_b200 as hrc

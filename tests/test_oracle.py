@@ -93,6 +93,24 @@ def test_maxsim_oracle_matches_float64_known_answers(golden_dir):
         assert np.abs(naive - exp).max() <= 2e-6 * np.abs(exp).max(), name
 
 
+def test_maxsim_oracle_matches_vllm_outputs(golden_dir):
+    """maxsim_vllm_pin.npz: scores produced by vLLM 0.22.0's own ColBERT scoring functions (compute_maxsim_score and
+    compute_maxsim_score_batched; tests/golden/make_vllm_pin.py) — an implementation of MaxSim this repo did not write.
+    The oracle must reproduce them on ragged documents around every chunk / tile boundary, for 32-, 7- and 1-token queries."""
+    from golden.make_vllm_pin import load_pin
+    z = load_pin(os.path.join(golden_dir, "maxsim_vllm_pin.npz"))
+    assert z["vllm_version"] == "0.22.0"
+    tok, off = torch.from_numpy(z["tok"]), torch.from_numpy(z["off"])
+    for name in ("q32", "q7", "q1"):
+        q, pair, batched = z[name]
+        got = o.maxsim_scores(torch.from_numpy(q), tok, off).numpy()
+        for exp in (pair, batched):
+            assert np.abs(got - exp).max() <= 2e-6 * np.abs(exp).max(), name
+        if name != "q32":                                   # the triple loop is slow: the 7- and 1-token queries only
+            naive = o.maxsim_naive(q, z["tok"], z["off"])
+            assert np.abs(naive - pair).max() <= 2e-6 * np.abs(pair).max(), name
+
+
 def test_rrf_reference_matches_reference_outputs(golden_dir):
     cases = json.load(open(os.path.join(golden_dir, "rrf.json")))
     assert len(cases) >= 8

@@ -62,6 +62,19 @@ def test_c_maxsim_pinned_by_reference_and_float64_vectors(clib, golden_dir):
         assert np.abs(out - k[f"{name}_scores_f64"]).max() <= 2e-6 * np.abs(k[f"{name}_scores_f64"]).max()
 
 
+def test_c_maxsim_matches_vllm_outputs(clib, golden_dir):
+    """The C restatement against the vectors vLLM's MaxSim functions produced (maxsim_vllm_pin.npz)."""
+    from golden.make_vllm_pin import load_pin
+    z = load_pin(os.path.join(golden_dir, "maxsim_vllm_pin.npz"))
+    tok, off = np.ascontiguousarray(z["tok"]), np.ascontiguousarray(z["off"])
+    for name in ("q32", "q7", "q1"):
+        q, pair, _ = z[name]
+        q = np.ascontiguousarray(q)
+        out = np.empty(pair.shape, dtype=np.float32)
+        clib.oracle_maxsim_scores(_p(q), q.shape[0], q.shape[1], _p(tok), _p(off), ctypes.c_int64(len(off) - 1), _p(out))
+        assert np.abs(out - pair).max() <= 2e-6 * np.abs(pair).max(), name
+
+
 def test_c_literal_matches_reference_outputs(clib, golden_dir):
     """The C restatement of what the reference's `_maxsim_score` literally computes, against the vectors the
     unmodified reference produced (both fixtures)."""
