@@ -504,7 +504,7 @@ def run_ours(args):
         "step_ms": head["step_ms"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic["bytes_per_launch"] if traffic else None,
-                     "kernel": "maxsim_tc_kernel<MT=1,ZP=1,CG=1>", "kernel_ms": kernel_ms,
+                     "kernel": "maxsim_dm_kernel<TK=1> (doc-major single-query MaxSim, top-k fused into the epilogue)", "kernel_ms": kernel_ms,
                      "kernel_ms_per_step": head["kernel_ms"], "kernel_launches_per_step": head["kernel_launches_per_step"],
                      "kernel_timing": "CUDA events around the kernel's launches INSIDE the timed steps (hrc_trace_*), "
                                       "mean over the same steps as ms_per_step",

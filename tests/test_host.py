@@ -37,6 +37,16 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert _lib.topk_workspace_bytes(1_000_000, 1, 1000) > 123 * 1000 * 8          # radix select (k > 128)
 
 
+def test_integration_guide_names_every_declared_symbol():
+    """INTEGRATION.md's symbol table (what each entry point replaces in the reference) stays in step with include/hrc.h."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "hrc.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    names = sorted(set(re.findall(r"\b(hrc_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 40
+    assert [n for n in names if n not in doc] == []
+
+
 def test_no_cpu_fallback():
     """The product path must fail loudly without the CUDA device, never fall back."""
     tok = torch.zeros((8, 128), dtype=torch.bfloat16)
