@@ -103,12 +103,6 @@ static int check_device() {
 // kernel organisation for one query (maxsim_tc.cu: 0 query-major, 2 doc-major, 3 auto)
 static int tc_variant(int path) { return path == HRC_PATH_TC_DM ? 2 : (path == HRC_PATH_AUTO ? 3 : 0); }
 
-// bytes of caller workspace one scoring call needs (only queries longer than 32 tokens on the tensor-core path)
-static size_t maxsim_ws_bytes(int64_t n_items, int n_queries, int lq, int path) {
-  if (path == HRC_PATH_SIMT) return 0;
-  return maxsim_tc_workspace_bytes(n_items, n_queries, lq);
-}
-
 static int maxsim_dispatch(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
                            const int32_t* d_cand_ids, int64_t n_items, const void* d_queries, int n_queries, int lq,
                            float* d_scores, int path, void* d_workspace, size_t workspace_bytes, cudaStream_t stream) {

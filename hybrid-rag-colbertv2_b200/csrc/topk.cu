@@ -278,7 +278,7 @@ select_keys_kernel(const uint64_t* __restrict__ keys_in, int n_in, int k, uint64
 // The cost is the HBM read of the scores: C3's 256 x 1M matrix (1 GB) in ~0.3 ms, where the radix select took 3.9 ms.
 constexpr int kStreamThreads = 256;
 constexpr int kStreamWarps = kStreamThreads / 32;
-constexpr int kStreamMaxChunks = kMergeMax / kKeyListOut;      // chunk lists per row the merge level can take (192)
+static_assert(64 * kKeyListOut <= kMergeMax, "stream_chunks' 64 lists per row must fit the merge level");
 
 __host__ __device__ inline int stream_chunks(int64_t n, int n_rows) {
   int64_t want = (2 * 148 + n_rows - 1) / n_rows;              // ~2 CTAs per SM over all rows ...
