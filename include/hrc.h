@@ -13,6 +13,10 @@
  *   - every pointer named d_* is DEVICE memory owned by the caller, valid on the current device.
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy stream).
  *   - return value: 0 = ok, non-zero = error; hrc_last_error() returns a thread-local message.
+ *   - threads: any number of host threads may call concurrently as long as calls that share a workspace (or output
+ *     buffers) are ordered on one stream; the library's own state (descriptor cache, trace, launch counter) is locked
+ *     or atomic.  Calls that take device pointers neither allocate nor synchronise, so they can be captured in a
+ *     CUDA graph; the *_host entry points, hrc_store_validate, the file IO and the trace collector synchronise.
  *   - token embeddings are bf16, HRC_DIM (=128) wide, rows L2-normalised by the caller.
  *   - corpus layout: packed, padding-free  d_tokens[total_tokens][128]  plus CSR  d_offsets[n_docs+1]
  *     (int64, d_offsets[0] == 0, d_offsets[n_docs] == total_tokens).
