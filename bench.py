@@ -739,7 +739,9 @@ def sharded_breakdown(torch, dist, hrc, _lib, retr, searcher, queries, dev, max_
     out["overhead_us"] = out[f"exchange_merge_{searcher.transport}_us"]
     out["transport"] = searcher.transport
     out["note"] = ("each part timed alone, 20 reps back to back; exchange = k x 8 bytes per rank; nccl = ncclAllGather + merge "
-                   "kernel, p2p = push kernel (peer stores + release flag) + merge kernel (acquires the flags), both inside libhrc")
+                   "kernel, p2p = push kernel (peer stores + release flag) + merge kernel (acquires the flags), both inside libhrc; "
+                   "step_p2p_us is the whole sharded search with the exchange FUSED into the search's final selection kernel "
+                   "(peer stores, flags, wait, merge: 2 launches per search, scripts/check_sharded_nccl.py small_shard_step_us)")
     return out
 
 

@@ -62,7 +62,9 @@ void set_stages(int);
 size_t topk_workspace_bytes(int64_t, int, int);
 int launch_topk(const float*, const int32_t*, int64_t, int, int, int32_t, uint64_t*, void*, size_t, cudaStream_t,
                 int32_t* = nullptr, float* = nullptr);
-int launch_topk_merge(const uint64_t*, int, int, int, uint64_t*, cudaStream_t, int32_t* = nullptr, float* = nullptr, int = 0);
+int launch_topk_merge(const uint64_t*, int, int, int, uint64_t*, cudaStream_t, int32_t* = nullptr, float* = nullptr, int = 0,
+                      const KeyExchange* = nullptr);
+bool topk_exchange_supported(int n_rows, int k, int world, int max_keys);
 bool tc_topk_supported(int64_t, int, int, int);
 bool tc_rerank_supported(int64_t, int, int, int);
 int launch_maxsim_tc_rerank(const void*, const int64_t*, int64_t, int64_t, const int32_t*, int, const void*, int, int, int,
@@ -320,6 +322,27 @@ size_t hrc_search_workspace_bytes(int64_t n_docs, int64_t total_tokens, int n_qu
 int hrc_search(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens, const void* d_queries,
                int n_queries, int lq, int k, int32_t id_base, void* d_workspace, size_t workspace_bytes,
                uint64_t* d_keys_out, int32_t* d_ids_out, float* d_scores_out, int path, void* stream) {
+  return hrc::search_with_exchange(d_tokens, d_offsets, n_docs, total_tokens, d_queries, n_queries, lq, k, id_base,
+                                   d_workspace, workspace_bytes, d_keys_out, d_ids_out, d_scores_out, path, stream, nullptr);
+}
+
+}  // extern "C"
+
+namespace hrc {
+
+// Can a sharded search hand the exchange to the search's own final kernel?  (one query on the fused-top-k route)
+bool search_exchange_supported(int64_t n_docs, int64_t total_tokens, int n_queries, int lq, int k, int path, int world,
+                               int max_keys) {
+  return k >= 1 && k <= n_docs && search_is_fused(total_tokens, n_queries, lq, k, path) &&
+         topk_exchange_supported(n_queries, k, world, max_keys);
+}
+
+// hrc_search; with `xch` the final selection kernel also exchanges the keys with the other ranks over peer memory and
+// the outputs are the GLOBAL top-k (comm.cu: hrc_sharded_search, P2P transport).
+int search_with_exchange(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                         const void* d_queries, int n_queries, int lq, int k, int32_t id_base, void* d_workspace,
+                         size_t workspace_bytes, uint64_t* d_keys_out, int32_t* d_ids_out, float* d_scores_out, int path,
+                         void* stream, const KeyExchange* xch) {
   if (int rc = check_device()) return rc;
   HRC_REQUIRE(n_queries >= 0 && lq >= 1 && k >= 0 && k <= n_docs, "search: k=%d must be in [0, n_docs]", k);
   if (n_queries == 0 || k == 0) return 0;
@@ -339,8 +362,9 @@ int hrc_search(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, i
                                        nullptr, cand, tc_variant(path), st))
       return rc;
     return launch_topk_merge(cand, L.n_seg * tc_topk_list_len(), n_queries, k, d_keys_out, st, d_ids_out, d_scores_out,
-                             tc_topk_list_len());
+                             tc_topk_list_len(), xch);
   }
+  HRC_REQUIRE(xch == nullptr, "search: the fused exchange needs the fused top-k route");
   float* scores = reinterpret_cast<float*>(ws + L.scores);
   if (int rc = maxsim_dispatch(d_tokens, d_offsets, n_docs, total_tokens, nullptr, n_docs, d_queries, n_queries, lq,
                                scores, path, ws + L.part, L.part_bytes, st))
@@ -348,6 +372,10 @@ int hrc_search(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, i
   return launch_topk(scores, nullptr, n_docs, n_queries, k, id_base, d_keys_out, ws + L.topk, L.topk_bytes, st, d_ids_out,
                      d_scores_out);
 }
+
+}  // namespace hrc
+
+extern "C" {
 
 size_t hrc_search_host_workspace_bytes(int64_t n_docs, int64_t total_tokens, int n_queries, int lq, int k, int path) {
   if (n_docs < 0 || total_tokens < 0 || n_queries < 0 || lq < 1 || k < 0) return 0;

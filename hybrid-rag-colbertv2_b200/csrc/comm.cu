@@ -31,6 +31,7 @@ namespace hrc {
 int launch_topk_merge_parts(const uint64_t*, int, int, int, int, uint64_t*, cudaStream_t, int32_t*, float*, const uint64_t*,
                             uint64_t, int, uint64_t);
 int launch_keys_unpack(const uint64_t*, int64_t, int32_t*, float*, cudaStream_t);
+uint64_t get_watchdog_ns();
 int launch_rerank_unpack(const uint64_t*, int, int, const int32_t*, int, int32_t*, int32_t*, float*, cudaStream_t);
 int launch_rrf(const int32_t*, int, const int32_t*, int, int, int, int, int32_t*, double*, int32_t*, cudaStream_t);
 
@@ -72,8 +73,6 @@ int load_nccl() {
     }                                                                                                  \
   } while (0)
 
-constexpr int kMaxWorld = 16;
-
 }  // namespace
 
 struct Comm {
@@ -90,9 +89,9 @@ struct Comm {
 
 namespace {
 
-constexpr size_t kFlagBytes = 2 * kMaxWorld * sizeof(uint64_t);
+constexpr size_t kFlagBytes = kExchangeFlagBytes;
 __host__ __device__ inline size_t slot_offset(int parity, int src_rank, int world, int max_keys) {
-  return kFlagBytes + (size_t(parity) * world + src_rank) * size_t(max_keys) * sizeof(uint64_t);
+  return exchange_slot_offset(parity, src_rank, world, max_keys);
 }
 
 // One CTA per destination rank: copy this rank's keys into slot[parity][my_rank] of the destination's receive buffer,
@@ -375,6 +374,23 @@ int hrc_sharded_search(hrc_comm_t* comm, int transport, const void* d_tokens, co
   uint8_t* ws = static_cast<uint8_t*>(d_workspace);
   uint64_t* local = reinterpret_cast<uint64_t*>(ws + L.local);
   const int k_local = int(n_docs < k ? n_docs : k);       // a shard with fewer than k documents pads with empty slots
+  if (transport == HRC_TRANSPORT_P2P && c->p2p && k_local == k &&
+      search_exchange_supported(n_docs, total_tokens, n_queries, lq, k, path, c->world, c->max_keys)) {
+    // ONE query over peer memory: the search's final selection kernel stores this GPU's top-k into every rank's slot,
+    // waits for the others' and emits the global top-k itself — two launches, like a single-GPU search.  A rank that
+    // takes the separate push + merge kernels below (small shard, other route) speaks the same slot / flag protocol.
+    KeyExchange x;
+    x.peers = c->d_peer;
+    x.local = c->local;
+    x.world = c->world;
+    x.my_rank = c->rank;
+    x.max_keys = c->max_keys;
+    x.seq = ++c->seq;
+    x.parity = int(x.seq & 1);
+    x.watchdog_ns = get_watchdog_ns();
+    return search_with_exchange(d_tokens, d_offsets, n_docs, total_tokens, d_queries, n_queries, lq, k, id_base, ws + L.search,
+                                L.search_bytes, d_keys_out, d_ids_out, d_scores_out, path, stream, &x);
+  }
   if (k_local < k) HRC_CHECK_CUDA(cudaMemsetAsync(local, 0, size_t(n_queries) * k * sizeof(uint64_t), st));
   if (k_local > 0) {
     // (a shard smaller than k writes rows of k_local keys; re-spread them to rows of k below)

@@ -80,6 +80,32 @@ __host__ __device__ __forceinline__ float key_score(uint64_t key) {
   return orderable_to_float(uint32_t(key >> 32));
 }
 
+// ---------------------------------------------------------------------------------------------
+// multi-GPU key exchange over peer memory (comm.cu owns the buffers; the final selection kernel of a search can do the
+// exchange itself: topk.cu).  A rank's receive buffer: flags[2][kMaxWorld] (u64 step numbers), then
+// slots[2][world][max_keys] (u64 keys); the two halves alternate by step parity.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxWorld = 16;
+constexpr size_t kExchangeFlagBytes = 2 * kMaxWorld * sizeof(uint64_t);
+__host__ __device__ inline size_t exchange_slot_offset(int parity, int src_rank, int world, int max_keys) {
+  return kExchangeFlagBytes + (size_t(parity) * world + src_rank) * size_t(max_keys) * sizeof(uint64_t);
+}
+struct KeyExchange {
+  uint8_t* const* peers = nullptr;   // device table: every rank's receive buffer as mapped on THIS GPU (peers[my_rank] = local)
+  const uint8_t* local = nullptr;    // this rank's receive buffer
+  int world = 0, my_rank = 0, max_keys = 0, parity = 0;
+  unsigned long long seq = 0;        // step number published in the flags
+  unsigned long long watchdog_ns = 0;
+};
+
+// capi.cu: hrc_search whose final selection kernel also does the exchange (outputs = the GLOBAL top-k)
+bool search_exchange_supported(int64_t n_docs, int64_t total_tokens, int n_queries, int lq, int k, int path, int world,
+                               int max_keys);
+int search_with_exchange(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
+                         const void* d_queries, int n_queries, int lq, int k, int32_t id_base, void* d_workspace,
+                         size_t workspace_bytes, uint64_t* d_keys_out, int32_t* d_ids_out, float* d_scores_out, int path,
+                         void* stream, const KeyExchange* xch);
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // small device utilities

@@ -181,6 +181,68 @@ select_scores_kernel(const float* __restrict__ scores, const int32_t* __restrict
   select_topk(keys, cn, k, dst, final_sorted != 0, sort_buf, sc);
 }
 
+// the final answer of a row: sorted keys (+ unpacked ids / scores)
+__device__ __forceinline__ void emit_sorted(const uint64_t* sorted, int k, int64_t row, uint64_t* __restrict__ out,
+                                            int32_t* __restrict__ ids_out, float* __restrict__ scores_out) {
+  for (int i = threadIdx.x; i < k; i += kSelThreads) {
+    const uint64_t key = sorted[i];
+    out[row * k + i] = key;
+    if (ids_out) ids_out[row * k + i] = key ? key_id(key) : -1;
+    if (scores_out) scores_out[row * k + i] = key ? key_score(key) : -INFINITY;
+  }
+}
+
+// Selection fused with the multi-GPU exchange (ONE query, P2P transport): the CTA that holds this GPU's sorted top-k
+// stores it straight into every rank's receive slot over NVLink (peer stores, then a system-scope release of the step
+// number in each rank's flag), acquires the flags of all ranks in its own buffer, merges the world x k keys and emits
+// the GLOBAL top-k — no separate push or merge launch, a sharded search is the same two launches as a local one.
+// `sorted` (k keys) and `buf` (>= next_pow2(world * k) keys) are shared memory and may alias.
+__device__ __noinline__ void exchange_then_emit(const KeyExchange& x, const uint64_t* sorted, uint64_t* buf, int k,
+                                   uint64_t* __restrict__ out, int32_t* __restrict__ ids_out,
+                                   float* __restrict__ scores_out) {
+  for (int i = threadIdx.x; i < k * x.world; i += kSelThreads) {
+    const int dst = i / k, j = i - dst * k;
+    uint64_t* slot = reinterpret_cast<uint64_t*>(x.peers[dst] + exchange_slot_offset(x.parity, x.my_rank, x.world, x.max_keys));
+    slot[j] = sorted[j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (int(threadIdx.x) < x.world) {
+    uint64_t* flag = reinterpret_cast<uint64_t*>(x.peers[threadIdx.x]) + x.parity * kMaxWorld + x.my_rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(x.seq) : "memory");
+    const uint64_t* mine = reinterpret_cast<const uint64_t*>(x.local) + x.parity * kMaxWorld + threadIdx.x;
+    uint64_t t0 = 0, v = 0;
+    uint32_t spins = 0;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+      if (v >= x.seq) break;
+      if ((++spins & 0xffu) == 0 && x.watchdog_ns != 0) {
+        uint64_t now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        if (now - t0 > x.watchdog_ns) {
+          printf("hrc: peer %d never published step %llu\n", int(threadIdx.x), x.seq);
+          __trap();
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const uint64_t* slots = reinterpret_cast<const uint64_t*>(x.local + exchange_slot_offset(x.parity, 0, x.world, x.max_keys));
+  const int n = x.world * k;
+  const int n_pad = next_pow2(n);
+  for (int i = threadIdx.x; i < n_pad; i += kSelThreads) {
+    uint64_t key = 0;
+    if (i < n) {
+      const int p = i / k, j = i - p * k;
+      key = __ldcg(slots + size_t(p) * x.max_keys + j);
+    }
+    buf[i] = key;
+  }
+  bitonic_sort_desc(buf, n_pad);
+  emit_sorted(buf, k, 0, out, ids_out, scores_out);
+}
+
 // ids_out / scores_out (optional, final level only): the unpacked result, so that no separate unpack launch is needed.
 // list_len > 0 (final level only): the input is a concatenation of n_lists lists of list_len keys, each SORTED best
 // first (what the fused MaxSim epilogue and the streaming top-k hand over).  Let j = ceil(k / n_lists) - 1 and
@@ -191,7 +253,7 @@ select_scores_kernel(const float* __restrict__ scores, const int32_t* __restrict
 __global__ void __launch_bounds__(kSelThreads)
 select_keys_kernel(const uint64_t* __restrict__ keys_in, int n_in, int k, uint64_t* __restrict__ out,
                    int n_groups, int group_len, int final_sorted, int32_t* __restrict__ ids_out,
-                   float* __restrict__ scores_out, int list_len) {
+                   float* __restrict__ scores_out, int list_len, const KeyExchange xch) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem);
   uint64_t* sort_buf = keys + group_len;
@@ -206,12 +268,8 @@ select_keys_kernel(const uint64_t* __restrict__ keys_in, int n_in, int k, uint64
     const int n_pad = next_pow2(gn < k ? k : gn);
     for (int i = threadIdx.x; i < n_pad; i += kSelThreads) keys[i] = i < gn ? src[i] : 0;
     bitonic_sort_desc(keys, n_pad);
-    for (int i = threadIdx.x; i < k; i += kSelThreads) {
-      const uint64_t key = keys[i];
-      out[row * k + i] = key;
-      if (ids_out) ids_out[row * k + i] = key ? key_id(key) : -1;
-      if (scores_out) scores_out[row * k + i] = key ? key_score(key) : -INFINITY;
-    }
+    if (xch.world > 0) exchange_then_emit(xch, keys, keys, k, out, ids_out, scores_out);
+    else emit_sorted(keys, k, row, out, ids_out, scores_out);
     return;
   }
   if (list_len > 0 && final_sorted && n_groups == 1 && k <= list_len && gn > kSmallMerge) {
@@ -245,12 +303,8 @@ select_keys_kernel(const uint64_t* __restrict__ keys_in, int n_in, int k, uint64
         const int n_pad = next_pow2(got < k ? k : got);
         for (int i = got + threadIdx.x; i < n_pad; i += kSelThreads) keys[i] = 0;
         bitonic_sort_desc(keys, n_pad);
-        for (int i = threadIdx.x; i < k; i += kSelThreads) {
-          const uint64_t key = keys[i];
-          out[row * k + i] = key;
-          if (ids_out) ids_out[row * k + i] = key ? key_id(key) : -1;
-          if (scores_out) scores_out[row * k + i] = key ? key_score(key) : -INFINITY;
-        }
+        if (xch.world > 0) exchange_then_emit(xch, keys, keys, k, out, ids_out, scores_out);
+        else emit_sorted(keys, k, row, out, ids_out, scores_out);
         return;
       }
       __syncthreads();
@@ -260,7 +314,10 @@ select_keys_kernel(const uint64_t* __restrict__ keys_in, int n_in, int k, uint64
   __syncthreads();
   uint64_t* dst = out + (row * n_groups + group) * k;
   select_topk(keys, gn, k, dst, final_sorted != 0, sort_buf, sc);
-  if (final_sorted && (ids_out != nullptr || scores_out != nullptr)) {     // sort_buf still holds the sorted keys
+  if (final_sorted && xch.world > 0) {                                      // sort_buf holds the sorted keys
+    __syncthreads();
+    exchange_then_emit(xch, sort_buf, keys, k, out, ids_out, scores_out);
+  } else if (final_sorted && (ids_out != nullptr || scores_out != nullptr)) {
     for (int i = threadIdx.x; i < k; i += kSelThreads) {
       const uint64_t key = sort_buf[i];
       if (ids_out) ids_out[row * k + i] = key ? key_id(key) : -1;
@@ -491,7 +548,7 @@ int configure_smem() {
 // levels of stage 2 over n_in keys per row; writes sorted top-k to d_out.  tmp holds intermediates.
 int run_key_levels(const uint64_t* d_in, int64_t n_in, int n_rows, int k, uint64_t* d_out, uint64_t* tmp0,
                    uint64_t* tmp1, cudaStream_t stream, int32_t* d_ids_out = nullptr, float* d_scores_out = nullptr,
-                   int list_len = 0) {
+                   int list_len = 0, const KeyExchange* xch = nullptr) {
   const uint64_t* cur = d_in;
   int64_t cur_n = n_in;
   int flip = 0;
@@ -507,9 +564,16 @@ int run_key_levels(const uint64_t* d_in, int64_t n_in, int n_rows, int k, uint64
       while (n_pad < size_t(group_len) || n_pad < size_t(k)) n_pad <<= 1;
       if (n_pad * 8 > smem) smem = n_pad * 8;
     }
+    KeyExchange x;                                           // world == 0: no exchange
+    if (last && xch != nullptr) {
+      x = *xch;
+      size_t n_pad = 1;
+      while (n_pad < size_t(x.world) * k) n_pad <<= 1;
+      if (n_pad * 8 > smem) smem = n_pad * 8;
+    }
     select_keys_kernel<<<dim3(n_groups, n_rows), kSelThreads, smem, stream>>>(
         cur, int(cur_n), k, dst, n_groups, group_len, last ? 1 : 0, last ? d_ids_out : nullptr,
-        last ? d_scores_out : nullptr, (last && cur == d_in) ? list_len : 0);
+        last ? d_scores_out : nullptr, (last && cur == d_in) ? list_len : 0, x);
     count_launch();
     HRC_CHECK_CUDA(cudaGetLastError());
     if (last) break;
@@ -593,9 +657,16 @@ int launch_topk(const float* d_scores, const int32_t* d_ids, int64_t n, int n_ro
   return run_key_levels(cand, a, n_rows, k, d_keys_out, tmp0, tmp1, stream, d_ids_out, d_scores_out);
 }
 
+bool topk_exchange_supported(int n_rows, int k, int world, int max_keys) {
+  return n_rows == 1 && world >= 1 && world <= kMaxWorld && k >= 1 && k <= max_keys && world * k <= kSmallMerge;
+}
+
 int launch_topk_merge(const uint64_t* d_keys_in, int n_in, int n_rows, int k, uint64_t* d_keys_out,
-                      cudaStream_t stream, int32_t* d_ids_out, float* d_scores_out, int sorted_list_len) {
+                      cudaStream_t stream, int32_t* d_ids_out, float* d_scores_out, int sorted_list_len,
+                      const KeyExchange* xch) {
   if (n_rows == 0 || k == 0) return 0;
+  HRC_REQUIRE(xch == nullptr || (n_in > 0 && topk_exchange_supported(n_rows, k, xch->world, xch->max_keys)),
+              "top-k merge: fused exchange needs one row and world x k <= %d keys", kSmallMerge);
   HRC_REQUIRE(k >= 1 && k <= HRC_MAX_TOPK, "top-k merge: k=%d not in [1,%d]", k, HRC_MAX_TOPK);
   HRC_REQUIRE(n_in >= 0 && n_in <= kMergeMax, "top-k merge: n_in=%d exceeds %d", n_in, kMergeMax);
   HRC_REQUIRE(n_rows <= 65535, "top-k merge: too many rows (%d)", n_rows);
@@ -605,7 +676,7 @@ int launch_topk_merge(const uint64_t* d_keys_in, int n_in, int n_rows, int k, ui
     return 0;
   }
   return run_key_levels(d_keys_in, n_in, n_rows, k, d_keys_out, nullptr, nullptr, stream, d_ids_out, d_scores_out,
-                        sorted_list_len);
+                        sorted_list_len, xch);
 }
 
 uint64_t get_watchdog_ns();

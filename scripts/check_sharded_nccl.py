@@ -134,7 +134,59 @@ def main():
         s = hrc.ShardedSearcher(part, transport=transport)
         check(torch.equal(s.search_keys(q[:2], 25), tiny.search_keys(q[:2], 25)), f"[{transport}] shards smaller than k / empty shard")
         s.close()
+    # uneven shards, ONE query: rank 0 holds 100 documents (k = 25: its search's final kernel does the exchange itself),
+    # every other rank 10 (fewer than k: separate push + merge kernels) — the two routes share one slot / flag protocol
+    n_small = 100 + 10 * (world - 1)
+    mixed_full = synth_store(n_small, 5, 20, seed=6, device=dev)
+    mixed = hrc.JinaColBERTRetriever(cfg)
+    mixed.store = mixed_full
+    lo = 0 if rank == 0 else 100 + 10 * (rank - 1)
+    hi = 100 if rank == 0 else lo + 10
+    off = mixed_full.offsets
+    t0, t1 = int(off[lo]), int(off[hi])
+    part = hrc.JinaColBERTRetriever(cfg)
+    part.store = hrc.PackedStore(mixed_full.tokens[t0:t1].contiguous(), (off[lo:hi + 1] - off[lo]).contiguous(), doc_id_base=lo)
+    launches = {}
+    for transport in ("nccl", "p2p"):
+        s = hrc.ShardedSearcher(part, transport=transport)
+        same = all(torch.equal(s.search_keys(q[i:i + 1], 25), mixed.search_keys(q[i:i + 1], 25)) for i in range(19))
+        check(same, f"[{transport}] uneven shards, single queries (fused-exchange and separate routes mixed)")
+        s.close()
+        s = hrc.ShardedSearcher(r, transport=transport)              # launches of one sharded single-query search
+        s.search_keys(q[:1], 100)
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        s.search_keys(q[:1], 100)
+        launches[transport] = _lib.launch_count() - l0
+        s.close()
+    # what the exchange costs on top of a search, seen where the search itself is short: 4,000 documents per rank
+    small = hrc.JinaColBERTRetriever(cfg)
+    small.store = synth_store(4000 * world, 32, 64, seed=9, device=dev, rank=rank, world_size=world)
+    step_us = {}
+
+    def time_us(fn, reps=200):
+        for _ in range(10):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps * 1e3], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return round(float(t[0]), 2)
+
+    step_us["local_search"] = time_us(lambda: small.search_keys(q[:1], 100))
+    for transport in ("torch", "nccl", "p2p"):
+        s = hrc.ShardedSearcher(small, transport=transport)
+        step_us[f"sharded_search_{transport}"] = time_us(lambda: s.search_keys(q[:1], 100))
+        s.close()
     if rank == 0:
+        print(json.dumps({"world": world, "small_shard_step_us": step_us}), flush=True)
+        print(json.dumps({"world": world, "launches_per_single_query_search": launches}), flush=True)
         print(json.dumps({"world": world, "exchange_plus_merge_us": timings}), flush=True)
         print(f"world={world}: {'ALL OK' if ok else 'FAILED'}", flush=True)
     dist.destroy_process_group()
