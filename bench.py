@@ -54,9 +54,10 @@ def parse():
     ap.add_argument("--secondary", default="sustained,read_peak,c4,c3,c1,ragged,c5,pipelined",
                     help="comma-separated subset of the secondary measurements")
     ap.add_argument("--c5-global-docs", type=int, default=10_000_000)
-    ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p", "torch"],
-                    help="exchange step of the sharded search (N > 1): ncclAllGather inside libhrc (default), peer stores + "
-                         "flags inside libhrc, or torch.distributed")
+    ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "p2p", "torch"],
+                    help="exchange step of the sharded search (N > 1): peer stores + flags over NVLink inside libhrc when "
+                         "every rank can map its peers, else ncclAllGather inside libhrc (auto, default); or force one; "
+                         "or torch.distributed")
     return ap.parse_args()
 
 
@@ -385,7 +386,7 @@ def run_ours(args):
         breakdown = sharded_breakdown(torch, dist, hrc, _lib, retr, searcher, queries, dev, max_over_ranks, barrier)
 
     # ---- multi-GPU, pipelined: exchange + merge on a side stream, so a rank's next scan does not wait for the collective ---
-    if world > 1 and args.transport != "torch" and "pipelined" in want:
+    if world > 1 and searcher.transport != "torch" and "pipelined" in want:
         pending = []
 
         def step_async(i):
@@ -517,7 +518,7 @@ def run_ours(args):
                 "ms_per_step": e2e["ms_per_step"], "step_ms": e2e["step_ms"], "kernel_ms": e2e["kernel_ms"],
                 "api": ("JinaColBERTRetriever.search_host: pinned fp32 query -> hrc_search_host (H2D, bf16, MaxSim, top-k, "
                         "unpack, D2H) -> ids/scores on the host" if world == 1 else
-                        f"ShardedSearcher.search_host (transport {args.transport}): pinned fp32 query -> hrc_sharded_search_host "
+                        f"ShardedSearcher.search_host (transport {searcher.transport}): pinned fp32 query -> hrc_sharded_search_host "
                         "(H2D, bf16, local MaxSim + top-k, exchange of k keys per rank, merge + unpack, D2H), one C call per rank")},
         "gpu_launches": head["launches"],
         "clocks": head.get("clocks"),
@@ -713,17 +714,24 @@ def sharded_breakdown(torch, dist, hrc, _lib, retr, searcher, queries, dev, max_
     q = queries[0:1]
     local = retr.search_keys(q, K).contiguous()
     ws = _lib.Workspace()
-    p2p = searcher if searcher.transport == "p2p" else hrc.ShardedSearcher(retr, transport="p2p")
-    nccl_comm = searcher.comm if searcher.transport == "nccl" else p2p.comm
+    p2p = searcher if searcher.transport == "p2p" else None
+    if p2p is None:
+        try:                                                    # fails on every rank or on none (hrc_comm_enable_p2p)
+            p2p = hrc.ShardedSearcher(retr, transport="p2p")
+        except _lib.HrcError:
+            p2p = None
+    extra = hrc.ShardedSearcher(retr, transport="nccl") if (searcher.comm is None and p2p is None) else None
+    nccl_comm = searcher.comm if searcher.comm is not None else (p2p.comm if p2p is not None else extra.comm)
     parts = {"local_search_us": lambda: retr.search_keys(q, K),
              "exchange_merge_nccl_us": lambda: _lib.allgather_merge_topk(nccl_comm, local, K, transport=_lib.TRANSPORT_NCCL, workspace=ws),
-             "exchange_merge_p2p_us": lambda: _lib.allgather_merge_topk(p2p.comm, local, K, transport=_lib.TRANSPORT_P2P, workspace=ws),
              "exchange_merge_torch_us": lambda: _lib.topk_merge(all_gather_keys(local, K), K),
              "step_nccl_us": lambda: _lib.sharded_search(nccl_comm, retr.store.tokens, retr.store.offsets, q, K,
-                                                         id_base=retr.store.doc_id_base, workspace=ws, unpack=False),
-             "step_p2p_us": lambda: _lib.sharded_search(p2p.comm, retr.store.tokens, retr.store.offsets, q, K,
-                                                        id_base=retr.store.doc_id_base, transport=_lib.TRANSPORT_P2P,
-                                                        workspace=ws, unpack=False)}
+                                                         id_base=retr.store.doc_id_base, workspace=ws, unpack=False)}
+    if p2p is not None:
+        parts["exchange_merge_p2p_us"] = lambda: _lib.allgather_merge_topk(p2p.comm, local, K, transport=_lib.TRANSPORT_P2P, workspace=ws)
+        parts["step_p2p_us"] = lambda: _lib.sharded_search(p2p.comm, retr.store.tokens, retr.store.offsets, q, K,
+                                                           id_base=retr.store.doc_id_base, transport=_lib.TRANSPORT_P2P,
+                                                           workspace=ws, unpack=False)
     out = {}
     for name, fn in parts.items():
         for _ in range(3):

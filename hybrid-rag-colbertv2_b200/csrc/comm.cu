@@ -22,6 +22,7 @@ typedef enum { ncclSuccess = 0 } ncclResult_t;
 typedef enum { ncclInt8 = 0, ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5 } ncclDataType_t;
 }
 
+#include <cstdio>
 #include <cstring>
 
 #include "hrc_common.cuh"
@@ -259,39 +260,70 @@ int hrc_comm_enable_p2p(hrc_comm_t* comm, int max_keys, void* stream) {
   HRC_REQUIRE(c != nullptr && max_keys >= 1, "comm_enable_p2p: bad argument");
   if (c->p2p && c->max_keys >= max_keys) return 0;
   HRC_REQUIRE(!c->p2p, "comm_enable_p2p: already enabled with a smaller capacity (%d < %d)", c->max_keys, max_keys);
+  // Collective: every rank of the communicator calls this.  A failure on ANY rank (no peer access, IPC not permitted
+  // in this container, out of memory) must fail on EVERY rank, or the others would wait for it in the next collective:
+  // every rank takes part in both all-gathers whatever happened locally, and the second one carries its verdict.
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t bytes = kFlagBytes + size_t(2) * c->world * size_t(max_keys) * sizeof(uint64_t);
-  HRC_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->local), bytes));     // set-up time, never on the query path
-  HRC_CHECK_CUDA(cudaMemsetAsync(c->local, 0, bytes, st));
-  // exchange the IPC handles of the receive buffers with the communicator itself
+  bool ok = true;
+  char why[256] = "";
+  auto fail = [&](const char* what, cudaError_t e) {
+    if (ok) snprintf(why, sizeof(why), "%s: %s", what, cudaGetErrorString(e));
+    ok = false;
+    cudaGetLastError();
+  };
+  cudaError_t e;
   cudaIpcMemHandle_t mine;
-  HRC_CHECK_CUDA(cudaIpcGetMemHandle(&mine, c->local));
-  uint8_t* d_handles = nullptr;
-  HRC_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_handles), sizeof(mine) * (c->world + 1)));
+  memset(&mine, 0, sizeof(mine));
+  uint8_t* local = nullptr;
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&local), bytes)) != cudaSuccess) fail("cudaMalloc(receive buffer)", e);
+  if (ok && (e = cudaMemsetAsync(local, 0, bytes, st)) != cudaSuccess) fail("cudaMemsetAsync", e);
+  if (ok && (e = cudaIpcGetMemHandle(&mine, local)) != cudaSuccess) fail("cudaIpcGetMemHandle", e);
+  // scratch for the two all-gathers: world + 1 handles, world + 1 verdicts
+  uint8_t* d_tmp = nullptr;
+  const size_t hbytes = sizeof(mine) * size_t(c->world + 1), vbytes = sizeof(uint64_t) * size_t(c->world + 1);
+  HRC_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_tmp), hbytes + vbytes));     // (failing here fails every later call too)
+  uint8_t* d_handles = d_tmp;
+  uint64_t* d_verdict = reinterpret_cast<uint64_t*>(d_tmp + hbytes);
   HRC_CHECK_CUDA(cudaMemcpyAsync(d_handles + sizeof(mine) * c->world, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
   HRC_CHECK_NCCL(g_nccl.AllGather(d_handles + sizeof(mine) * c->world, d_handles, sizeof(mine), ncclUint8, c->nccl, st));
   cudaIpcMemHandle_t all[kMaxWorld];
   HRC_CHECK_CUDA(cudaMemcpyAsync(all, d_handles, sizeof(mine) * c->world, cudaMemcpyDeviceToHost, st));
   HRC_CHECK_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_handles);
-  for (int r = 0; r < c->world; ++r) {
-    if (r == c->rank) { c->peer[r] = c->local; continue; }
+  uint8_t* peer[kMaxWorld] = {};
+  for (int r = 0; ok && r < c->world; ++r) {
+    if (r == c->rank) { peer[r] = local; continue; }
     void* p = nullptr;
-    cudaError_t e = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) {
-      set_error("comm_enable_p2p: cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
-      return 1;
-    }
-    c->peer[r] = static_cast<uint8_t*>(p);
+    if ((e = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess) fail("cudaIpcOpenMemHandle", e);
+    peer[r] = static_cast<uint8_t*>(p);
   }
-  HRC_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_peer), sizeof(uint8_t*) * kMaxWorld));
-  HRC_CHECK_CUDA(cudaMemcpy(c->d_peer, c->peer, sizeof(uint8_t*) * kMaxWorld, cudaMemcpyHostToDevice));
-  // every rank's buffer is zeroed and mapped before anybody pushes: one more (tiny) collective as the barrier
-  uint64_t* d_tmp = nullptr;
-  HRC_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_tmp), sizeof(uint64_t) * (c->world + 1)));
-  HRC_CHECK_NCCL(g_nccl.AllGather(d_tmp + c->world, d_tmp, 1, ncclUint64, c->nccl, st));
+  uint8_t** d_peer = nullptr;
+  if (ok && (e = cudaMalloc(reinterpret_cast<void**>(&d_peer), sizeof(uint8_t*) * kMaxWorld)) != cudaSuccess) fail("cudaMalloc(peer table)", e);
+  if (ok && (e = cudaMemcpy(d_peer, peer, sizeof(uint8_t*) * kMaxWorld, cudaMemcpyHostToDevice)) != cudaSuccess) fail("cudaMemcpy(peer table)", e);
+  // the verdicts — and the barrier: every rank's buffer is zeroed and mapped before anybody pushes
+  const uint64_t verdict = ok ? 1 : 0;
+  uint64_t verdicts[kMaxWorld] = {};
+  HRC_CHECK_CUDA(cudaMemcpyAsync(d_verdict + c->world, &verdict, sizeof(verdict), cudaMemcpyHostToDevice, st));
+  HRC_CHECK_NCCL(g_nccl.AllGather(d_verdict + c->world, d_verdict, 1, ncclUint64, c->nccl, st));
+  HRC_CHECK_CUDA(cudaMemcpyAsync(verdicts, d_verdict, sizeof(uint64_t) * c->world, cudaMemcpyDeviceToHost, st));
   HRC_CHECK_CUDA(cudaStreamSynchronize(st));
   cudaFree(d_tmp);
+  int first_bad = -1;
+  for (int r = 0; r < c->world; ++r)
+    if (verdicts[r] != 1 && first_bad < 0) first_bad = r;
+  if (first_bad >= 0) {                       // the same answer on every rank: undo, report, leave the NCCL transport usable
+    for (int r = 0; r < c->world; ++r)
+      if (r != c->rank && peer[r] != nullptr) cudaIpcCloseMemHandle(peer[r]);
+    if (d_peer) cudaFree(d_peer);
+    if (local) cudaFree(local);
+    cudaGetLastError();
+    set_error("comm_enable_p2p: peer-memory transport unavailable (first failing rank %d%s%s)", first_bad, ok ? "" : "; here: ",
+              ok ? "" : why);
+    return 5;
+  }
+  c->local = local;
+  for (int r = 0; r < kMaxWorld; ++r) c->peer[r] = peer[r];
+  c->d_peer = d_peer;
   c->max_keys = max_keys;
   c->p2p = true;
   c->seq = 0;

@@ -58,8 +58,8 @@ class ShardedSearcher:
     """search / hybrid retrieve over a corpus sharded across the ranks of a torch.distributed group (one rank per GPU)."""
 
     def __init__(self, retriever: JinaColBERTRetriever, group=None, transport: str = "nccl", p2p_max_keys: int = 1 << 16):
-        if transport not in ("nccl", "p2p", "torch"):
-            raise ValueError(f"transport must be 'nccl', 'p2p' or 'torch', got {transport!r}")
+        if transport not in ("auto", "nccl", "p2p", "torch"):
+            raise ValueError(f"transport must be 'auto', 'nccl', 'p2p' or 'torch', got {transport!r}")
         self.retriever = retriever          # holds THIS rank's shard; store.doc_id_base makes ids global
         self.group = group
         self.transport = transport
@@ -70,7 +70,17 @@ class ShardedSearcher:
         self._n_global: Optional[int] = None
         self._side: Optional[torch.cuda.Stream] = None       # exchange stream of search_keys_async
         self._side_ws = _lib.Workspace()
-        if transport != "torch":
+        if transport == "auto":
+            # peer memory over NVLink when EVERY rank can map every other rank's buffer (hrc_comm_enable_p2p fails on all
+            # ranks or on none), else NCCL: same results, two launches per single-query search instead of three
+            self.comm = _lib.Comm(retriever.device, group)
+            try:
+                self.comm.enable_p2p(p2p_max_keys)
+                self.transport = "p2p"
+            except _lib.HrcError:
+                self.transport = "nccl"
+            self._host = _lib.ShardedHostSearch(self.comm)
+        elif transport != "torch":
             self.comm = _lib.Comm(retriever.device, group, p2p_max_keys=p2p_max_keys if transport == "p2p" else 0)
             self._host = _lib.ShardedHostSearch(self.comm)
 

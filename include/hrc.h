@@ -269,12 +269,16 @@ int hrc_synth_tokens(void* d_tokens_out, int64_t token_begin, int64_t n_tokens, 
  *   hrc_comm_init       collective over the ranks: joins the communicator on the CURRENT device.  libnccl.so.2 is
  *                       loaded at run time (dlopen); libhrc.so does not link against it
  *   hrc_comm_enable_p2p collective: maps every rank's receive buffer into every other rank (CUDA IPC over NVLink) for
- *                       HRC_TRANSPORT_P2P; max_keys = the largest n_rows * k a later call will exchange
+ *                       HRC_TRANSPORT_P2P; max_keys = the largest n_rows * k a later call will exchange.  Returns 5
+ *                       ON EVERY RANK when any rank cannot (no peer access, IPC not permitted): the ranks agree on the
+ *                       verdict inside the call, and the NCCL transport stays usable
  * Transports of the exchange:
  *   HRC_TRANSPORT_NCCL  ncclAllGather of n_rows * k keys per rank, then the merge kernel
  *   HRC_TRANSPORT_P2P   a push kernel STORES this rank's keys into every peer's receive buffer and releases a sequence
  *                       flag (system scope); the merge kernel acquires the world's flags and merges.  No collective
- *                       launch; the exchange is part of the producer and the consumer kernels.
+ *                       launch; the exchange is part of the producer and the consumer kernels.  For ONE query,
+ *                       hrc_sharded_search goes further: the search's own final selection kernel stores its top-k into
+ *                       the peers, waits for theirs and emits the global top-k — two launches, like a local search.
  */
 #define HRC_COMM_ID_BYTES 128
 #define HRC_TRANSPORT_NCCL 0
