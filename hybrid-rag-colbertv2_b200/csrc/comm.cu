@@ -211,6 +211,12 @@ __global__ void f32_to_bf16_rows_kernel(const float* __restrict__ in, __nv_bfloa
 
 using namespace hrc;
 
+#ifdef HRC_EXPERIMENTS
+// libhrc_exp.so only: make hrc_comm_enable_p2p fail locally on one rank, to test that every rank then gets the same verdict
+static int g_exp_fail_p2p_rank = -1;
+extern "C" void hrc_exp_fail_p2p(int rank) { g_exp_fail_p2p_rank = rank; }
+#endif
+
 extern "C" {
 
 int hrc_comm_unique_id(void* id_out) {
@@ -276,7 +282,10 @@ int hrc_comm_enable_p2p(hrc_comm_t* comm, int max_keys, void* stream) {
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
   uint8_t* local = nullptr;
-  if ((e = cudaMalloc(reinterpret_cast<void**>(&local), bytes)) != cudaSuccess) fail("cudaMalloc(receive buffer)", e);
+#ifdef HRC_EXPERIMENTS
+  if (c->rank == g_exp_fail_p2p_rank) fail("forced by hrc_exp_fail_p2p", cudaErrorNotSupported);
+#endif
+  if (ok && (e = cudaMalloc(reinterpret_cast<void**>(&local), bytes)) != cudaSuccess) fail("cudaMalloc(receive buffer)", e);
   if (ok && (e = cudaMemsetAsync(local, 0, bytes, st)) != cudaSuccess) fail("cudaMemsetAsync", e);
   if (ok && (e = cudaIpcGetMemHandle(&mine, local)) != cudaSuccess) fail("cudaIpcGetMemHandle", e);
   // scratch for the two all-gathers: world + 1 handles, world + 1 verdicts
