@@ -31,8 +31,7 @@ def main():
     ap.add_argument("--rounds", type=int, default=12)
     ap.add_argument("--launches", type=int, default=10)
     ap.add_argument("--docs", type=int, default=0)
-    ap.add_argument("--env-ab", default="", help="NAME: run every library with NAME=<each of --env-values> as separate contestants")
-    ap.add_argument("--env-values", default="0,1")
+    ap.add_argument("--path", type=int, default=0, help="HRC_PATH_* selector passed to every library (0 auto, 2 query-major, 3 doc-major)")
     ap.add_argument("libs", nargs="+")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -45,19 +44,13 @@ def main():
     q = synth_queries(nq, 32, device=dev)
     out = torch.empty((nq, store.n_docs), dtype=torch.float32, device=dev)
     fns = [bind(os.path.abspath(p)) for p in a.libs]
-    envs = [None] * len(fns)
-    if a.env_ab:
-        vals = a.env_values.split(",")
-        fns = [f for f in fns for _ in vals]
-        envs = vals * len(a.libs)
-        a.libs = [f"{os.path.basename(p)}[{a.env_ab}={v}]" for p in a.libs for v in vals]
+    envs = [None] * len(fns)                 # (the libraries read no environment variables any more: builds are the A/B axis)
     stream = torch.cuda.current_stream(dev).cuda_stream
+    ws = torch.empty(max(int(_lib.load().hrc_maxsim_workspace_bytes(store.n_docs, nq, 32)), 256), dtype=torch.uint8, device=dev)
 
     def launch(fn, env=None):
-        if env is not None:
-            os.environ[a.env_ab] = env
         rc = fn(store.tokens.data_ptr(), store.offsets.data_ptr(), store.n_docs, store.total_tokens, q.data_ptr(), nq, 32,
-                out.data_ptr(), 0, stream)
+                out.data_ptr(), a.path, ws.data_ptr(), ws.numel(), stream)
         assert rc == 0, rc
 
     for fn, env in zip(fns, envs):
