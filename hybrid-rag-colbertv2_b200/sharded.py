@@ -69,6 +69,7 @@ class ShardedSearcher:
         self._pinned = None
         self._n_global: Optional[int] = None
         self._side: Optional[torch.cuda.Stream] = None       # exchange stream of search_keys_async
+        self._async_done: Optional[torch.cuda.Event] = None  # the last exchange issued on it
         self._side_ws = _lib.Workspace()
         if transport == "auto":
             # peer memory over NVLink when EVERY rank can map every other rank's buffer (hrc_comm_enable_p2p fails on all
@@ -91,6 +92,14 @@ class ShardedSearcher:
     def _path(self) -> int:
         return _knob(self.retriever.config, "maxsim_path")
 
+    def _join_async(self) -> None:
+        """Exchanges of one communicator must run in issue order on every rank (the peer-memory slots are double-buffered
+        by step parity, NCCL wants one order per communicator): an exchange issued on the CURRENT stream first waits for
+        the exchanges search_keys_async put on the side stream."""
+        if self._async_done is not None:
+            torch.cuda.current_stream(self.retriever.device).wait_event(self._async_done)
+            self._async_done = None
+
     def n_docs_global(self) -> int:
         """Documents of the whole corpus (sum over the ranks' shards), cached."""
         if self._n_global is None:
@@ -110,6 +119,7 @@ class ShardedSearcher:
             return _lib.topk_merge(gathered, k)                           # [Bq, k] sorted, 0 = empty
         q = r._prep_queries(query_embeddings)
         s = r.store
+        self._join_async()
         return _lib.sharded_search(self.comm, s.tokens, s.offsets, q, int(k), id_base=s.doc_id_base, path=self._path(),
                                    transport=_TRANSPORTS[self.transport], workspace=self._ws, unpack=False)[0]
 
@@ -144,6 +154,7 @@ class ShardedSearcher:
                                                workspace=self._side_ws)[0]
             done = torch.cuda.Event()
             done.record(self._side)
+        self._async_done = done
         merged.record_stream(torch.cuda.current_stream(dev))
         return PendingKeys(merged, done)
 
@@ -154,6 +165,7 @@ class ShardedSearcher:
         else:
             q = r._prep_queries(query_embeddings)
             s = r.store
+            self._join_async()
             _, ids, scores = _lib.sharded_search(self.comm, s.tokens, s.offsets, q, int(k), id_base=s.doc_id_base,
                                                  path=self._path(), transport=_TRANSPORTS[self.transport],
                                                  workspace=self._ws, unpack=True)
@@ -170,6 +182,7 @@ class ShardedSearcher:
         q = query_embeddings if query_embeddings.dim() == 3 else query_embeddings.unsqueeze(0)
         if self.transport != "torch" and not r._literal() and not q.is_cuda:
             s = r.store
+            self._join_async()
             ids, sc = self._host(s.tokens, s.offsets, q.to(torch.float32).contiguous(), int(k), id_base=s.doc_id_base,
                                  path=self._path(), transport=_TRANSPORTS[self.transport], copy=copy)
             return ids, r._finish_scores(sc, self._lq(q))
@@ -198,6 +211,7 @@ class ShardedSearcher:
         a = bm25_ids.to(r.device, torch.int32).contiguous()
         s = r.store
         if self.transport != "torch" and not r._literal() and k_final <= n_cand:
+            self._join_async()
             ids, scores = _lib.sharded_hybrid_retrieve(
                 self.comm, s.tokens, s.offsets, self.n_docs_global(), q, a, colbert_k=colbert_k, rrf_k=_knob(cfg, "rrf_k"),
                 n_candidates=n_cand, final_k=k_final, id_base=s.doc_id_base, path=self._path(),

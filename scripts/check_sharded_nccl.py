@@ -88,6 +88,15 @@ def main():
             pend = [s.search_keys_async(q[i % 19: i % 19 + 1], 100) for i in range(30)]
             same = all(torch.equal(p.result(), one.search_keys(q[i % 19: i % 19 + 1], 100)) for i, p in enumerate(pend))
             check(same, f"[{transport}] 30 pipelined steps (search_keys_async)")
+            # synchronous searches issued while pipelined exchanges are still in flight (no .result() in between)
+            same = True
+            for rnd in range(6):
+                pend = [s.search_keys_async(q[(rnd + i) % 19: (rnd + i) % 19 + 1], 100) for i in range(3)]
+                sync_keys = s.search_keys(q[rnd:rnd + 1], 100)
+                same = same and torch.equal(sync_keys, one.search_keys(q[rnd:rnd + 1], 100))
+                same = same and all(torch.equal(p.result(), one.search_keys(q[(rnd + i) % 19: (rnd + i) % 19 + 1], 100))
+                                    for i, p in enumerate(pend))
+            check(same, f"[{transport}] synchronous searches interleaved with pipelined ones")
         a_ids, a_sc = s.retrieve_batch(q, bm25)
         check(torch.equal(a_ids, hy_ids) and torch.equal(a_sc, hy_sc), f"[{transport}] sharded hybrid retrieve, 19 queries")
         b_ids, b_sc = s.retrieve_batch(q[:1], bm25[:1])
