@@ -1114,6 +1114,66 @@ def test_graphed_rerank_equals_rerank_ids(cuda_dev):
         plan.run()
 
 
+def test_sharded_entry_points_on_a_one_rank_communicator(cuda_dev):
+    """The multi-GPU entry points (csrc/comm.cu) inside the single-GPU suite: a ONE-rank NCCL communicator on this GPU
+    drives hrc_comm_*, hrc_sharded_search[_host] and hrc_sharded_hybrid_retrieve over every transport — NCCL all-gather
+    + merge kernel, peer-memory push + merge kernels (5 queries), and the exchange fused into the search's final
+    selection kernel (1 query) — and must return exactly what the unsharded calls return.  (N = 2, 4, 8 over NVLink:
+    scripts/check_sharded_nccl.py, bench.py's parity_check.)"""
+    import socket
+
+    import torch.distributed as dist
+
+    import hybrid_rag_colbertv2_b200 as hrc
+    L = _lib()
+    if dist.is_initialized():
+        pytest.skip("a process group already exists in this process")
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1, device_id=cuda_dev)
+    try:
+        q, tok, off = _case(61, 40_000, 8, 200, 5, 32)
+        cfg = hrc.RAGConfig(device=str(cuda_dev), colbert_top_k=100, rerank_candidates=50, final_top_k=10)
+        r = hrc.JinaColBERTRetriever(cfg)
+        r.store = hrc.PackedStore(tok.to(cuda_dev), off.to(cuda_dev), doc_id_base=1000)      # a shard with a non-zero base
+        idx = hrc.DualIndexer(cfg)
+        idx.colbert_retriever = r
+        h = hrc.HybridRetriever(cfg, idx, None, verbose=False)
+        q_d = q.to(cuda_dev)
+        g = torch.Generator().manual_seed(3)
+        bm25 = torch.randint(1000, 41_000, (5, 100), generator=g, dtype=torch.int32).to(cuda_dev)
+        want_1, want_5 = r.search_keys(q_d[:1], 100), r.search_keys(q_d, 100)
+        want_ids, want_sc = r.search_embeddings(q_d, 100)
+        hy_ids, hy_sc = h.retrieve_batch(q_d, bm25)
+        hy1_ids, hy1_sc = h.retrieve_batch(q_d[:1], bm25[:1])
+        for transport in ("nccl", "p2p", "auto", "torch"):
+            s = hrc.ShardedSearcher(r, transport=transport)
+            if transport == "auto":
+                assert s.transport == "p2p"
+            l0 = L.launch_count()
+            assert torch.equal(s.search_keys(q_d[:1], 100), want_1), transport
+            if s.transport == "p2p":
+                assert L.launch_count() - l0 == 2, "one query over peer memory: the exchange rides in the search's 2 launches"
+            assert torch.equal(s.search_keys(q_d, 100), want_5), transport
+            ids, sc = s.search_embeddings(q_d, 100)
+            assert torch.equal(ids, want_ids) and torch.equal(sc, want_sc), transport
+            hi, hs = s.search_host(q.float(), 100)
+            assert torch.equal(hi, want_ids.cpu()) and torch.equal(hs, want_sc.cpu()), transport
+            a_ids, a_sc = s.retrieve_batch(q_d, bm25)
+            assert torch.equal(a_ids, hy_ids) and torch.equal(a_sc, hy_sc), transport
+            b_ids, b_sc = s.retrieve_batch(q_d[:1], bm25[:1])
+            assert torch.equal(b_ids, hy1_ids) and torch.equal(b_sc, hy1_sc), transport
+            if s.transport != "torch":
+                pend = [s.search_keys_async(q_d[i:i + 1], 100) for i in range(5)]
+                mid = s.search_keys(q_d[2:3], 100)                                  # issued while exchanges are in flight
+                assert torch.equal(mid, r.search_keys(q_d[2:3], 100)), transport
+                assert all(torch.equal(p.result(), r.search_keys(q_d[i:i + 1], 100)) for i, p in enumerate(pend)), transport
+            s.close()
+    finally:
+        dist.destroy_process_group()
+
+
 def test_two_host_threads_on_two_streams_share_one_retriever(cuda_dev):
     """SURVEY §8(b) 'thread-safe per (device, stream)': two host threads drive ONE retriever on their own CUDA streams at
     the same time (search, rerank, hybrid pipeline); each must get exactly what a single-threaded run returns.  Scratch is
