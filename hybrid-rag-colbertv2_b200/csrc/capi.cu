@@ -58,6 +58,9 @@ void store_release(const void*);
 #ifdef HRC_EXPERIMENTS
 void set_debug(int);
 void set_stages(int);
+void set_ctas(int);
+void set_dyn(int, int);
+void set_cta_times(unsigned long long*);
 #endif
 size_t topk_workspace_bytes(int64_t, int, int);
 int launch_topk(const float*, const int32_t*, int64_t, int, int, int32_t, uint64_t*, void*, size_t, cudaStream_t,
@@ -72,7 +75,7 @@ int launch_maxsim_tc_rerank(const void*, const int64_t*, int64_t, int64_t, const
 int tc_topk_segments(int64_t);
 int tc_topk_list_len();
 int launch_maxsim_tc_topk(const void*, const int64_t*, int64_t, int64_t, const void*, int, int, int, int32_t, float*,
-                          uint64_t*, int, cudaStream_t);
+                          uint64_t*, int, uint32_t*, cudaStream_t);
 int launch_keys_unpack(const uint64_t*, int64_t, int32_t*, float*, cudaStream_t);
 int launch_rerank_unpack(const uint64_t*, int, int, const int32_t*, int, int32_t*, int32_t*, float*, cudaStream_t);
 int launch_rrf(const int32_t*, int, const int32_t*, int, int, int, int, int32_t*, double*, int32_t*, cudaStream_t);
@@ -148,8 +151,9 @@ static bool search_is_fused(int64_t total_tokens, int nq, int lq, int k, int pat
   return (path == HRC_PATH_AUTO || path == HRC_PATH_TC || path == HRC_PATH_TC_DM) && tc_topk_supported(total_tokens, nq, lq, k);
 }
 
-struct SearchLayout {      // fused: candidate keys.  staged: score matrix, slot partials (lq > 32), top-k scratch
-  size_t cand, scores, part, topk, total, part_bytes, topk_bytes;
+struct SearchLayout {      // fused: candidate keys, the doc-major kernel's claim counter.  staged: score matrix, slot
+                           // partials (lq > 32) or that counter, top-k scratch
+  size_t cand, counter, scores, part, topk, total, part_bytes, topk_bytes;
   bool fused;
   int n_seg;
 };
@@ -160,6 +164,7 @@ static SearchLayout search_layout(int64_t n_docs, int64_t total_tokens, int nq, 
   if (L.fused) {
     L.n_seg = tc_topk_segments(total_tokens);
     L.cand = o; o += align256(size_t(nq) * size_t(L.n_seg) * size_t(tc_topk_list_len()) * sizeof(uint64_t));
+    L.counter = o; o += 256;
   } else {
     L.scores = o; o += align256(size_t(nq) * size_t(n_docs) * sizeof(float));
     L.part_bytes = maxsim_tc_workspace_bytes(n_docs, nq, lq);
@@ -272,6 +277,9 @@ int hrc_trace_collect(float* ms_out, int max_n) {
 #ifdef HRC_EXPERIMENTS
 void hrc_exp_set_debug(int bits) { set_debug(bits); }
 void hrc_exp_set_stages(int n) { set_stages(n); }
+void hrc_exp_set_ctas(int n) { set_ctas(n); }
+void hrc_exp_set_dyn(int share, int per_cta) { set_dyn(share, per_cta); }
+void hrc_exp_set_cta_times(void* d) { set_cta_times(static_cast<unsigned long long*>(d)); }
 #endif
 
 int hrc_store_register(const void* d_tokens, int64_t total_tokens) {
@@ -359,7 +367,7 @@ int search_with_exchange(const void* d_tokens, const int64_t* d_offsets, int64_t
     HRC_REQUIRE(n_queries <= 65535, "search: too many queries (%d)", n_queries);
     uint64_t* cand = reinterpret_cast<uint64_t*>(ws + L.cand);
     if (int rc = launch_maxsim_tc_topk(d_tokens, d_offsets, n_docs, total_tokens, d_queries, n_queries, lq, k, id_base,
-                                       nullptr, cand, tc_variant(path), st))
+                                       nullptr, cand, tc_variant(path), reinterpret_cast<uint32_t*>(ws + L.counter), st))
       return rc;
     return launch_topk_merge(cand, L.n_seg * tc_topk_list_len(), n_queries, k, d_keys_out, st, d_ids_out, d_scores_out,
                              tc_topk_list_len(), xch);

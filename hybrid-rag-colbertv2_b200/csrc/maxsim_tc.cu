@@ -112,7 +112,11 @@ struct TcParams {
   int n_qgroups;            // corpus mode: query groups (4*MT queries each)
   int n_stages;             // smem ring depth
   int slots_used;           // distinct queries per A tile: 1, 2 or 4
+  int n_units;              // doc-major kernel: work units (>= n_segments); the first n_segments are the CTAs' own
+  int64_t static_tokens;    // doc-major kernel: tokens [0, static_tokens) form the n_segments own units, the rest the shared ones
+  uint32_t* unit_counter;   // doc-major kernel: shared units are claimed here (zeroed before the launch); nullptr = none
   int debug;                // HRC_EXPERIMENTS builds only
+  unsigned long long* cta_times;   // HRC_EXPERIMENTS builds only (hrc_exp_set_cta_times): [2 * CTAs] end time (ns), SM id
   uint64_t watchdog_ns;     // mbarrier waits trap after this long (0 = never)
   uint64_t doc_policy;      // L2 policy for document tiles (evict-first when read once)
 };
@@ -668,7 +672,11 @@ constexpr int kDmQBytes = 32 * HRC_DIM * 2;         // the query as the B operan
 constexpr int kDmTileBytes = 128 * HRC_DIM * 2;      // 4 streams x 32 tokens, 32 KB
 constexpr int kDmStages = 5;
 constexpr int kDmAcc = 16;                          // accumulator stages: 512 TMEM columns / 32
-constexpr int kDmThreads = 6 * 32;                  // TMA warp, MMA warp, 4 epilogue warps
+constexpr int kDmThreads = 7 * 32;                  // TMA warp, MMA warp, 4 epilogue warps, unit scheduler warp
+constexpr int kDmBarBytes = 768;                    // mbarriers + the unit-descriptor ring
+constexpr int kDmSharedShare = 8;                   // 1 / this of the corpus is handed out dynamically ...
+constexpr int kDmSharedPerCta = 16;                 // ... in this many units per CTA
+constexpr int64_t kDmDynMinTokensPerCta = 4096;     // below this a shared unit would be shorter than two tiles
 
 // max over the 32 lanes of v, returned to every lane: ONE instruction on sm_100a (CREDUX.MAX.F32, result in a uniform
 // register).  scripts/micro/redux_bench.cu: 32 of these + 32 FMNMX take 174 cycles per 32 x 32 block and warp, the 5-level
@@ -691,6 +699,22 @@ __device__ __forceinline__ float sum32_butterfly_order(const float (&x)[32]) {
   return (c[0] + c[2]) + (c[1] + c[3]);
 }
 
+// Work distribution.  The corpus is NOT cut into one equal token range per CTA: SMs pull data at different rates (GPCs
+// of 16 / 18 / 20 SMs share a port to the L2, near / far die), and with equal ranges ~20 CTAs of one GPC finished 190-220 us
+// after the first (scripts/exp_cta_times.py) — 5 % of the kernel waiting for its slowest members.  Instead the first
+// 7/8 of the tokens form one OWN unit per CTA and the rest is cut into 16 small SHARED units per CTA, claimed with an
+// atomic counter by whoever is free (same-box A/B, scripts/ab_dynamic_units.py / exp_dyn_sweep.py: C2 kernel 4.38-4.42 ms
+// against 4.46-4.49 with equal ranges, the CTAs now finish within 63 us of each other; ragged corpus and power-capped
+// runs: unchanged).  A dedicated scheduler warp claims units and resolves their document boundaries
+// (binary searches over `offsets`, ~10 us of dependent loads) one or two units ahead and hands them to the other warps
+// through a two-entry descriptor ring, so the TMA ring, the accumulator ring and the epilogue never drain between units.
+// Every unit is a range of WHOLE documents, so the result does not depend on which CTA scored it.
+__device__ __forceinline__ int64_t dm_unit_first_token(const TcParams& p, int64_t u) {
+  if (u >= p.n_units) return p.total_tokens;
+  if (u < p.n_segments) return (p.static_tokens * u) / p.n_segments;
+  return p.static_tokens + ((p.total_tokens - p.static_tokens) * (u - p.n_segments)) / (p.n_units - p.n_segments);
+}
+
 template <bool TK>
 __global__ void __launch_bounds__(kDmThreads, 1)
 maxsim_dm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_q, const TcParams p) {
@@ -706,36 +730,23 @@ maxsim_dm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   uint64_t* tempty = bars + 32;                    // [kDmAcc]    epilogue -> MMA
   uint64_t* qfull = bars + 48;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 49);
-  int64_t* sdoc = reinterpret_cast<int64_t*>(bars + 50);     // [5] first document of each stream (+ end)
-  int64_t* stok = reinterpret_cast<int64_t*>(bars + 55);     // [5] first token of each stream (+ end)
-  uint64_t* lists = bars + 64;                               // TK: [4][kListCap] keys
+  uint64_t* ufull = bars + 50;                     // [2] scheduler -> the six consumer warps: a unit descriptor is ready
+  uint64_t* uempty = bars + 52;                    // [2] consumers -> scheduler: descriptor read
+  int64_t* udesc = reinterpret_cast<int64_t*>(bars + 56);    // [2][11]: first document of each stream (+ end), first token
+                                                             // of each stream (+ end), tiles (< 0: no more units)
+  uint64_t* lists = bars + kDmBarBytes / 8;                  // TK: [4][kListCap] keys
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint64_t wd = p.watchdog_ns;
   const int64_t item = blockIdx.x;
 
-  if (threadIdx.x < 5) {       // stream boundaries: the segment's token range cut in four at document starts
-    const int64_t b0 = (p.total_tokens * item) / p.n_segments;
-    const int64_t b1 = (p.total_tokens * (item + 1)) / p.n_segments;
-    const int64_t d0 = item == 0 ? 0 : lower_bound_doc(p.offsets, p.n_docs, b0);
-    const int64_t d1 = (item + 1 == p.n_segments) ? p.n_docs : lower_bound_doc(p.offsets, p.n_docs, b1);
-    const int64_t t0 = p.offsets[d0], t1 = p.offsets[d1];
-    int64_t d;
-    if (threadIdx.x == 0) d = d0;
-    else if (threadIdx.x == 4) d = d1;
-    else {
-      d = lower_bound_doc(p.offsets, p.n_docs, t0 + ((t1 - t0) * int64_t(threadIdx.x)) / 4);
-      d = d < d0 ? d0 : (d > d1 ? d1 : d);
-    }
-    sdoc[threadIdx.x] = d;
-    stok[threadIdx.x] = p.offsets[d];
-  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_d);
     tma_prefetch_desc(&tmap_q);
     for (int i = 0; i < kDmStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < kDmAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&ufull[i], 1); mbar_init(&uempty[i], 6); }
     mbar_init(qfull, 1);
     fence_mbar_init();
   }
@@ -745,49 +756,110 @@ maxsim_dm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   tc_fence_after_sync();
 
   const uint32_t acc_base = *tmem_slot;
-  int64_t longest = 0;
-#pragma unroll
-  for (int s4 = 0; s4 < 4; ++s4) longest = max(longest, stok[s4 + 1] - stok[s4]);
-  const int n_tiles = int((longest + 31) / 32);
+  int uslot = 0; uint32_t uphase = 0;              // position in the descriptor ring (every warp walks it in step)
 
-  if (warp == 0) {
+  if (warp == 6) {
+    // =============================== unit scheduler ===========================================
+    int64_t u = item;                                // the CTA's own unit first
+    while (true) {
+      mbar_wait_wd(&uempty[uslot], uphase ^ 1, wd);
+      int64_t* d = udesc + uslot * 11;
+      const bool more = u < p.n_units;
+      if (more) {
+        if (lane < 5) {      // stream boundaries: the unit's token range cut in four at document starts
+          const int64_t b0 = dm_unit_first_token(p, u), b1 = dm_unit_first_token(p, u + 1);
+          const int64_t d0 = u == 0 ? 0 : lower_bound_doc(p.offsets, p.n_docs, b0);
+          const int64_t d1 = (u + 1 == p.n_units) ? p.n_docs : lower_bound_doc(p.offsets, p.n_docs, b1);
+          const int64_t t0 = p.offsets[d0], t1 = p.offsets[d1];
+          int64_t dd;
+          if (lane == 0) dd = d0;
+          else if (lane == 4) dd = d1;
+          else {
+            dd = lower_bound_doc(p.offsets, p.n_docs, t0 + ((t1 - t0) * int64_t(lane)) / 4);
+            dd = dd < d0 ? d0 : (dd > d1 ? d1 : dd);
+          }
+          d[lane] = dd;
+          d[5 + lane] = p.offsets[dd];
+        }
+        __syncwarp();
+        if (lane == 0) {
+          int64_t longest = 0;
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) longest = max(longest, d[5 + s4 + 1] - d[5 + s4]);
+          d[10] = (longest + 31) / 32;
+        }
+      } else if (lane == 0) {
+        d[10] = -1;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ufull[uslot]);
+      if (!more) break;
+      if (++uslot == 2) { uslot = 0; uphase ^= 1; }
+      int64_t nu = p.n_units;                        // claim a shared unit
+      if (lane == 0 && p.unit_counter != nullptr) nu = int64_t(p.n_segments) + int64_t(atomicAdd(p.unit_counter, 1u));
+      u = __shfl_sync(0xffffffffu, nu, 0);
+    }
+  } else if (warp == 0) {
     // =============================== TMA producer =============================================
-    if (n_tiles > 0 && elect_one()) {
+    if (lane == 0) {
       mbar_arrive_expect_tx(qfull, kDmQBytes);
       tma_load_3d(sQ, &tmap_q, qfull, 0, 0, p.vq_base, kEvictLast);                  // rows >= lq arrive as zeros
       tma_load_3d(sQ + kDmQBytes / 2, &tmap_q, qfull, 64, 0, p.vq_base, kEvictLast);
-      int64_t row0[4];
-#pragma unroll
-      for (int s4 = 0; s4 < 4; ++s4) row0[s4] = stok[s4];
       int stage = 0; uint32_t phase = 0;
-      for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait_wd(&empty[stage], phase ^ 1, wd);
-        uint8_t* dst = sD + stage * kDmTileBytes;
-        if (HRC_DBG(p, 2)) {
-          mbar_arrive(&full[stage]);
-        } else {
-          mbar_arrive_expect_tx(&full[stage], kDmTileBytes);
+      while (true) {
+        mbar_wait_wd(&ufull[uslot], uphase, wd);
+        const int64_t* d = udesc + uslot * 11;
+        const int n_tiles = int(d[10]);
+        int64_t row0[4];
+        int tiles_of[4];                             // chunks of 32 tokens each stream has in this unit
 #pragma unroll
-          for (int s4 = 0; s4 < 4; ++s4) {
-            // a stream that has ended keeps loading (its neighbour's tokens, or zeros beyond the store): harmless, no
-            // document of this warp owns those lanes, and the byte count of a tile stays constant
-            const int row = int(row0[s4] + int64_t(t) * 32);
-            tma_load_2d(dst + s4 * 4096, &tmap_d, &full[stage], 0, row, p.doc_policy);
-            tma_load_2d(dst + kDmTileBytes / 2 + s4 * 4096, &tmap_d, &full[stage], 64, row, p.doc_policy);
-          }
+        for (int s4 = 0; s4 < 4; ++s4) {
+          row0[s4] = d[5 + s4];
+          tiles_of[s4] = int((d[5 + s4 + 1] - d[5 + s4] + 31) / 32);
         }
-        if (++stage == kDmStages) { stage = 0; phase ^= 1; }
+        mbar_arrive(&uempty[uslot]);
+        if (++uslot == 2) { uslot = 0; uphase ^= 1; }
+        if (n_tiles < 0) break;
+        for (int t = 0; t < n_tiles; ++t) {
+          mbar_wait_wd(&empty[stage], phase ^ 1, wd);
+          uint8_t* dst = sD + stage * kDmTileBytes;
+          if (HRC_DBG(p, 2)) {
+            mbar_arrive(&full[stage]);
+          } else {
+            // a stream that has ended loads nothing more (its quarter of the tile keeps stale tokens: harmless, no
+            // document of its warp owns those lanes) — with whole-document streams the four lengths of a unit differ by
+            // up to a document, and reading on would waste that much HBM traffic per unit
+            int live = 0;
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) live += t < tiles_of[s4] ? 1 : 0;
+            mbar_arrive_expect_tx(&full[stage], uint32_t(live) * (kDmTileBytes / 4));
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+              if (t >= tiles_of[s4]) continue;
+              const int row = int(row0[s4] + int64_t(t) * 32);
+              tma_load_2d(dst + s4 * 4096, &tmap_d, &full[stage], 0, row, p.doc_policy);
+              tma_load_2d(dst + kDmTileBytes / 2 + s4 * 4096, &tmap_d, &full[stage], 64, row, p.doc_policy);
+            }
+          }
+          if (++stage == kDmStages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================================
-    if (n_tiles > 0) {
-      mbar_wait_wd(qfull, 0, wd);
-      tc_fence_after_sync();
-      const uint32_t sQ_addr = smem_u32(sQ);
-      const uint32_t sD_addr = smem_u32(sD);
-      int stage = 0; uint32_t phase = 0;
-      int ts = 0; uint32_t tphase = 0;
+    mbar_wait_wd(qfull, 0, wd);
+    tc_fence_after_sync();
+    const uint32_t sQ_addr = smem_u32(sQ);
+    const uint32_t sD_addr = smem_u32(sD);
+    int stage = 0; uint32_t phase = 0;
+    int ts = 0; uint32_t tphase = 0;
+    while (true) {
+      mbar_wait_wd(&ufull[uslot], uphase, wd);
+      const int n_tiles = int(udesc[uslot * 11 + 10]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&uempty[uslot]);
+      if (++uslot == 2) { uslot = 0; uphase ^= 1; }
+      if (n_tiles < 0) break;
       for (int t = 0; t < n_tiles; ++t) {
         mbar_wait_wd(&full[stage], phase, wd);
         mbar_wait_wd(&tempty[ts], tphase ^ 1, wd);
@@ -813,44 +885,14 @@ maxsim_dm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
     // =============================== epilogue: one stream per warp ============================
     const int quad = warp & 3;                           // TMEM lanes 32*quad.. = rows 32*quad.. of the tile = stream `quad`
     const uint32_t lane_base = uint32_t(quad * 32) << 16;
-    const int64_t doc_begin = sdoc[quad], doc_end = sdoc[quad + 1], tok_begin = stok[quad];
-    const int n_docs_seg = int(doc_end - doc_begin);
-    const int my_chunks = int((stok[quad + 1] - tok_begin + 31) / 32);
     const bool q_active = p.vq_base < p.n_queries;
     const int64_t out_row = int64_t(p.vq_base) * p.n_items;
 
-    const uint32_t tok_begin_lo = uint32_t(tok_begin);
-    const uint32_t raw_none = tok_begin_lo + uint32_t(INT_MAX);
-    int batch = 0;
-    uint32_t ends = raw_none, ends_next = raw_none;
-    auto load_ends = [&](int b) -> uint32_t {
-      const int d = b * 32 + lane;
-      uint32_t r = raw_none;
-      if (d < n_docs_seg) r = uint32_t(p.offsets[doc_begin + d + 1]);
-      return r;
-    };
-    auto end_of = [&](int d) -> int {   // d non-decreasing over calls, -1 <= d < n_docs_seg
-      if (d < 0) return 0;
-#pragma unroll 1
-      while ((d >> 5) > batch) {
-        ends = ends_next;
-        ++batch;
-        ends_next = load_ends(batch + 1);
-      }
-      return int(__shfl_sync(0xffffffffu, ends, d & 31) - tok_begin_lo);
-    };
-    ends = load_ends(0);
-    ends_next = load_ends(1);
-
-    int my = 0;                              // local index of the document being accumulated
-    bool have_doc = q_active && n_docs_seg > 0;
-    int s_tok = 0, e_tok = 0;
-    if (have_doc) e_tok = end_of(0);
     float mr[32];                           // mr[j]: running max_t <q_j, d_t> of the current document, in every lane
 #pragma unroll
     for (int j = 0; j < 32; ++j) mr[j] = -INFINITY;
 
-    // fused top-k state (see the query-major kernel)
+    // fused top-k state (see the query-major kernel); the list spans all the units this CTA scores
     uint64_t* lst = lists + size_t(quad) * kListCap;
     uint32_t cnt = 0;                        // warp-uniform, like thr and thr_f: every lane holds the score after warp_sum
     uint64_t thr = 0;
@@ -859,64 +901,106 @@ maxsim_dm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
       for (int i = lane; i < kListCap; i += 32) lst[i] = 0;
       __syncwarp();
     }
-    auto finish_doc = [&]() {
-      const float sc = sum32_butterfly_order(mr);
-      const int64_t col = doc_begin + my;
-      if (lane == 0 && (!TK || p.scores != nullptr)) p.scores[out_row + col] = sc;
-      if constexpr (TK) {
-        if (!HRC_DBG(p, 8) && !(sc < thr_f)) {   // one compare per document; warp-uniform (also taken for NaN)
-          const uint64_t key = make_key(sc, int32_t(p.id_base + int32_t(col)));
-          if (key > thr) {
-            if (lane == 0) lst[cnt] = key;
-            if (++cnt == uint32_t(kListCap)) {
-              warp_sort256_desc(lst, lane);
-              cnt = uint32_t(p.k);
-              thr = lst[p.k - 1];
-              thr_f = key_score(thr);
+    int ts = 0; uint32_t tphase = 0;
+    int stage_e = 0;
+
+    while (true) {
+      mbar_wait_wd(&ufull[uslot], uphase, wd);
+      const int64_t* ud = udesc + uslot * 11;
+      const int64_t doc_begin = ud[quad], doc_end = ud[quad + 1], tok_begin = ud[5 + quad], tok_end = ud[5 + quad + 1];
+      const int n_tiles = int(ud[10]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&uempty[uslot]);
+      if (++uslot == 2) { uslot = 0; uphase ^= 1; }
+      if (n_tiles < 0) break;
+
+      const int n_docs_seg = int(doc_end - doc_begin);
+      const int my_chunks = int((tok_end - tok_begin + 31) / 32);
+      const uint32_t tok_begin_lo = uint32_t(tok_begin);
+      const uint32_t raw_none = tok_begin_lo + uint32_t(INT_MAX);
+      int batch = 0;
+      uint32_t ends = raw_none, ends_next = raw_none;
+      auto load_ends = [&](int b) -> uint32_t {
+        const int d = b * 32 + lane;
+        uint32_t r = raw_none;
+        if (d < n_docs_seg) r = uint32_t(p.offsets[doc_begin + d + 1]);
+        return r;
+      };
+      auto end_of = [&](int d) -> int {   // d non-decreasing over calls, -1 <= d < n_docs_seg
+        if (d < 0) return 0;
+#pragma unroll 1
+        while ((d >> 5) > batch) {
+          ends = ends_next;
+          ++batch;
+          ends_next = load_ends(batch + 1);
+        }
+        return int(__shfl_sync(0xffffffffu, ends, d & 31) - tok_begin_lo);
+      };
+      ends = load_ends(0);
+      ends_next = load_ends(1);
+
+      int my = 0;                              // local index of the document being accumulated
+      bool have_doc = q_active && n_docs_seg > 0;
+      int s_tok = 0, e_tok = 0;
+      if (have_doc) e_tok = end_of(0);
+
+      auto finish_doc = [&]() {
+        const float sc = sum32_butterfly_order(mr);
+        const int64_t col = doc_begin + my;
+        if (lane == 0 && (!TK || p.scores != nullptr)) p.scores[out_row + col] = sc;
+        if constexpr (TK) {
+          if (!HRC_DBG(p, 8) && !(sc < thr_f)) {   // one compare per document; warp-uniform (also taken for NaN)
+            const uint64_t key = make_key(sc, int32_t(p.id_base + int32_t(col)));
+            if (key > thr) {
+              if (lane == 0) lst[cnt] = key;
+              if (++cnt == uint32_t(kListCap)) {
+                warp_sort256_desc(lst, lane);
+                cnt = uint32_t(p.k);
+                thr = lst[p.k - 1];
+                thr_f = key_score(thr);
+              }
             }
           }
         }
-      }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mr[j] = -INFINITY;
-      ++my;
-      have_doc = my < n_docs_seg;
-      s_tok = e_tok;
-      if (have_doc) e_tok = end_of(my);
-    };
+        for (int j = 0; j < 32; ++j) mr[j] = -INFINITY;
+        ++my;
+        have_doc = my < n_docs_seg;
+        s_tok = e_tok;
+        if (have_doc) e_tok = end_of(my);
+      };
 
-    int ts = 0; uint32_t tphase = 0;
-    int stage_e = 0;
-    for (int t = 0; t < n_tiles; ++t) {
-      mbar_wait_wd(&tfull[ts], tphase, wd);
-      if (quad == 0 && lane == 0) mbar_arrive(&empty[stage_e]);   // the tile's MMAs are done: its smem slot may be refilled
-      if (++stage_e == kDmStages) stage_e = 0;
-      tc_fence_after_sync();
-      if (t < my_chunks && have_doc && !HRC_DBG(p, 1)) {
-        uint32_t v[32];
-        tmem_ld_32x32(acc_base + lane_base + uint32_t(ts * 32), v);
-        tmem_ld_wait();
-        const int c0 = t * 32, c1 = c0 + 32;
-        while (have_doc && s_tok < c1) {
-          const int lo = max(s_tok, c0), hi = min(e_tok, c1);     // this document's tokens inside this chunk: lanes [lo-c0, hi-c0)
-          if (hi - lo == 32) {                  // the chunk lies inside the document
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait_wd(&tfull[ts], tphase, wd);
+        if (quad == 0 && lane == 0) mbar_arrive(&empty[stage_e]);   // the tile's MMAs are done: its smem slot may be refilled
+        if (++stage_e == kDmStages) stage_e = 0;
+        tc_fence_after_sync();
+        if (t < my_chunks && have_doc && !HRC_DBG(p, 1)) {
+          uint32_t v[32];
+          tmem_ld_32x32(acc_base + lane_base + uint32_t(ts * 32), v);
+          tmem_ld_wait();
+          const int c0 = t * 32, c1 = c0 + 32;
+          while (have_doc && s_tok < c1) {
+            const int lo = max(s_tok, c0), hi = min(e_tok, c1);     // this document's tokens inside this chunk: lanes [lo-c0, hi-c0)
+            if (hi - lo == 32) {                  // the chunk lies inside the document
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mr[j] = fmaxf(mr[j], lanes_max(__uint_as_float(v[j])));
-          } else if (hi > lo) {                 // a boundary inside the chunk: the other documents' lanes read as -inf
-            const bool mine = lane >= lo - c0 && lane < hi - c0;
+              for (int j = 0; j < 32; ++j) mr[j] = fmaxf(mr[j], lanes_max(__uint_as_float(v[j])));
+            } else if (hi > lo) {                 // a boundary inside the chunk: the other documents' lanes read as -inf
+              const bool mine = lane >= lo - c0 && lane < hi - c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mr[j] = fmaxf(mr[j], lanes_max(mine ? __uint_as_float(v[j]) : -INFINITY));
+              for (int j = 0; j < 32; ++j) mr[j] = fmaxf(mr[j], lanes_max(mine ? __uint_as_float(v[j]) : -INFINITY));
+            }
+            if (e_tok > c1) break;              // the document continues in the next chunk
+            finish_doc();
           }
-          if (e_tok > c1) break;              // the document continues in the next chunk
-          finish_doc();
         }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[ts]);
+        if (++ts == kDmAcc) { ts = 0; tphase ^= 1; }
       }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[ts]);
-      if (++ts == kDmAcc) { ts = 0; tphase ^= 1; }
+      while (have_doc) finish_doc();            // trailing empty documents: -inf
     }
-    while (have_doc) finish_doc();            // trailing empty documents: -inf
 
     if constexpr (TK) {
       if (!HRC_DBG(p, 32)) warp_sort256_desc(lst, lane);
@@ -938,6 +1022,16 @@ maxsim_dm_kernel(const __grid_constant__ CUtensorMap tmap_d, const __grid_consta
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(acc_base, kTmemCols);
+#ifdef HRC_EXPERIMENTS
+  if (p.cta_times != nullptr && threadIdx.x == 0) {        // when did this CTA finish, and where did it run
+    unsigned long long now;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.cta_times[2 * blockIdx.x] = now;
+    p.cta_times[2 * blockIdx.x + 1] = smid;
+  }
+#endif
 }
 
 // --- host side -------------------------------------------------------------------------------
@@ -1013,7 +1107,16 @@ int cached_map(const void* base, uint64_t d1, uint64_t d2, uint32_t box_rows, CU
   return 0;
 }
 
+#ifdef HRC_EXPERIMENTS
+unsigned long long* g_exp_cta_times = nullptr;   // hrc_exp_set_cta_times: device buffer the doc-major kernel's CTAs stamp at exit
+int g_exp_dyn_share = 0, g_exp_dyn_per_cta = 0;  // hrc_exp_set_dyn: 1/share of the corpus in per_cta shared units per CTA (0 = default)
+int g_exp_ctas = 0;                               // hrc_exp_set_ctas: CTAs (corpus segments) of the persistent kernels, 0 = one per SM
+#endif
+
 int sm_count() {
+#ifdef HRC_EXPERIMENTS
+  if (g_exp_ctas > 0) return g_exp_ctas;
+#endif
   static int cached[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1090,7 +1193,23 @@ int launch_dm(const void* d_tokens, const void* d_queries, int lq, int n_real_qu
   if (int rc = cached_map(d_tokens, uint64_t(p.total_tokens), 0, 32, &tmap_d)) return rc;     // one stream's 32-token box
   if (int rc = cached_map(d_queries, uint64_t(lq), uint64_t(n_real_queries), 32, &tmap_q)) return rc;
   p.n_stages = kDmStages;
-  const int smem_bytes = 1024 + kDmQBytes + kDmStages * kDmTileBytes + 512 + (TK ? 4 * kListCap * 8 : 0);
+  // work units: one own unit per CTA over the first 3/4 of the tokens + 16 shared units per CTA over the rest, when the
+  // caller's workspace holds the claim counter and a CTA's share is long enough for the SMs' speed spread to matter
+  p.n_units = p.n_segments;
+  p.static_tokens = p.total_tokens;
+  if (p.unit_counter != nullptr && p.total_tokens >= int64_t(p.n_segments) * kDmDynMinTokensPerCta) {
+    int share = kDmSharedShare, per_cta = kDmSharedPerCta;
+#ifdef HRC_EXPERIMENTS
+    if (g_exp_dyn_share > 0) share = g_exp_dyn_share;
+    if (g_exp_dyn_per_cta > 0) per_cta = g_exp_dyn_per_cta;
+#endif
+    p.n_units = p.n_segments * (1 + per_cta);
+    p.static_tokens = p.total_tokens - p.total_tokens / share;
+    HRC_CHECK_CUDA(cudaMemsetAsync(p.unit_counter, 0, sizeof(uint32_t), stream));
+  } else {
+    p.unit_counter = nullptr;
+  }
+  const int smem_bytes = 1024 + kDmQBytes + kDmStages * kDmTileBytes + kDmBarBytes + (TK ? 4 * kListCap * 8 : 0);
   static PerDeviceOnce once;
   int dev;
   if (once.pending(&dev)) {
@@ -1138,7 +1257,7 @@ constexpr int kRerankFusedMax = 1024;
 int launch_tc_slots(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
                     const int32_t* d_cand_ids, int64_t n_items, const void* d_queries, int n_real_queries,
                     int q_slots, int lq, float* d_scores, int variant, const TopkOut* tk, const RerankOut* rr,
-                    cudaStream_t stream) {
+                    uint32_t* unit_counter, cudaStream_t stream) {
   const bool dm = variant == kVariantDocMajor || (variant == kVariantAuto && d_cand_ids == nullptr && q_slots == 1);
   const int n_queries = n_real_queries * q_slots;      // virtual queries from here on
   HRC_REQUIRE(total_tokens > 0 && total_tokens < (1ll << 31), "tc path: total_tokens=%lld out of range",
@@ -1168,9 +1287,14 @@ int launch_tc_slots(const void* d_tokens, const int64_t* d_offsets, int64_t n_do
   p.n_qgroups = 1;
   p.n_stages = 0;
   p.slots_used = 1;
+  p.n_units = 1;
+  p.static_tokens = total_tokens;
+  p.unit_counter = unit_counter;
   p.debug = 0;
+  p.cta_times = nullptr;
 #ifdef HRC_EXPERIMENTS
   p.debug = g_debug;
+  p.cta_times = g_exp_cta_times;
 #endif
   p.watchdog_ns = g_watchdog_ns;
   p.doc_policy = kEvictFirst;
@@ -1225,6 +1349,9 @@ uint64_t get_watchdog_ns() { return g_watchdog_ns; }
 #ifdef HRC_EXPERIMENTS
 void set_debug(int bits) { g_debug = bits; }
 void set_stages(int n) { g_stages = n; }
+void set_ctas(int n) { g_exp_ctas = n; }
+void set_dyn(int share, int per_cta) { g_exp_dyn_share = share; g_exp_dyn_per_cta = per_cta; }
+void set_cta_times(unsigned long long* d) { g_exp_cta_times = d; }
 #endif
 
 int store_register(const void* d_tokens, int64_t total_tokens) {
@@ -1260,14 +1387,14 @@ int tc_topk_list_len() { return kListOut; }
 // d_cand_keys: uint64 [n_queries][tc_topk_segments()][kListOut]; d_scores optional (the full matrix, if wanted)
 int launch_maxsim_tc_topk(const void* d_tokens, const int64_t* d_offsets, int64_t n_docs, int64_t total_tokens,
                           const void* d_queries, int n_queries, int lq, int k, int32_t id_base, float* d_scores,
-                          uint64_t* d_cand_keys, int variant, cudaStream_t stream) {
+                          uint64_t* d_cand_keys, int variant, uint32_t* d_unit_counter, cudaStream_t stream) {
   if (n_docs == 0 || n_queries == 0) return 0;
   HRC_REQUIRE(tc_topk_supported(total_tokens, n_queries, lq, k), "fused top-k: needs <= %d queries, lq <= %d and k <= %d",
               HRC_FUSED_TOPK_MAX_QUERIES, HRC_TC_MAX_LQ, kListOut);
   HRC_REQUIRE(d_cand_keys != nullptr, "fused top-k: null candidate buffer");
   const TopkOut tk{d_cand_keys, k, id_base};
   return launch_tc_slots(d_tokens, d_offsets, n_docs, total_tokens, nullptr, n_docs, d_queries, n_queries, 1, lq, d_scores,
-                         variant, &tk, nullptr, stream);
+                         variant, &tk, nullptr, d_unit_counter, stream);
 }
 
 // ---- fused rerank: candidate MaxSim + sorted top-k in ONE launch (hrc_rerank's default) ----------------------------
@@ -1288,12 +1415,13 @@ int launch_maxsim_tc_rerank(const void* d_tokens, const int64_t* d_offsets, int6
   HRC_CHECK_CUDA(cudaMemsetAsync(d_counter, 0, size_t(n_queries) * sizeof(uint32_t), stream));
   const RerankOut rr{d_counter, k, d_pos, d_ids, d_scores_out};
   return launch_tc_slots(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_cand, d_queries, n_queries, 1, lq,
-                         d_scores, kVariantDefault, nullptr, &rr, stream);
+                         d_scores, kVariantDefault, nullptr, &rr, nullptr, stream);
 }
 
 // bytes of caller workspace the tensor-core path needs: the per-slot partial scores of queries longer than 32 tokens
 size_t maxsim_tc_workspace_bytes(int64_t n_items, int n_queries, int lq) {
   const int q_slots = (lq + HRC_TC_MAX_LQ - 1) / HRC_TC_MAX_LQ;
+  if (q_slots == 1 && n_queries == 1) return 256;      // the doc-major kernel's claim counter (optional: see launch_maxsim_tc)
   if (q_slots <= 1 || q_slots > HRC_TC_MAX_SLOTS) return 0;
   return size_t(n_queries) * size_t(q_slots) * size_t(n_items) * sizeof(float);
 }
@@ -1305,9 +1433,15 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
   HRC_REQUIRE(lq >= 1 && lq <= HRC_TC_MAX_LQ * HRC_TC_MAX_SLOTS, "tc path: lq=%d not in [1,%d]", lq,
               HRC_TC_MAX_LQ * HRC_TC_MAX_SLOTS);
   const int q_slots = (lq + HRC_TC_MAX_LQ - 1) / HRC_TC_MAX_LQ;
-  if (q_slots == 1)
+  if (q_slots == 1) {
+    // (one query over the corpus: the doc-major kernel hands part of the work out dynamically when the caller's
+    // workspace can hold its 4-byte claim counter; without one it falls back to equal shares)
+    uint32_t* counter = (d_cand_ids == nullptr && n_queries == 1 && d_workspace != nullptr && workspace_bytes >= sizeof(uint32_t) &&
+                         (reinterpret_cast<uintptr_t>(d_workspace) & 3) == 0)
+                            ? static_cast<uint32_t*>(d_workspace) : nullptr;
     return launch_tc_slots(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_items, d_queries, n_queries, 1, lq,
-                           d_scores, variant, nullptr, nullptr, stream);
+                           d_scores, variant, nullptr, nullptr, counter, stream);
+  }
   // A query of more than 32 tokens is scored as q_slots virtual queries of <= 32 tokens (rows beyond lq arrive as
   // zeros from TMA and add max_t <0, d_t> = 0); their partial scores (caller workspace) are summed in slot order.
   HRC_REQUIRE(int64_t(n_queries) * q_slots <= 65535, "tc path: too many query slots (%d x %d)", n_queries, q_slots);
@@ -1318,7 +1452,7 @@ int launch_maxsim_tc(const void* d_tokens, const int64_t* d_offsets, int64_t n_d
   float* part = static_cast<float*>(d_workspace);
   const int64_t total = int64_t(n_queries) * n_items;
   if (int rc = launch_tc_slots(d_tokens, d_offsets, n_docs, total_tokens, d_cand_ids, n_items, d_queries, n_queries,
-                               q_slots, lq, part, variant, nullptr, nullptr, stream))
+                               q_slots, lq, part, variant, nullptr, nullptr, nullptr, stream))
     return rc;
   sum_slots_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(part, q_slots, n_items, total, d_scores);
   count_launch();

@@ -110,7 +110,7 @@ def test_scoring_entry_points_stay_inside_their_buffers(cuda_dev, nq, lq, path):
     expc[0, 3] = float("-inf")
     _close(_typed(v_cs, torch.float32, (nq, n_cand)).cpu(), expc, f"maxsim_scores_ids {nq}x{lq} {path}")
     # a workspace one byte too small must be refused, not overrun
-    if ws_bytes:
+    if ws_bytes and lq > 32:      # (for one short query the 256 bytes hold an OPTIONAL claim counter: nothing to refuse)
         rc = lib.hrc_maxsim_scores(p_tok, p_off, n_docs, T, p_q, nq, lq, p_sc, P, p_ws, ws_bytes - 1, st)
         assert rc != 0 and b"workspace" in lib.hrc_last_error()
 

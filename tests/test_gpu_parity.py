@@ -735,6 +735,32 @@ def test_decisive_token_at_every_chunk_and_tile_boundary(cuda_dev, nq, path):
         _assert_scores(gotc, exp.flip(1), f"boundary candidates nq={nq}", bucket="boundary")
 
 
+@pytest.mark.parametrize("path", ["tc_dm", "auto"])
+def test_boundary_suite_through_the_dynamic_work_units(cuda_dev, path):
+    """The doc-major kernel hands a quarter of a large corpus out in small shared units claimed at run time (which CTA
+    scores which documents then differs from launch to launch).  The boundary corpus, repeated until the dynamic route
+    engages (>= 4096 tokens per CTA), must still match the oracle on every document, 5 launches in a row bit for bit,
+    through the score matrix AND through the fused top-k search."""
+    L = _lib()
+    q, tok, off, planted = _boundary_corpus(1, 32)
+    reps = int(148 * 4096 * 1.3 / int(off[-1])) + 1
+    tok_r = tok.repeat(reps, 1)
+    off_r = torch.cat([off[:1]] + [off[1:] + r * int(off[-1]) for r in range(reps)])
+    assert int(off_r[-1]) >= 148 * 4096
+    tok_d, off_d, q_d = tok_r.to(cuda_dev), off_r.to(cuda_dev), q.to(cuda_dev)
+    exp = o.maxsim_scores(q.float(), tok_r.float(), off_r)
+    first = None
+    for _ in range(5):
+        got = L.maxsim_scores(tok_d, off_d, q_d, path=_path(L, path))
+        _assert_scores(got, exp, f"dynamic units {path}", bucket="boundary")
+        keys = L.search(tok_d, off_d, q_d, 100, path=_path(L, path))[0]
+        if first is None:
+            first = (got.clone(), keys.clone())
+        assert torch.equal(got, first[0]) and torch.equal(keys, first[1]), "results differ between launches"
+    want = L.topk(first[0], 100)
+    assert torch.equal(first[1], want), "fused search over dynamic units != top-k of the score matrix"
+
+
 @pytest.mark.parametrize("path", ["tc", "simt", "tc_dm"])
 def test_maxsim_kernels_reproduce_the_reference_where_it_computes_maxsim(cuda_dev, golden_dir, path):
     """REFERENCE PIN for the MaxSim kernels: tests/golden/maxsim_pin.npz holds outputs of the UNMODIFIED reference
