@@ -12,7 +12,10 @@
 // maxsim_dm_kernel<TK> — ONE query, DOC-MAJOR: A = document tokens (M = 128), B = the query (N = 32), so exactly the
 //   useful tensor work is issued; a tile is 4 streams x 32 tokens, one stream of whole documents per epilogue warp;
 //   the max over a document's tokens is one redux.sync.max.f32 per query token.  HRC_PATH_AUTO's choice for a single
-//   query; TK fuses the per-segment top-k into the epilogue (hrc_search = 2 launches).  See the comment above it.
+//   query; TK fuses the per-CTA top-k into the epilogue (hrc_search = 2 launches).  Work is handed out in UNITS of
+//   whole documents: one own unit per CTA (7/8 of the corpus) + small shared units claimed at run time, resolved one or
+//   two units ahead by a scheduler warp (SMs pull data at different rates; equal shares left 5 % waiting for the
+//   slowest GPC).  See the comments above it.
 //
 // maxsim_tc_kernel<MT, ZP, CG, TK, RR> — QUERY-MAJOR: A = queries (M = 4 slots x 32 tokens), B = document tokens
 //   (N = 128): D[row = query token][col = doc token].  One CTA = one contiguous run of whole documents ("segment") x
@@ -39,8 +42,9 @@
 //   units (round 1), the M=64 variant (round 2) — are no longer in the source: profiles/experiments/ keeps their diffs.
 //
 // The product library reads no environment variables.  Building with -DHRC_EXPERIMENTS (make exp -> libhrc_exp.so)
-// adds hrc_exp_set_debug() / hrc_exp_set_stages(): kernel skeletons (no epilogue math / no document TMA / no MMA) and
-// the shared-memory-ring cap behind the measurements in DESIGN.md §4 (scripts/exp_sweep.py, scripts/exp_dm_tk.py).
+// adds hrc_exp_set_debug() / hrc_exp_set_stages() / hrc_exp_set_ctas() / hrc_exp_set_dyn() / hrc_exp_set_cta_times():
+// kernel skeletons (no epilogue math / no document TMA / no MMA), the shared-memory-ring cap, the CTA count, the
+// dynamic share and per-CTA finish times behind the measurements in DESIGN.md §4 (scripts/exp_*.py).
 //
 // Reference semantics: local_rag_complete.py:807-812 (docstring), :813-817 (shapes), summed over
 // query tokens per BASELINE.json north_star.  Algorithmic traffic: 256 B per document token.
