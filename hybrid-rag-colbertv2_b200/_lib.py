@@ -360,8 +360,8 @@ class HostSearch:
             self.ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
             self.ws_bytes = need
             self.q_pinned = torch.empty((nq, lq, DIM), dtype=torch.float32).pin_memory()
-            self.ids = torch.empty((nq, k), dtype=torch.int32).pin_memory()
-            self.scores = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+            self.out = torch.empty((2, nq, k), dtype=torch.int32).pin_memory()     # ids | scores: adjacent -> ONE D2H copy
+            self.ids, self.scores = self.out[0], self.out[1].view(torch.float32)
             self.key = key
 
     def _call(self, tokens: torch.Tensor, offsets: torch.Tensor, queries_host: torch.Tensor, k: int, *,
@@ -644,8 +644,8 @@ class ShardedHostSearch:
             self.ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
             self.ws_bytes = need
             self.q_pinned = torch.empty((nq, lq, DIM), dtype=torch.float32).pin_memory()
-            self.ids = torch.empty((nq, k), dtype=torch.int32).pin_memory()
-            self.scores = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+            self.out = torch.empty((2, nq, k), dtype=torch.int32).pin_memory()     # ids | scores: adjacent -> ONE D2H copy
+            self.ids, self.scores = self.out[0], self.out[1].view(torch.float32)
             self.key = key
         src = queries_host.contiguous()
         if not src.is_pinned():

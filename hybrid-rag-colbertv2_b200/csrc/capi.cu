@@ -225,9 +225,9 @@ static HostSearchLayout host_search_layout(int64_t n_docs, int64_t total_tokens,
   L.search_bytes = search_layout(n_docs, total_tokens, n_queries, lq, k, path).total;
   L.search = o; o += align256(L.search_bytes);
   L.keys = o; o += align256(size_t(n_queries) * k * sizeof(uint64_t));
-  L.ids = o; o += align256(size_t(n_queries) * k * sizeof(int32_t));
-  L.out_scores = o; o += align256(size_t(n_queries) * k * sizeof(float));
-  L.total = o;
+  L.ids = o; o += size_t(n_queries) * k * sizeof(int32_t);          // ids and scores back to back: ONE device -> host
+  L.out_scores = o; o += align256(size_t(n_queries) * k * sizeof(float));   // copy when the host buffers are adjacent too
+  L.total = align256(o);
   return L;
 }
 
@@ -415,8 +415,13 @@ int hrc_search_host(const void* d_tokens, const int64_t* d_offsets, int64_t n_do
   if (int rc = hrc_search(d_tokens, d_offsets, n_docs, total_tokens, q16, n_queries, lq, k, id_base, ws + L.search,
                           L.search_bytes, reinterpret_cast<uint64_t*>(ws + L.keys), d_ids, d_sc, path, stream))
     return rc;
-  HRC_CHECK_CUDA(cudaMemcpyAsync(h_ids_out, d_ids, size_t(n_queries) * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  HRC_CHECK_CUDA(cudaMemcpyAsync(h_scores_out, d_sc, size_t(n_queries) * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+  const size_t half = size_t(n_queries) * k * sizeof(int32_t);
+  if (reinterpret_cast<const uint8_t*>(h_scores_out) == reinterpret_cast<const uint8_t*>(h_ids_out) + half) {
+    HRC_CHECK_CUDA(cudaMemcpyAsync(h_ids_out, d_ids, 2 * half, cudaMemcpyDeviceToHost, st));
+  } else {
+    HRC_CHECK_CUDA(cudaMemcpyAsync(h_ids_out, d_ids, half, cudaMemcpyDeviceToHost, st));
+    HRC_CHECK_CUDA(cudaMemcpyAsync(h_scores_out, d_sc, half, cudaMemcpyDeviceToHost, st));
+  }
   return 0;
 }
 

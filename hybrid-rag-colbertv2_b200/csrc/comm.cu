@@ -163,9 +163,9 @@ ShardedHostLayout sharded_host_layout(int world, int64_t n_docs, int64_t total_t
   L.q16 = o; o += al256(size_t(nq) * lq * HRC_DIM * 2);
   L.inner_bytes = sharded_search_layout(world, n_docs, total_tokens, nq, lq, k, path).total + al256(size_t(nq) * k * 8);
   L.inner = o; o += al256(L.inner_bytes);
-  L.ids = o; o += al256(size_t(nq) * k * sizeof(int32_t));
+  L.ids = o; o += size_t(nq) * k * sizeof(int32_t);                 // ids and scores back to back: one D2H copy
   L.scores = o; o += al256(size_t(nq) * k * sizeof(float));
-  L.total = o;
+  L.total = al256(o);
   return L;
 }
 
@@ -480,8 +480,13 @@ int hrc_sharded_search_host(hrc_comm_t* comm, int transport, const void* d_token
   if (int rc = hrc_sharded_search(comm, transport, d_tokens, d_offsets, n_docs, total_tokens, q16, n_queries, lq, k, id_base,
                                   ws + L.inner, inner, keys, d_ids, d_sc, path, stream))
     return rc;
-  HRC_CHECK_CUDA(cudaMemcpyAsync(h_ids_out, d_ids, size_t(n_queries) * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  HRC_CHECK_CUDA(cudaMemcpyAsync(h_scores_out, d_sc, size_t(n_queries) * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+  const size_t half = size_t(n_queries) * k * sizeof(int32_t);
+  if (reinterpret_cast<const uint8_t*>(h_scores_out) == reinterpret_cast<const uint8_t*>(h_ids_out) + half) {
+    HRC_CHECK_CUDA(cudaMemcpyAsync(h_ids_out, d_ids, 2 * half, cudaMemcpyDeviceToHost, st));
+  } else {
+    HRC_CHECK_CUDA(cudaMemcpyAsync(h_ids_out, d_ids, half, cudaMemcpyDeviceToHost, st));
+    HRC_CHECK_CUDA(cudaMemcpyAsync(h_scores_out, d_sc, half, cudaMemcpyDeviceToHost, st));
+  }
   return 0;
 }
 
