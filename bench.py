@@ -7,7 +7,8 @@
 Headline: a step = one full-corpus MaxSim top-100 search of one 32-token query (config C2: 1M passages x 128
 tokens per GPU, 32.8 GB bf16, far larger than the 126 MB L2, so every step streams from HBM).  With N>1 each
 rank holds its own 1M-document shard of an N-million-document corpus (weak scaling); a step
-adds the all-gather of k keys per rank and the on-device merge.  The dominant kernel is timed INSIDE the timed
+adds the exchange of k keys per rank and the merge (over peer memory inside the search's own final kernel when every
+rank can map its peers, else ncclAllGather + a merge kernel; --transport).  The dominant kernel is timed INSIDE the timed
 steps (hrc_trace_*: CUDA events around its launches on its own stream), so kernel_ms <= ms_per_step by
 construction.
 
@@ -15,8 +16,9 @@ After the headline the same process measures, outside the headline's timed regio
 other BASELINE.json configs: `sustained` (C2 back to back for >= 2 s, clocks recorded), `read_peak` (pure-read
 bandwidth probe over the same corpus), `c4` (hybrid pipeline, 1k queries, sequential and in batches of 64), `c3`
 (256 queries x 1M ragged passages: tensor roofline), `c1` (rerank of 50 candidates: latency), `ragged` (single
-query over the C3 corpus) and, with N>1, `c5` (10M passages x 128 tokens split over the ranks), a `parity_check`
-of the merged top-k over real NCCL and the `breakdown` of a sharded step.
+query over the C3 corpus) and, with N>1, `c5` (10M passages x 128 tokens split over the ranks), `c4_sharded` (the
+hybrid pipeline over that corpus), `pipelined`, a `parity_check` of the merged top-k over the real interconnect and
+the `breakdown` of a sharded step.
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the same path.
 """
