@@ -1201,12 +1201,23 @@ int launch_dm(const void* d_tokens, const void* d_queries, int lq, int n_real_qu
   // caller's workspace holds the claim counter and a CTA's share is long enough for the SMs' speed spread to matter
   p.n_units = p.n_segments;
   p.static_tokens = p.total_tokens;
-  if (p.unit_counter != nullptr && p.total_tokens >= int64_t(p.n_segments) * kDmDynMinTokensPerCta) {
-    int share = kDmSharedShare, per_cta = kDmSharedPerCta;
+  int share = kDmSharedShare, per_cta = kDmSharedPerCta;
+  // A unit is cut into four streams of WHOLE documents: a shared unit must hold >= 16 average documents or its streams
+  // are badly balanced, and there must be >= 8 shared units per CTA or the last one to be claimed IS the new tail
+  // (32k documents of 4,000 tokens: one 27-document shared unit per CTA made the kernel 8 % slower than equal
+  // ranges, profiles/r02_logs/r02_ab_dynamic_units_long.log) — long documents keep the static distribution.
+  const int64_t mean_len = p.total_tokens / (p.n_docs > 0 ? p.n_docs : 1) + 1;
+  const int64_t fit = (p.total_tokens / share / p.n_segments) / (16 * mean_len);
+  if (fit < per_cta) per_cta = int(fit);
+  bool dynamic = p.unit_counter != nullptr && p.total_tokens >= int64_t(p.n_segments) * kDmDynMinTokensPerCta && per_cta >= 8;
 #ifdef HRC_EXPERIMENTS
-    if (g_exp_dyn_share > 0) share = g_exp_dyn_share;
-    if (g_exp_dyn_per_cta > 0) per_cta = g_exp_dyn_per_cta;
+  if (g_exp_dyn_share > 0 && g_exp_dyn_per_cta > 0 && p.unit_counter != nullptr) {
+    share = g_exp_dyn_share;
+    per_cta = g_exp_dyn_per_cta;
+    dynamic = true;
+  }
 #endif
+  if (dynamic) {
     p.n_units = p.n_segments * (1 + per_cta);
     p.static_tokens = p.total_tokens - p.total_tokens / share;
     HRC_CHECK_CUDA(cudaMemsetAsync(p.unit_counter, 0, sizeof(uint32_t), stream));

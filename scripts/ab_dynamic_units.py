@@ -4,7 +4,7 @@ counter -> static) against own + shared units claimed at run time (256-byte work
 (hrc_maxsim_scores, HRC_PATH_TC_DM), alternating, at burst (20 launches after an idle second) and sustained (3 s back
 to back, second half); kernel time from hrc_trace.
 
-    python scripts/ab_dynamic_units.py [c2|ragged]
+    python scripts/ab_dynamic_units.py [c2|ragged|long]
 """
 import json
 import os
@@ -22,7 +22,9 @@ from hybrid_rag_colbertv2_b200.synth import synth_queries, synth_store  # noqa: 
 dev = torch.device("cuda:0")
 lib = L.load()
 which = sys.argv[1] if len(sys.argv) > 1 else "c2"
-store = synth_store(1_000_000, 128, 128, seed=20260102, device=dev) if which == "c2" else synth_store(1_000_000, 32, 512, seed=20260103, device=dev)
+store = (synth_store(1_000_000, 128, 128, seed=20260102, device=dev) if which == "c2" else
+         synth_store(32_000, 3000, 5000, seed=20260104, device=dev) if which == "long" else      # 4,000-token documents
+         synth_store(1_000_000, 32, 512, seed=20260103, device=dev))
 q = synth_queries(1, 32, device=dev)
 out = torch.empty((1, store.n_docs), dtype=torch.float32, device=dev)
 ws = torch.zeros(256, dtype=torch.uint8, device=dev)
@@ -60,7 +62,7 @@ def run(dynamic, seconds):
     return {"kernel_ms_mean": round(sum(half) / len(half), 3), "kernel_ms_median": round(statistics.median(half), 3)}
 
 
-for rnd in range(3):
+for rnd in range(int(sys.argv[2]) if len(sys.argv) > 2 else 3):
     for dynamic in (False, True):
         time.sleep(1.0)
         burst = run(dynamic, 0.0)

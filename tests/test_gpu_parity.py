@@ -737,28 +737,36 @@ def test_decisive_token_at_every_chunk_and_tile_boundary(cuda_dev, nq, path):
 
 @pytest.mark.parametrize("path", ["tc_dm", "auto"])
 def test_boundary_suite_through_the_dynamic_work_units(cuda_dev, path):
-    """The doc-major kernel hands a quarter of a large corpus out in small shared units claimed at run time (which CTA
-    scores which documents then differs from launch to launch).  The boundary corpus, repeated until the dynamic route
-    engages (>= 4096 tokens per CTA), must still match the oracle on every document, 5 launches in a row bit for bit,
-    through the score matrix AND through the fused top-k search."""
+    """The doc-major kernel hands the last eighth of a large corpus out in small shared units claimed at run time (which
+    CTA scores which documents then differs from launch to launch).  The boundary corpus, repeated (on the device) until
+    the dynamic route engages, must still match the oracle on every document — the oracle's scores of the base corpus,
+    tiled — 5 launches in a row bit for bit, through the score matrix AND through the fused top-k search, and must equal
+    the static distribution (no workspace -> no claim counter) bit for bit."""
     L = _lib()
     q, tok, off, planted = _boundary_corpus(1, 32)
-    reps = int(148 * 4096 * 1.3 / int(off[-1])) + 1
-    tok_r = tok.repeat(reps, 1)
+    # the dynamic route needs >= 8 shared units of >= 16 average documents per CTA in the last eighth of the corpus
+    mean_len = int(off[-1]) // (off.numel() - 1) + 1
+    need = 148 * 8 * (8 * 16 * mean_len)
+    reps = int(need * 1.25 / int(off[-1])) + 1
+    tok_d = tok.to(cuda_dev).repeat(reps, 1)
     off_r = torch.cat([off[:1]] + [off[1:] + r * int(off[-1]) for r in range(reps)])
-    assert int(off_r[-1]) >= 148 * 4096
-    tok_d, off_d, q_d = tok_r.to(cuda_dev), off_r.to(cuda_dev), q.to(cuda_dev)
-    exp = o.maxsim_scores(q.float(), tok_r.float(), off_r)
+    assert int(off_r[-1]) >= need and tok_d.shape[0] == int(off_r[-1])
+    off_d, q_d = off_r.to(cuda_dev), q.to(cuda_dev)
+    exp = o.maxsim_scores(q.float(), tok.float(), off).repeat(1, reps)
     first = None
     for _ in range(5):
         got = L.maxsim_scores(tok_d, off_d, q_d, path=_path(L, path))
-        _assert_scores(got, exp, f"dynamic units {path}", bucket="boundary")
         keys = L.search(tok_d, off_d, q_d, 100, path=_path(L, path))[0]
         if first is None:
+            _assert_scores(got, exp, f"dynamic units {path}", bucket="boundary")
             first = (got.clone(), keys.clone())
         assert torch.equal(got, first[0]) and torch.equal(keys, first[1]), "results differ between launches"
-    want = L.topk(first[0], 100)
-    assert torch.equal(first[1], want), "fused search over dynamic units != top-k of the score matrix"
+    assert torch.equal(first[1], L.topk(first[0], 100)), "fused search over dynamic units != top-k of the score matrix"
+    static = torch.empty_like(first[0])
+    rc = L.load().hrc_maxsim_scores(tok_d.data_ptr(), off_d.data_ptr(), off_d.numel() - 1, tok_d.shape[0], q_d.data_ptr(), 1, 32,
+                                    static.data_ptr(), _path(L, path), None, 0, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    assert torch.equal(static, first[0]), "dynamic and static distributions differ"
 
 
 @pytest.mark.parametrize("path", ["tc", "simt", "tc_dm"])
