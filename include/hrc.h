@@ -108,8 +108,11 @@ int hrc_store_validate(const void* d_tokens, const int64_t* d_offsets, int64_t n
  *               kernel for ONE query of <= 32 tokens, the query-major kernels otherwise (a query longer than 32 tokens
  *               is scored as ceil(lq / 32) slots whose partial scores are summed in slot order) — and the CUDA cores
  *               beyond.  All tensor-core organisations return bit-identical scores.
- *   d_workspace : hrc_maxsim_workspace_bytes(n_docs, n_queries, lq) bytes of scratch (0 bytes, and NULL allowed, when
- *               lq <= 32): the per-slot partial scores of long queries.  No call allocates device memory.
+ *   d_workspace : hrc_maxsim_workspace_bytes(n_docs, n_queries, lq) bytes of scratch: the per-slot partial scores of
+ *               queries longer than 32 tokens (required), or — for ONE query of <= 32 tokens — 256 bytes holding the
+ *               doc-major kernel's claim counter (OPTIONAL: NULL / 0 is accepted and selects equal token ranges per
+ *               CTA instead of run-time work units; same scores, ~2 % slower on large corpora of short documents);
+ *               0 bytes otherwise.  No call allocates device memory.
  * An empty document (length 0) scores -inf.
  */
 size_t hrc_maxsim_workspace_bytes(int64_t n_items, int n_queries, int lq);
