@@ -1165,7 +1165,10 @@ def test_sharded_entry_points_on_a_one_rank_communicator(cuda_dev):
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
-    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1, device_id=cuda_dev)
+    try:
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1, device_id=cuda_dev)
+    except Exception as exc:  # noqa: BLE001  (torch's own rendezvous, not the library under test)
+        pytest.skip(f"cannot create a one-rank torch.distributed group here: {exc!r}")
     try:
         q, tok, off = _case(61, 40_000, 8, 200, 5, 32)
         cfg = hrc.RAGConfig(device=str(cuda_dev), colbert_top_k=100, rerank_candidates=50, final_top_k=10)
