@@ -752,6 +752,30 @@ def sharded_breakdown(torch, dist, hrc, _lib, retr, searcher, queries, dev, max_
         out[name] = max_over_ranks(e0.elapsed_time(e1)) / 20 * 1e3
     out["overhead_us"] = out[f"exchange_merge_{searcher.transport}_us"]
     out["transport"] = searcher.transport
+    # what the exchange adds to a whole search, seen where the search itself is short (4,000 passages per rank): the
+    # difference of two ~60 us numbers instead of two ~4,500 us ones
+    from hybrid_rag_colbertv2_b200.synth import synth_store
+    world, rank = dist.get_world_size(), dist.get_rank()
+    small = hrc.JinaColBERTRetriever(retr.config)
+    small.store = synth_store(4000 * world, DOC_LEN, DOC_LEN, seed=SEED + 21, device=dev, rank=rank, world_size=world)
+    small_searcher = hrc.ShardedSearcher(small, transport=searcher.transport)
+    small_parts = {"local": lambda: small.search_keys(q, K), "sharded": lambda: small_searcher.search_keys(q, K)}
+    small_us = {}
+    for name, fn in small_parts.items():
+        for _ in range(10):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(200):
+            fn()
+        e1.record()
+        barrier()
+        small_us[name] = max_over_ranks(e0.elapsed_time(e1)) / 200 * 1e3
+    out["small_shard"] = {"what": f"4,000 passages per rank, transport {searcher.transport}, 200 searches back to back",
+                          "local_search_us": small_us["local"], "sharded_search_us": small_us["sharded"],
+                          "exchange_overhead_us": small_us["sharded"] - small_us["local"]}
+    small_searcher.close()
     out["note"] = ("each part timed alone, 20 reps back to back; exchange = k x 8 bytes per rank; nccl = ncclAllGather + merge "
                    "kernel, p2p = push kernel (peer stores + release flag) + merge kernel (acquires the flags), both inside libhrc; "
                    "step_p2p_us is the whole sharded search with the exchange FUSED into the search's final selection kernel "
