@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--rounds", type=int, default=12)
     ap.add_argument("--launches", type=int, default=10)
     ap.add_argument("--docs", type=int, default=0)
+    ap.add_argument("--sleep", type=float, default=0.0, help="idle seconds before every measurement (burst clocks instead of the power cap)")
     ap.add_argument("--path", type=int, default=0, help="HRC_PATH_* selector passed to every library (0 auto, 2 query-major, 3 doc-major)")
     ap.add_argument("libs", nargs="+")
     a = ap.parse_args()
@@ -53,16 +54,24 @@ def main():
                 out.data_ptr(), a.path, ws.data_ptr(), ws.numel(), stream)
         assert rc == 0, rc
 
+    first = None
     for fn, env in zip(fns, envs):
         for _ in range(3):
             launch(fn, env)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        if first is None:
+            first = out.clone()
+        assert torch.equal(out, first), "the libraries disagree on the scores"
     times = [[] for _ in fns]
     for r in range(a.rounds):
         order = list(range(len(fns)))
         if r % 2:
             order.reverse()
         for i in order:
+            if a.sleep > 0:
+                import time
+                time.sleep(a.sleep)
+                launch(fns[i], envs[i])
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(a.launches):
