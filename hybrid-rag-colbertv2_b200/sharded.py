@@ -55,9 +55,13 @@ class PendingKeys:
 
 
 class ShardedSearcher:
-    """search / hybrid retrieve over a corpus sharded across the ranks of a torch.distributed group (one rank per GPU)."""
+    """search / hybrid retrieve over a corpus sharded across the ranks of a torch.distributed group (one rank per GPU).
 
-    def __init__(self, retriever: JinaColBERTRetriever, group=None, transport: str = "nccl", p2p_max_keys: int = 1 << 16):
+    transport: "auto" (default: the exchange runs over peer memory inside libhrc when every rank can map its peers, else
+    over ncclAllGather inside libhrc), "p2p", "nccl", or "torch" (torch.distributed collectives; the only one that works
+    without CUDA, used by the CPU tests and as the cross-check)."""
+
+    def __init__(self, retriever: JinaColBERTRetriever, group=None, transport: str = "auto", p2p_max_keys: int = 1 << 16):
         if transport not in ("auto", "nccl", "p2p", "torch"):
             raise ValueError(f"transport must be 'auto', 'nccl', 'p2p' or 'torch', got {transport!r}")
         self.retriever = retriever          # holds THIS rank's shard; store.doc_id_base makes ids global
